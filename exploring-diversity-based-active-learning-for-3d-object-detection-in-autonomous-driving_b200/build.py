@@ -1,0 +1,40 @@
+"""In-tree build of the CUDA library (sm_100a only) -- ``libadsel_b200.so`` next to the sources.
+
+The built ``.so`` is git-ignored but travels with the tree to the GPU box.  No JIT cache, no torch
+extension machinery: the library has a plain C ABI (include/adsel_b200.h) and is bound with ctypes.
+"""
+import os
+import subprocess
+
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB = os.path.join(CSRC, "libadsel_b200.so")
+SOURCES = ["api.cu", "knn_graph.cu", "geodesic.cu", "greedy.cu", "dense.cu", "bev.cu", "pairdist.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = _sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(os.path.dirname(CSRC), "..", "include", "adsel_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu for sm_100a into one shared library; returns its path."""
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources() + ["-lcuda"]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

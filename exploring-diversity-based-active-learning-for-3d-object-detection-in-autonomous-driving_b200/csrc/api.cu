@@ -1,0 +1,215 @@
+// api.cu -- extern "C" surface of libadsel_b200.so (include/adsel_b200.h).
+#include <vector>
+
+#include "common.cuh"
+
+namespace adsel {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int begin_stage(adsel_handle *h) {
+    ADSEL_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    return ADSEL_OK;
+}
+int end_stage(adsel_handle *h, int stage) {
+    ADSEL_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    ADSEL_CUDA(cudaEventSynchronize(h->ev[1]));
+    float ms = 0.f;
+    ADSEL_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->stage_ms[stage] = ms;
+    return ADSEL_OK;
+}
+
+int build_knn_graph(adsel_handle *h, int32_t k);
+int geodesic_rows(adsel_handle *h, const int32_t *sources, int32_t m, double radius, double *out_host);
+int geodesic_max_finite(adsel_handle *h, double *out);
+int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
+                  int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
+
+__global__ void exp_f64_kernel(const double *__restrict__ x, long long n, double *__restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = np_exp_f64(x[i]);
+}
+
+}  // namespace adsel
+
+using namespace adsel;
+
+extern "C" {
+
+const char *adsel_version(void) { return "adsel_b200 0.1.0 (sm_100a)"; }
+const char *adsel_last_error(void) { return g_last_error.c_str(); }
+
+int adsel_device_count(int *count) {
+    ADSEL_REQUIRE(count, "adsel_device_count: null argument");
+    ADSEL_CUDA(cudaGetDeviceCount(count));
+    return ADSEL_OK;
+}
+
+int adsel_create(int device, adsel_handle **out) {
+    ADSEL_REQUIRE(out, "adsel_create: null argument");
+    int count = 0;
+    ADSEL_CUDA(cudaGetDeviceCount(&count));
+    ADSEL_REQUIRE(device >= 0 && device < count, "adsel_create: no such CUDA device (this library has no CPU fallback)");
+    ADSEL_CUDA(cudaSetDevice(device));
+    adsel_handle *h = new adsel_handle();
+    h->device = device;
+    ADSEL_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+    ADSEL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    ADSEL_CUDA(cudaEventCreate(&h->ev[0]));
+    ADSEL_CUDA(cudaEventCreate(&h->ev[1]));
+    *out = h;
+    return ADSEL_OK;
+}
+
+int adsel_destroy(adsel_handle *h) {
+    if (!h) return ADSEL_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->loc.release(); h->group_id.release(); h->n_boxes.release(); h->group_ptr.release(); h->group_members.release();
+    h->knn_idx.release(); h->knn_dist.release(); h->row_ptr.release(); h->col.release(); h->deg_own.release();
+    h->deg_rev.release(); h->w.release();
+    h->sc_dist.release(); h->sc_stamp.release(); h->sc_q0.release(); h->sc_q1.release(); h->sc_touched.release();
+    h->list_off.release(); h->list_len.release(); h->list_idx.release(); h->list_val.release(); h->cursor.release();
+    h->fps.release(); h->blk_val.release(); h->blk_idx.release(); h->is_selected.release(); h->tlut.release();
+    h->d_sampled.release(); h->d_out.release(); h->d_result.release();
+    cudaEventDestroy(h->ev[0]);
+    cudaEventDestroy(h->ev[1]);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return ADSEL_OK;
+}
+
+int adsel_get_stream(adsel_handle *h, void **stream) {
+    ADSEL_REQUIRE(h && stream, "adsel_get_stream: null argument");
+    *stream = (void *)h->stream;
+    return ADSEL_OK;
+}
+
+int adsel_synchronize(adsel_handle *h) {
+    ADSEL_REQUIRE(h, "adsel_synchronize: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    return ADSEL_OK;
+}
+
+int adsel_set_pool(adsel_handle *h, int32_t n, const double *loc_xy, const int32_t *group_id, const int32_t *n_boxes) {
+    ADSEL_REQUIRE(h && n > 0 && loc_xy && group_id && n_boxes, "adsel_set_pool: null/empty argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    int32_t n_groups = 0;
+    for (int i = 0; i < n; ++i) {
+        ADSEL_REQUIRE(group_id[i] >= 0, "adsel_set_pool: negative group id");
+        ADSEL_REQUIRE(n_boxes[i] >= 0, "adsel_set_pool: negative box count");
+        if (group_id[i] + 1 > n_groups) n_groups = group_id[i] + 1;
+    }
+    // frames by group, ascending index inside a group (counting sort)
+    std::vector<int32_t> ptr(n_groups + 1, 0), members(n);
+    for (int i = 0; i < n; ++i) ptr[group_id[i] + 1]++;
+    for (int g = 0; g < n_groups; ++g) ptr[g + 1] += ptr[g];
+    {
+        std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+        for (int i = 0; i < n; ++i) members[fill[group_id[i]]++] = i;
+    }
+    h->n = n;
+    h->n_groups = n_groups;
+    h->graph_ready = false;
+    h->lists_mode = -1;
+    ADSEL_TRY(h->loc.reserve(n));
+    ADSEL_TRY(h->group_id.reserve(n));
+    ADSEL_TRY(h->n_boxes.reserve(n));
+    ADSEL_TRY(h->group_ptr.reserve(n_groups + 1));
+    ADSEL_TRY(h->group_members.reserve(n));
+    ADSEL_CUDA(cudaMemcpyAsync(h->loc.p, loc_xy, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    ADSEL_CUDA(cudaMemcpyAsync(h->group_id.p, group_id, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    ADSEL_CUDA(cudaMemcpyAsync(h->n_boxes.p, n_boxes, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    ADSEL_CUDA(cudaMemcpyAsync(h->group_ptr.p, ptr.data(), sizeof(int32_t) * (n_groups + 1), cudaMemcpyHostToDevice, h->stream));
+    ADSEL_CUDA(cudaMemcpyAsync(h->group_members.p, members.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
+    return ADSEL_OK;
+}
+
+int adsel_build_knn_graph(adsel_handle *h, int32_t k) {
+    ADSEL_REQUIRE(h, "adsel_build_knn_graph: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return build_knn_graph(h, k);
+}
+
+int adsel_get_knn(adsel_handle *h, int32_t *knn_idx, double *knn_dist) {
+    ADSEL_REQUIRE(h && h->graph_ready && knn_idx && knn_dist, "adsel_get_knn: graph not built / null argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    const size_t cells = (size_t)h->n * (h->k + 1);
+    ADSEL_CUDA(cudaMemcpy(knn_idx, h->knn_idx.p, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost));
+    ADSEL_CUDA(cudaMemcpy(knn_dist, h->knn_dist.p, sizeof(double) * cells, cudaMemcpyDeviceToHost));
+    return ADSEL_OK;
+}
+
+int adsel_get_csr(adsel_handle *h, int32_t *row_ptr, int32_t *col, double *w, int64_t *nnz) {
+    ADSEL_REQUIRE(h && h->graph_ready && nnz, "adsel_get_csr: graph not built / null argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    *nnz = h->nnz;
+    if (row_ptr) ADSEL_CUDA(cudaMemcpy(row_ptr, h->row_ptr.p, sizeof(int32_t) * (h->n + 1), cudaMemcpyDeviceToHost));
+    if (col) ADSEL_CUDA(cudaMemcpy(col, h->col.p, sizeof(int32_t) * h->nnz, cudaMemcpyDeviceToHost));
+    if (w) ADSEL_CUDA(cudaMemcpy(w, h->w.p, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost));
+    return ADSEL_OK;
+}
+
+int adsel_geodesic_rows(adsel_handle *h, const int32_t *sources, int32_t m, double radius, double *out) {
+    ADSEL_REQUIRE(h, "adsel_geodesic_rows: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return geodesic_rows(h, sources, m, radius, out);
+}
+
+int adsel_geodesic_max_finite(adsel_handle *h, double *out) {
+    ADSEL_REQUIRE(h && out, "adsel_geodesic_max_finite: null argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return geodesic_max_finite(h, out);
+}
+
+int adsel_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
+                 int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {
+    ADSEL_REQUIRE(h, "adsel_select: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return greedy_select(h, p, sampled, n_sampled, first_index, out_idx, out_cap, out_m, out_cost);
+}
+
+int adsel_get_fps(adsel_handle *h, double *fps) {
+    ADSEL_REQUIRE(h && fps && h->fps.p, "adsel_get_fps: no selection has run");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    ADSEL_CUDA(cudaMemcpy(fps, h->fps.p, sizeof(double) * h->n, cudaMemcpyDeviceToHost));
+    return ADSEL_OK;
+}
+
+int adsel_get_stage_ms(adsel_handle *h, float *ms5) {
+    ADSEL_REQUIRE(h && ms5, "adsel_get_stage_ms: null argument");
+    memcpy(ms5, h->stage_ms, sizeof(h->stage_ms));
+    return ADSEL_OK;
+}
+
+int adsel_get_counters(adsel_handle *h, int64_t *c4) {
+    ADSEL_REQUIRE(h && c4, "adsel_get_counters: null argument");
+    c4[0] = h->launches;
+    c4[1] = h->last_steps;
+    c4[2] = h->list_total;
+    c4[3] = h->nnz;
+    return ADSEL_OK;
+}
+
+int adsel_exp_f64(adsel_handle *h, const double *x, int64_t n, double *out) {
+    ADSEL_REQUIRE(h && x && out && n > 0, "adsel_exp_f64: null/empty argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    double *dx = nullptr, *dy = nullptr;
+    ADSEL_CUDA(cudaMalloc(&dx, sizeof(double) * n));
+    ADSEL_CUDA(cudaMalloc(&dy, sizeof(double) * n));
+    ADSEL_CUDA(cudaMemcpyAsync(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    exp_f64_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(dx, n, dy);
+    h->launches += 1;
+    ADSEL_CUDA(cudaGetLastError());
+    ADSEL_CUDA(cudaMemcpyAsync(out, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(dx);
+    cudaFree(dy);
+    return ADSEL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// common.cuh -- shared declarations of the sm_100a selection library (see include/adsel_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <limits>
+#include <string>
+
+#include "../../include/adsel_b200.h"
+
+namespace adsel {
+
+void set_error(const std::string &msg);
+
+#define ADSEL_CUDA(expr)                                                                        \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            adsel::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +        \
+                             __FILE__ + ":" + std::to_string(__LINE__) + ")");                  \
+            return ADSEL_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+#define ADSEL_REQUIRE(cond, msg)                                                                \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            adsel::set_error(std::string(msg));                                                 \
+            return ADSEL_ERR_INVALID;                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define ADSEL_TRY(expr)                                                                         \
+    do {                                                                                        \
+        int _s = (expr);                                                                        \
+        if (_s != ADSEL_OK) return _s;                                                          \
+    } while (0)
+
+constexpr unsigned long long INF_BITS = 0x7ff0000000000000ull;   // +inf as an ordered u64 key
+constexpr double TEMPORAL_MARGIN = 1e6;                            // spatial_temporal_selector.py:112
+constexpr double NULL_EDGE_ATOL = 1e-8;                            // scipy csgraph_from_dense / masked_values
+
+// Device buffer with explicit capacity (grown geometrically; never shrinks).
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return ADSEL_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        ADSEL_CUDA(cudaMalloc(&p, n * sizeof(T)));
+        cap = n;
+        return ADSEL_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace adsel
+
+struct adsel_handle {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    float stage_ms[5] = {0, 0, 0, 0, 0};
+    int64_t launches = 0, last_steps = 0;
+
+    // pool
+    int32_t n = 0;
+    adsel::DevBuf<double2> loc;
+    adsel::DevBuf<int32_t> group_id, n_boxes;
+    adsel::DevBuf<int32_t> group_ptr, group_members;   // CSR of frames by group (ascending index)
+    int32_t n_groups = 0;
+
+    // kNN + CSR graph
+    int32_t k = 0;
+    adsel::DevBuf<int32_t> knn_idx;
+    adsel::DevBuf<double> knn_dist;
+    adsel::DevBuf<int32_t> row_ptr, col, deg_own, deg_rev;
+    adsel::DevBuf<double> w;
+    int64_t nnz = 0;
+    bool graph_ready = false;
+
+    // SSSP scratch (per resident CTA)
+    int32_t sssp_ctas = 0;
+    adsel::DevBuf<unsigned long long> sc_dist;
+    adsel::DevBuf<int32_t> sc_stamp, sc_q0, sc_q1, sc_touched;
+    size_t sc_n = 0;
+
+    // neighbour lists (truncated geodesic neighbourhood of every frame, normalised)
+    adsel::DevBuf<int64_t> list_off;
+    adsel::DevBuf<int32_t> list_len, list_idx;
+    adsel::DevBuf<double> list_val;
+    adsel::DevBuf<unsigned long long> cursor;   // [0] entries reserved, [1] max finite bits
+    int64_t list_total = 0;
+    int lists_mode = -1;                         // normalize mode the lists were built for
+    double lists_max_spatial = 0.0;
+
+    // greedy state
+    adsel::DevBuf<unsigned long long> fps;       // ordered-u64 view of non-negative doubles
+    adsel::DevBuf<unsigned long long> blk_val;
+    adsel::DevBuf<int32_t> blk_idx;
+    adsel::DevBuf<unsigned char> is_selected;
+    adsel::DevBuf<double> tlut;
+    adsel::DevBuf<int32_t> d_sampled, d_out;
+    adsel::DevBuf<double> d_result;              // [0] cost, [1] status, [2] m, [3] steps
+};
+
+namespace adsel {
+
+static inline double host_inf() { return std::numeric_limits<double>::infinity(); }
+int begin_stage(adsel_handle *h);
+int end_stage(adsel_handle *h, int stage);
+
+// ---------------------------------------------------------------------------------------------
+// numpy float64 exp on AVX512_SKX hosts == Intel SVML __svml_exp8_ha main path (oracle/npexp.c
+// documents how the sequence and the constants were obtained).  Bit-exact by construction: the
+// same IEEE operations in the same order (one round-toward-zero FMA, then round-to-nearest FMAs).
+// ---------------------------------------------------------------------------------------------
+static __device__ __constant__ unsigned long long EXP_TH[16] = {
+    0x3ff0000000000000ull, 0x3ff0b5586cf9890full, 0x3ff172b83c7d517bull, 0x3ff2387a6e756238ull,
+    0x3ff306fe0a31b715ull, 0x3ff3dea64c123422ull, 0x3ff4bfdad5362a27ull, 0x3ff5ab07dd485429ull,
+    0x3ff6a09e667f3bcdull, 0x3ff7a11473eb0187ull, 0x3ff8ace5422aa0dbull, 0x3ff9c49182a3f090ull,
+    0x3ffae89f995ad3adull, 0x3ffc199bdd85529cull, 0x3ffd5818dcfba487ull, 0x3ffea4afa2a490daull};
+static __device__ __constant__ unsigned long long EXP_TL[16] = {
+    0x0000000000000000ull, 0x3c979aa65d837b6dull, 0xbc801b15eaa59348ull, 0x3c968efde3a8a894ull,
+    0x3c834d754db0abb6ull, 0x3c859f48a72a4c6dull, 0x3c7690cebb7aafb0ull, 0x3c9063e1e21c5409ull,
+    0xbc93b3efbf5e2228ull, 0xbc7b32dcb94da51dull, 0x3c8db72fc1f0eab4ull, 0x3c71affc2b91ce27ull,
+    0x3c8c1a7792cb3387ull, 0x3c736eae30af0cb3ull, 0x3c74a385a63d07a7ull, 0xbc8ff7128fd391f0ull};
+
+__device__ __forceinline__ double np_exp_f64(double x) {
+    const double L2E = 0x1.71547652b82fep+0, SHIFTER = 0x1.8000000003ff0p+48;
+    const double L2H = 0x1.62e42fefa39efp-1, L2L = 0x1.abc9e3b39803fp-56;
+    const double C6 = 0x1.7411836940c04p-10, C5 = 0x1.1101cbbc265c0p-7, C4 = 0x1.55557242d68fep-5,
+                 C3 = 0x1.5555553939732p-3, C2 = 0x1.000000000d008p-1, C1 = 0x1.fffffffffff70p-1;
+    if (!(fabs(x) < 0x1.61da04cbafe44p+9)) return exp(x);   // SVML's scalar rare path: not bit-pinned
+    const double z = __fma_rz(x, L2E, SHIFTER);
+    const double N = __dsub_rn(z, SHIFTER);
+    const unsigned j = (unsigned)(__double_as_longlong(z) & 0xf);
+    double r = __fma_rn(-N, L2H, x);
+    r = __fma_rn(-L2L, N, r);
+    const double r2 = __dmul_rn(r, r);
+    const double p65 = __fma_rn(C6, r, C5);
+    const double p43 = __fma_rn(C4, r, C3);
+    const double p21 = __fma_rn(C2, r, C1);
+    double P = __fma_rn(r2, p65, p43);
+    P = __fma_rn(r2, P, p21);
+    const double th = __longlong_as_double(EXP_TH[j]), tl = __longlong_as_double(EXP_TL[j]);
+    double y = __fma_rn(P, r, tl);
+    y = __fma_rn(th, y, th);
+    return ldexp(y, (int)floor(N));
+}
+
+// Normalisation of one raw distance d >= 0 (spatial_temporal_selector.py:138-146).
+__device__ __forceinline__ double normalize_value(double d, int mode, double divisor) {
+    if (mode == ADSEL_NORM_EXP) return __dsub_rn(1.0, np_exp_f64(-d));
+    if (mode == ADSEL_NORM_LINEAR) return __ddiv_rn(d, divisor);
+    return d;
+}
+
+// Aggregate spatial s and temporal t (spatial_temporal_selector.py:148-155): sum is
+// s + lambda_t*t as a rounded multiply followed by a rounded add (numpy evaluates it unfused).
+__device__ __forceinline__ double aggregate_value(double s, double t, int agg, double lambda_t) {
+    if (agg == ADSEL_AGG_SUM) return __dadd_rn(s, __dmul_rn(lambda_t, t));
+    if (agg == ADSEL_AGG_MIN) return fmin(s, t);
+    return fmax(s, t);
+}
+
+}  // namespace adsel

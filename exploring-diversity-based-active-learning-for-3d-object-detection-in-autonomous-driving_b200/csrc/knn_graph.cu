@@ -1,0 +1,255 @@
+// knn_graph.cu -- exact float64 kNN over the ego locations and the symmetrised CSR graph that
+// scipy's Dijkstra walks in the reference (det3d/selectors/spatial_temporal_selector.py:93-104).
+//
+//   knn_bruteforce_kernel   replaces cKDTree(locations).query(locations, k+1)          (:97-98)
+//   count/fill edge kernels replace the symmetric dense scatter (:99-101) followed by scipy's
+//                           dense->CSR conversion, which drops entries with |w| <= 1e-8.
+//
+// Arithmetic contract (bit-exact with scipy): d2 = dx*dx + dy*dy with separately
+// rounded products (no FMA), neighbours ordered by (d2, index), reported distance sqrt(d2).
+#include "common.cuh"
+
+namespace adsel {
+
+constexpr int KNN_THREADS = 128;
+constexpr int KNN_TILE = 1024;   // candidates staged per shared-memory tile (16 KB)
+
+// One query per thread; candidates stream through shared memory as double2 (broadcast reads).
+// Each thread keeps its K1 = k+1 best (d2, idx) sorted ascending in registers.
+// SPLIT > 1: SPLIT consecutive threads share one query and scan interleaved candidate tiles; their
+// partial lists are merged through shared memory (used when n is too small to fill the GPU).
+template <int K1>
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_bruteforce_kernel(const double2 *__restrict__ loc, int n, int32_t *__restrict__ out_idx,
+                      double *__restrict__ out_dist) {
+    __shared__ double2 tile[KNN_TILE];
+    const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
+    const double2 me = loc[q < n ? q : n - 1];
+    double best_d[K1];
+    int best_i[K1];
+#pragma unroll
+    for (int s = 0; s < K1; ++s) {
+        best_d[s] = __longlong_as_double(INF_BITS);
+        best_i[s] = -1;
+    }
+    for (int base = 0; base < n; base += KNN_TILE) {
+        const int cnt = min(KNN_TILE, n - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += KNN_THREADS) tile[t] = loc[base + t];
+        __syncthreads();
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+            const double2 c = tile[t];
+            const double dx = __dsub_rn(me.x, c.x), dy = __dsub_rn(me.y, c.y);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            // candidates arrive in ascending index: strict '<' keeps the lower index on ties
+            if (d2 < best_d[K1 - 1]) {
+                double cd = d2;
+                int ci = base + t;
+#pragma unroll
+                for (int s = 0; s < K1; ++s) {
+                    if (cd < best_d[s]) {
+                        const double td = best_d[s];
+                        const int ti = best_i[s];
+                        best_d[s] = cd;
+                        best_i[s] = ci;
+                        cd = td;
+                        ci = ti;
+                    }
+                }
+            }
+        }
+    }
+    if (q < n) {
+#pragma unroll
+        for (int s = 0; s < K1; ++s) {
+            out_idx[(size_t)q * K1 + s] = best_i[s];
+            out_dist[(size_t)q * K1 + s] = __dsqrt_rn(best_d[s]);
+        }
+    }
+}
+
+// Generic k (K1 up to 64) with the running list in local memory; same ordering contract.
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_bruteforce_generic_kernel(const double2 *__restrict__ loc, int n, int k1, int32_t *__restrict__ out_idx,
+                              double *__restrict__ out_dist) {
+    __shared__ double2 tile[KNN_TILE];
+    const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
+    const double2 me = loc[q < n ? q : n - 1];
+    double best_d[64];
+    int best_i[64];
+    for (int s = 0; s < k1; ++s) {
+        best_d[s] = __longlong_as_double(INF_BITS);
+        best_i[s] = -1;
+    }
+    for (int base = 0; base < n; base += KNN_TILE) {
+        const int cnt = min(KNN_TILE, n - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += KNN_THREADS) tile[t] = loc[base + t];
+        __syncthreads();
+        for (int t = 0; t < cnt; ++t) {
+            const double2 c = tile[t];
+            const double dx = __dsub_rn(me.x, c.x), dy = __dsub_rn(me.y, c.y);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            if (d2 < best_d[k1 - 1]) {
+                int s = k1 - 1;
+                while (s > 0 && d2 < best_d[s - 1]) {
+                    best_d[s] = best_d[s - 1];
+                    best_i[s] = best_i[s - 1];
+                    --s;
+                }
+                best_d[s] = d2;
+                best_i[s] = base + t;
+            }
+        }
+    }
+    if (q < n) {
+        for (int s = 0; s < k1; ++s) {
+            out_idx[(size_t)q * k1 + s] = best_i[s];
+            out_dist[(size_t)q * k1 + s] = __dsqrt_rn(best_d[s]);
+        }
+    }
+}
+
+// An entry of the kNN table is an edge of the reference's graph unless scipy's dense->CSR
+// conversion masks it: np.isclose(w, 0, rtol=1e-5, atol=1e-8)  <=>  |w| <= 1e-8.
+__device__ __forceinline__ bool is_edge(int nbr, double d) { return nbr >= 0 && !(fabs(d) <= NULL_EDGE_ATOL); }
+
+// deg_own[i] = edges i keeps from its own kNN list; deg_rev[i] = edges (j -> i) whose reverse
+// (i -> j) is not already in i's own list (the dense scatter writes both [i,j] and [j,i]).
+__global__ void count_edges_kernel(const int32_t *__restrict__ knn_idx, const double *__restrict__ knn_dist,
+                                   int n, int k1, int32_t *__restrict__ deg_own, int32_t *__restrict__ deg_rev) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * k1) return;
+    const int j = t / k1;
+    const int i = knn_idx[t];
+    const double d = knn_dist[t];
+    if (!is_edge(i, d)) return;
+    atomicAdd(&deg_own[j], 1);
+    bool mutual = false;
+    for (int s = 0; s < k1; ++s) mutual |= (knn_idx[(size_t)i * k1 + s] == j && is_edge(j, knn_dist[(size_t)i * k1 + s]));
+    if (!mutual) atomicAdd(&deg_rev[i], 1);
+}
+
+// Single-CTA exclusive scan of deg_own + deg_rev -> row_ptr[0..n]; n <= a few 100k so one CTA
+// walking the array in 1024-wide strips is a few microseconds and keeps the build graph-free.
+__global__ void __launch_bounds__(1024)
+scan_degrees_kernel(const int32_t *__restrict__ deg_own, const int32_t *__restrict__ deg_rev, int n,
+                    int32_t *__restrict__ row_ptr) {
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n ? deg_own[i] + deg_rev[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warp_sum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += y;
+            }
+            warp_sum[lane] = ws;
+        }
+        __syncthreads();
+        const int before = carry + (wid > 0 ? warp_sum[wid - 1] : 0) + incl - v;
+        if (i < n) row_ptr[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_ptr[n] = carry;
+}
+
+// Own edges land at row_ptr[j] + (rank among j's valid slots); reverse-only edges after them in
+// arrival order (order inside a row never matters: relaxations take a min).
+__global__ void fill_edges_kernel(const int32_t *__restrict__ knn_idx, const double *__restrict__ knn_dist,
+                                  int n, int k1, const int32_t *__restrict__ row_ptr,
+                                  const int32_t *__restrict__ deg_own, int32_t *__restrict__ rev_fill,
+                                  int32_t *__restrict__ col, double *__restrict__ w) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * k1) return;
+    const int j = t / k1, slot = t - j * k1;
+    const int i = knn_idx[t];
+    const double d = knn_dist[t];
+    if (!is_edge(i, d)) return;
+    int rank = 0;
+    for (int s = 0; s < slot; ++s) rank += is_edge(knn_idx[(size_t)j * k1 + s], knn_dist[(size_t)j * k1 + s]) ? 1 : 0;
+    col[row_ptr[j] + rank] = i;
+    w[row_ptr[j] + rank] = d;
+    bool mutual = false;
+    for (int s = 0; s < k1; ++s) mutual |= (knn_idx[(size_t)i * k1 + s] == j && is_edge(j, knn_dist[(size_t)i * k1 + s]));
+    if (!mutual) {
+        const int pos = row_ptr[i] + deg_own[i] + atomicAdd(&rev_fill[i], 1);
+        col[pos] = j;
+        w[pos] = d;
+    }
+}
+
+template <int K1>
+static void launch_knn(adsel_handle *h) {
+    const int grid = (h->n + KNN_THREADS - 1) / KNN_THREADS;
+    knn_bruteforce_kernel<K1><<<grid, KNN_THREADS, 0, h->stream>>>(h->loc.p, h->n, h->knn_idx.p, h->knn_dist.p);
+}
+
+int build_knn_graph(adsel_handle *h, int32_t k) {
+    ADSEL_REQUIRE(h->n > 0, "adsel_build_knn_graph: call adsel_set_pool first");
+    ADSEL_REQUIRE(k >= 1 && k + 1 <= 64 && k + 1 <= h->n, "adsel_build_knn_graph: need 1 <= k < min(n, 64)");
+    const int n = h->n, k1 = k + 1;
+    h->k = k;
+    h->graph_ready = false;
+    h->lists_mode = -1;
+    ADSEL_TRY(h->knn_idx.reserve((size_t)n * k1));
+    ADSEL_TRY(h->knn_dist.reserve((size_t)n * k1));
+    ADSEL_TRY(h->row_ptr.reserve(n + 1));
+    ADSEL_TRY(h->deg_own.reserve(n));
+    ADSEL_TRY(h->deg_rev.reserve(2 * (size_t)n));   // [0,n) reverse counts, [n,2n) fill cursors
+
+    ADSEL_TRY(begin_stage(h));
+    switch (k1) {
+        case 9: launch_knn<9>(h); break;
+        case 5: launch_knn<5>(h); break;
+        case 17: launch_knn<17>(h); break;
+        default: {
+            const int grid = (n + KNN_THREADS - 1) / KNN_THREADS;
+            knn_bruteforce_generic_kernel<<<grid, KNN_THREADS, 0, h->stream>>>(h->loc.p, n, k1, h->knn_idx.p, h->knn_dist.p);
+        }
+    }
+    h->launches += 1;
+    ADSEL_CUDA(cudaGetLastError());
+    ADSEL_TRY(end_stage(h, 0));
+
+    ADSEL_TRY(begin_stage(h));
+    ADSEL_CUDA(cudaMemsetAsync(h->deg_own.p, 0, sizeof(int32_t) * n, h->stream));
+    ADSEL_CUDA(cudaMemsetAsync(h->deg_rev.p, 0, sizeof(int32_t) * 2 * n, h->stream));
+    const int threads = 256, blocks = (int)(((size_t)n * k1 + threads - 1) / threads);
+    count_edges_kernel<<<blocks, threads, 0, h->stream>>>(h->knn_idx.p, h->knn_dist.p, n, k1, h->deg_own.p, h->deg_rev.p);
+    scan_degrees_kernel<<<1, 1024, 0, h->stream>>>(h->deg_own.p, h->deg_rev.p, n, h->row_ptr.p);
+    h->launches += 2;
+    ADSEL_CUDA(cudaGetLastError());
+    int32_t nnz32 = 0;
+    ADSEL_CUDA(cudaMemcpyAsync(&nnz32, h->row_ptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    h->nnz = nnz32;
+    ADSEL_TRY(h->col.reserve((size_t)nnz32 + 1));
+    ADSEL_TRY(h->w.reserve((size_t)nnz32 + 1));
+    fill_edges_kernel<<<blocks, threads, 0, h->stream>>>(h->knn_idx.p, h->knn_dist.p, n, k1, h->row_ptr.p, h->deg_own.p,
+                                                         h->deg_rev.p + n, h->col.p, h->w.p);
+    h->launches += 1;
+    ADSEL_CUDA(cudaGetLastError());
+    ADSEL_TRY(end_stage(h, 1));
+    h->graph_ready = true;
+    return ADSEL_OK;
+}
+
+}  // namespace adsel

@@ -1,0 +1,213 @@
+"""ctypes binding of the C ABI in include/adsel_b200.h (``csrc/libadsel_b200.so``).
+
+This is the only door to the compute path.  There is no CPU fallback: if the library is missing
+``load()`` raises, and every compute call raises ``NativeError`` when no CUDA device is present.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_RESELECTED = 0, -1, -2, -3, -4
+SPATIAL = {"none": 0, "geodesic": 1, "euclid": 2}
+NORMALIZE = {"raw": 0, "exp": 1, "linear": 2}
+AGGREGATE = {"sum": 0, "min": 1, "max": 2}
+
+
+class NativeError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"adsel_b200 native call failed (status {status}): {message}")
+        self.status = status
+        self.message = message
+
+
+class SelectParams(ctypes.Structure):
+    _fields_ = [
+        ("spatial", ctypes.c_int32), ("temporal", ctypes.c_int32), ("normalize", ctypes.c_int32),
+        ("aggregate", ctypes.c_int32), ("lambda_t", ctypes.c_double), ("max_spatial", ctypes.c_double),
+        ("max_temporal", ctypes.c_double), ("cost_b", ctypes.c_double), ("cost_f", ctypes.c_double),
+        ("cost_start", ctypes.c_double), ("budget", ctypes.c_double), ("forbid_sampled", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+_P = ctypes.c_void_p
+_SIGNATURES = {
+    "adsel_version": (ctypes.c_char_p, []),
+    "adsel_last_error": (ctypes.c_char_p, []),
+    "adsel_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "adsel_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_P)]),
+    "adsel_destroy": (ctypes.c_int, [_P]),
+    "adsel_get_stream": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
+    "adsel_synchronize": (ctypes.c_int, [_P]),
+    "adsel_set_pool": (ctypes.c_int, [_P, ctypes.c_int32, _P, _P, _P]),
+    "adsel_build_knn_graph": (ctypes.c_int, [_P, ctypes.c_int32]),
+    "adsel_get_knn": (ctypes.c_int, [_P, _P, _P]),
+    "adsel_get_csr": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ctypes.c_int64)]),
+    "adsel_geodesic_rows": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_double, _P]),
+    "adsel_geodesic_max_finite": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
+    "adsel_select": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, ctypes.c_int32, ctypes.c_int32, _P,
+                                    ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
+    "adsel_get_fps": (ctypes.c_int, [_P, _P]),
+    "adsel_get_stage_ms": (ctypes.c_int, [_P, _P]),
+    "adsel_get_counters": (ctypes.c_int, [_P, _P]),
+    "adsel_exp_f64": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P]),
+}
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building in-tree if sources are newer) and type the library; raises if unavailable."""
+    global _lib
+    if _lib is None:
+        path = _build.build() if (_build.needs_build() and _nvcc_available()) else _build.LIB
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} is missing and nvcc is not available to build it: the selection hot path has "
+                "no CPU fallback (run __graft_entry__.build())")
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            if hasattr(lib, name):
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _nvcc_available() -> bool:
+    from shutil import which
+    return which(os.environ.get("NVCC", "nvcc")) is not None
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def _check(status):
+    if status != OK:
+        raise NativeError(status, load().adsel_last_error().decode())
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_P) if a is not None else None
+
+
+def device_count() -> int:
+    c = ctypes.c_int(0)
+    _check(load().adsel_device_count(ctypes.byref(c)))
+    return c.value
+
+
+class Handle:
+    """One selection context on one CUDA device (owns all device buffers and a stream)."""
+
+    def __init__(self, device: int = 0):
+        self._h = _P()
+        self.n = 0
+        self.k = 0
+        _check(load().adsel_create(device, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            load().adsel_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- pool / graph ----------------------------------------------------------------------
+    def set_pool(self, loc_xy, group_id, n_boxes):
+        loc_xy = np.ascontiguousarray(loc_xy, dtype=np.float64)
+        group_id = np.ascontiguousarray(group_id, dtype=np.int32)
+        n_boxes = np.ascontiguousarray(n_boxes, dtype=np.int32)
+        assert loc_xy.ndim == 2 and loc_xy.shape[1] == 2 and len(group_id) == len(loc_xy) == len(n_boxes)
+        self.n = len(loc_xy)
+        _check(load().adsel_set_pool(self._h, self.n, _ptr(loc_xy), _ptr(group_id), _ptr(n_boxes)))
+
+    def build_knn_graph(self, k: int = 8):
+        self.k = k
+        _check(load().adsel_build_knn_graph(self._h, k))
+
+    def get_knn(self):
+        idx = np.empty((self.n, self.k + 1), dtype=np.int32)
+        dist = np.empty((self.n, self.k + 1), dtype=np.float64)
+        _check(load().adsel_get_knn(self._h, _ptr(idx), _ptr(dist)))
+        return dist, idx
+
+    def get_csr(self):
+        nnz = ctypes.c_int64(0)
+        _check(load().adsel_get_csr(self._h, None, None, None, ctypes.byref(nnz)))
+        row_ptr = np.empty(self.n + 1, dtype=np.int32)
+        col = np.empty(nnz.value, dtype=np.int32)
+        w = np.empty(nnz.value, dtype=np.float64)
+        _check(load().adsel_get_csr(self._h, _ptr(row_ptr), _ptr(col), _ptr(w), ctypes.byref(nnz)))
+        return row_ptr, col, w
+
+    # -- geodesic ----------------------------------------------------------------------------
+    def geodesic_rows(self, sources, radius=np.inf):
+        sources = np.ascontiguousarray(sources, dtype=np.int32)
+        out = np.empty((len(sources), self.n), dtype=np.float64)
+        _check(load().adsel_geodesic_rows(self._h, _ptr(sources), len(sources), float(radius), _ptr(out)))
+        return out
+
+    def geodesic_max_finite(self) -> float:
+        v = ctypes.c_double(0.0)
+        _check(load().adsel_geodesic_max_finite(self._h, ctypes.byref(v)))
+        return v.value
+
+    # -- selection ---------------------------------------------------------------------------
+    def select(self, *, spatial, temporal, normalize, aggregate="sum", lambda_t=1.0, max_spatial=0.0,
+               max_temporal=0.0, cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=0.0, forbid_sampled=False,
+               sampled=(), first_index=-1, out_cap=None):
+        p = SelectParams(SPATIAL[spatial], int(bool(temporal)), NORMALIZE[normalize], AGGREGATE[aggregate],
+                         float(lambda_t), float(max_spatial), float(max_temporal), float(cost_b), float(cost_f),
+                         float(cost_start), float(budget), int(bool(forbid_sampled)), 0)
+        sampled = np.ascontiguousarray(sampled, dtype=np.int32)
+        out_cap = self.n if out_cap is None else out_cap
+        out = np.empty(out_cap, dtype=np.int32)
+        m, cost = ctypes.c_int32(0), ctypes.c_double(0.0)
+        status = load().adsel_select(self._h, ctypes.byref(p), _ptr(sampled) if len(sampled) else None, len(sampled),
+                                     int(first_index), _ptr(out), out_cap, ctypes.byref(m), ctypes.byref(cost))
+        if status == ERR_RESELECTED:
+            # the reference's AssertionError (spatial_temporal_selector.py:182), same message
+            raise AssertionError(load().adsel_last_error().decode())
+        _check(status)
+        return out[: m.value].tolist(), cost.value
+
+    def get_fps(self):
+        fps = np.empty(self.n, dtype=np.float64)
+        _check(load().adsel_get_fps(self._h, _ptr(fps)))
+        return fps
+
+    def stage_ms(self):
+        ms = np.zeros(5, dtype=np.float32)
+        _check(load().adsel_get_stage_ms(self._h, _ptr(ms)))
+        return dict(zip(("knn", "csr", "geodesic_lists", "greedy", "geodesic_max"), ms.tolist()))
+
+    def counters(self):
+        c = np.zeros(4, dtype=np.int64)
+        _check(load().adsel_get_counters(self._h, _ptr(c)))
+        return dict(zip(("launches", "steps", "list_entries", "nnz"), c.tolist()))
+
+    def stream_ptr(self) -> int:
+        s = _P()
+        _check(load().adsel_get_stream(self._h, ctypes.byref(s)))
+        return s.value or 0
+
+    def synchronize(self):
+        _check(load().adsel_synchronize(self._h))
+
+    def exp_f64(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        _check(load().adsel_exp_f64(self._h, _ptr(x), x.size, _ptr(out)))
+        return out

@@ -1,0 +1,90 @@
+"""``BaseSelector``: buffer JSON, cumulative-budget bookkeeping, cost model, dump
+(det3d/selectors/base_selector.py:12-86), plus the shared device-side greedy driver.
+"""
+import logging
+import os
+import random
+from typing import Optional
+
+from ..dist import master_only
+from ..fileio import dump, load
+from .registry import SELECTORS
+
+
+@SELECTORS.register_module
+class BaseSelector(object):
+    """Same constructor, attributes and methods as the reference class.
+
+    ``detector`` / ``dataloader`` are accepted and stored for drop-in compatibility
+    (tools/active_select.py:152-157 always passes them) but never used by the data-only selectors.
+    """
+
+    def __init__(self, budget: int, buffer_file: str, dump_file_name: Optional[str] = None,
+                 infos_origin="", detector=None, dataloader=None, logger: Optional[logging.Logger] = None,
+                 pred: bool = False, cost_b: float = 0.04, cost_f: float = 0.12) -> None:
+        super().__init__()
+        self.budget = budget
+        self.buffer_file = buffer_file
+        self.dump_file_name = buffer_file if dump_file_name is None else dump_file_name
+        self.buffer = load(buffer_file)                 # {"0": [], "<cumulative budget>": [idx, ...]}
+        self.detector = detector
+        self.dataloader = dataloader
+        self.selected_index = {}
+        self.infos_file = infos_origin
+        self.infos_origin = load(infos_origin)          # list[dict], whole pool in RAM (base_selector.py:39)
+        self.current_budget = str(self.budget + int(self.get_max_key()))
+        self.logger = logger if logger is not None else logging.getLogger(__file__)
+        self.pred = pred
+        self.cost_b = cost_b
+        self.cost_f = cost_f
+        self.last_stats = {}
+
+    def get_max_key(self):
+        return str(max(int(key) for key in self.buffer.keys()))
+
+    def select_samples(self, **kwargs) -> None:
+        return
+
+    @master_only
+    def dump_file(self) -> None:
+        """Write the updated buffer JSON and the infos subset ``<infos>_<budget>.<ext>`` (:57-73)."""
+        self.buffer.update(self.selected_index)
+        dump(self.buffer, self.dump_file_name)
+        self.logger.info(f"update the buffer, and save as {self.dump_file_name}")
+        ext = os.path.splitext(self.infos_file)[-1]
+        replace_path = self.infos_file.replace(ext, f"_{self.current_budget}{ext}")
+        infos_sampled = [self.infos_origin[i] for i in self.buffer[str(self.current_budget)]]
+        dump(infos_sampled, replace_path)
+        self.logger.info(f"sample the {self.current_budget} infos and save as {replace_path}")
+
+    def get_selected_samples(self):
+        return self.selected_index
+
+    def get_cost_amount(self):
+        """Annotation cost of the frames already in the buffer, accumulated in the reference's order (:78-86)."""
+        cost = 0
+        sampled_frames = [self.infos_origin[i] for i in self.buffer[self.get_max_key()]]
+        cost += self.cost_f * len(sampled_frames)
+        for anno in sampled_frames:
+            cost += anno["gt_names"].shape[0] * self.cost_b
+        return cost
+
+    # -- shared by the diversity selectors ---------------------------------------------------
+    @staticmethod
+    def _device_index(kwargs) -> int:
+        if kwargs.get("local_rank") is not None:
+            return int(kwargs["local_rank"])
+        return int(os.environ.get("LOCAL_RANK", "0"))
+
+    def _run_greedy(self, handle, **select_kwargs) -> None:
+        """Seed / resume exactly like the reference (:157-170) and run the device greedy loop (:172-193)."""
+        sampled = list(self.buffer[self.get_max_key()])
+        first_index = -1
+        if len(sampled) == 0:
+            # consumes the caller-seeded python RNG exactly like the reference (:168)
+            first_index = random.choice(range(len(self.infos_origin)))
+        selected, cost = handle.select(cost_b=self.cost_b, cost_f=self.cost_f, cost_start=self.get_cost_amount(),
+                                       budget=int(self.current_budget), sampled=sampled, first_index=first_index,
+                                       **select_kwargs)
+        self.last_stats = {"stage_ms": handle.stage_ms(), "counters": handle.counters(), "cost": cost}
+        self.selected_index[self.current_budget] = sampled + selected

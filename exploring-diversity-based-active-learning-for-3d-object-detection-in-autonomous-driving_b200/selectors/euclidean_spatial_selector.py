@@ -1,0 +1,39 @@
+"""``EuSpatialSelector``: 2-D Euclidean ego distance inside a city, margin 1e6 across cities
+(det3d/selectors/euclidean_spatial_selector.py:16-143)."""
+import logging
+from typing import Optional
+
+import numpy as np
+
+from .. import native, pool
+from ..fileio import load
+from .base_selector import BaseSelector
+from .registry import SELECTORS
+
+
+@SELECTORS.register_module
+class EuSpatialSelector(BaseSelector):
+    def __init__(self, budget: int, buffer_file: str, dump_file_name: Optional[str] = None, infos_origin="",
+                 detector=None, dataloader=None, logger: Optional[logging.Logger] = None, pred: bool = False,
+                 logs_file: str = "/home/st2000/data/Datasets/nuScenes/train/v1.0-trainval/log.json",
+                 distance_store_file: str = "/home/st2000/data/buffers/euclidean_distance_map.npy",
+                 cost_b: float = 0.04, cost_f: float = 0.12) -> None:
+        super().__init__(budget, buffer_file, dump_file_name, infos_origin=infos_origin, detector=detector,
+                         dataloader=dataloader, logger=logger, pred=pred, cost_b=cost_b, cost_f=cost_f)
+        self.logs_file = logs_file
+        self.distance_store_file = distance_store_file   # accepted, unused (see SpatialTemporalSelector)
+
+    def select_samples(self, **kwargs) -> None:
+        infos = self.infos_origin
+        city = pool.city_groups(pool.logfile_names(infos), load(self.logs_file))   # :57-60,75-76
+        locations = pool.ego_locations(infos)
+        # rows take the cross-city margin 1e6 as their maximum; the sparse update relies on it
+        extent = float(np.hypot(*(locations.max(0) - locations.min(0))))
+        if not extent < 1e6:
+            raise NotImplementedError("ego locations span >= 1e6 m: exceeds the reference's cross-city margin")
+        handle = native.Handle(self._device_index(kwargs))
+        try:
+            handle.set_pool(locations, city, pool.box_counts(infos))
+            self._run_greedy(handle, spatial="euclid", temporal=False, normalize="raw", forbid_sampled=True)
+        finally:
+            handle.close()

@@ -1,0 +1,122 @@
+/*
+ * adsel_b200.h -- C ABI of the B200-native diversity-based active-selection hot path.
+ *
+ * Drop-in boundary.  The reference has no native code on this path: the whole of
+ * det3d/selectors/spatial_temporal_selector.py:59-193 is host numpy/scipy.  Each entry point below
+ * names the reference lines it replaces.  Plain pointers and sizes only; no torch types.  Host
+ * arrays are owned by the caller, device buffers by the handle.  One handle per CUDA device / rank.
+ * Every function returns 0 on success and a negative adsel_status otherwise (never throws across
+ * the ABI); adsel_last_error() returns the message of the calling thread's last failure.
+ *
+ * There is NO CPU fallback: every compute entry point launches sm_100a kernels and fails with
+ * ADSEL_ERR_CUDA when no device is present.
+ */
+#ifndef ADSEL_B200_H
+#define ADSEL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct adsel_handle adsel_handle;
+
+enum adsel_status {
+    ADSEL_OK = 0,
+    ADSEL_ERR_INVALID = -1,    /* bad argument / call order */
+    ADSEL_ERR_CUDA = -2,       /* CUDA runtime failure (message has the cudaError string) */
+    ADSEL_ERR_CAPACITY = -3,   /* an output buffer supplied by the caller is too small */
+    ADSEL_ERR_RESELECTED = -4  /* greedy argmax landed on an already selected frame:
+                                  the reference's AssertionError (spatial_temporal_selector.py:182) */
+};
+
+/* spatial term of a row of the distance map */
+enum adsel_spatial {
+    ADSEL_SPATIAL_NONE = 0,      /* TemporalSelector (temporal_selector.py:41-104) */
+    ADSEL_SPATIAL_GEODESIC = 1,  /* kNN-graph Dijkstra geodesic (spatial_temporal_selector.py:93-104) */
+    ADSEL_SPATIAL_EUCLID = 2     /* 2-D Euclid inside a group, margin 1e6 outside
+                                    (euclidean_spatial_selector.py:93-101) */
+};
+enum adsel_normalize { ADSEL_NORM_RAW = 0, ADSEL_NORM_EXP = 1, ADSEL_NORM_LINEAR = 2 };
+enum adsel_aggregate { ADSEL_AGG_SUM = 0, ADSEL_AGG_MIN = 1, ADSEL_AGG_MAX = 2 };
+
+typedef struct adsel_select_params {
+    int32_t spatial;          /* adsel_spatial */
+    int32_t temporal;         /* 0: no temporal term; 1: |i-j| inside the frame's group else 1e6
+                                 (spatial_temporal_selector.py:110-134, temporal_selector.py:50-63) */
+    int32_t normalize;        /* adsel_normalize (spatial_temporal_selector.py:138-146) */
+    int32_t aggregate;        /* adsel_aggregate (spatial_temporal_selector.py:148-155) */
+    double lambda_t;          /* weight of the temporal term for ADSEL_AGG_SUM (:151) */
+    double max_spatial;       /* ADSEL_NORM_LINEAR divisor, from adsel_geodesic_max_finite (:139) */
+    double max_temporal;      /* ADSEL_NORM_LINEAR divisor "max_temporal_distance" (:127-129,141) */
+    double cost_b;            /* per-box annotation cost (base_selector.py:24,85) */
+    double cost_f;            /* per-frame annotation cost (base_selector.py:25,82) */
+    double cost_start;        /* get_cost_amount() of the frames already in the buffer (base_selector.py:78-86) */
+    double budget;            /* int(current_budget) (spatial_temporal_selector.py:186) */
+    int32_t forbid_sampled;   /* 1: also assert against the buffer's frames (spatial_selector.py:124) */
+    int32_t reserved;
+} adsel_select_params;
+
+/* ---- library ------------------------------------------------------------------------------ */
+const char *adsel_version(void);
+const char *adsel_last_error(void);
+int adsel_device_count(int *count);
+
+/* ---- handle ------------------------------------------------------------------------------- */
+int adsel_create(int device, adsel_handle **out);
+int adsel_destroy(adsel_handle *h);
+/* cudaStream_t all of the handle's work is enqueued on (returned as void*). */
+int adsel_get_stream(adsel_handle *h, void **stream);
+int adsel_synchronize(adsel_handle *h);
+
+/* ---- pool (replaces the per-frame python loops, spatial_temporal_selector.py:78-91,114-129) ---
+ * loc_xy   [n,2] float64  ego x,y per frame (the host keeps the reference's own expression
+ *                         -(cal[:3,3].T @ cal[:3,:3])[:2]; BLAS may fuse, so it is not redone here)
+ * group_id [n]   int32    temporal group per frame: consecutive-run id (SpatialTemporalSelector),
+ *                         logfile-name id (TemporalSelector) or city id (EuSpatialSelector)
+ * n_boxes  [n]   int32    len(info["gt_names"]) per frame (cost model)
+ */
+int adsel_set_pool(adsel_handle *h, int32_t n, const double *loc_xy, const int32_t *group_id,
+                   const int32_t *n_boxes);
+
+/* ---- spatial graph (replaces cKDTree.query + dense scatter + dense->CSR,
+ *      spatial_temporal_selector.py:93-101 and scipy's csgraph_from_dense |w|<=1e-8 drop) -------- */
+int adsel_build_knn_graph(adsel_handle *h, int32_t k);
+/* test/inspection read-backs (host buffers): knn_idx [n,k+1] int32, knn_dist [n,k+1] float64 */
+int adsel_get_knn(adsel_handle *h, int32_t *knn_idx, double *knn_dist);
+/* CSR of the symmetrised graph: row_ptr [n+1] int32; col/w [nnz] (pass NULL to query nnz only) */
+int adsel_get_csr(adsel_handle *h, int32_t *row_ptr, int32_t *col, double *w, int64_t *nnz);
+
+/* ---- geodesic rows (replaces csgraph.shortest_path(..., method="D"), :103-104) ---------------
+ * Dense rows for m sources: out [m,n] float64, inf when unreachable.  radius < inf truncates the
+ * search: entries whose geodesic distance is >= radius are reported as inf. */
+int adsel_geodesic_rows(adsel_handle *h, const int32_t *sources, int32_t m, double radius, double *out);
+/* max over all finite entries of the full geodesic map (linear normalisation, :139). */
+int adsel_geodesic_max_finite(adsel_handle *h, double *out);
+
+/* ---- selection (replaces :110-193: temporal map, normalise, aggregate, greedy k-center loop,
+ *      cost-budget stop).  sampled [n_sampled]: frames already in the buffer; first_index: the
+ *      caller's random.choice(range(n)) used when n_sampled == 0 (:168), ignored otherwise.
+ *      out_idx [out_cap] receives the NEW frames in selection order, *out_m their count,
+ *      *out_cost the accumulated cost including the frame that overflowed the budget. ---------- */
+int adsel_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
+                 int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
+/* Read back the final min-distance-to-selected vector fps [n] float64 (tests). */
+int adsel_get_fps(adsel_handle *h, double *fps);
+/* Device-time of the stages of the last build/select calls, milliseconds (CUDA events on the
+ * handle's stream): [0] knn, [1] csr build, [2] geodesic lists, [3] greedy loop, [4] geodesic max. */
+int adsel_get_stage_ms(adsel_handle *h, float *ms5);
+/* counters of the last select: [0] kernels launched since adsel_create, [1] greedy steps,
+ * [2] total neighbour-list entries, [3] csr nnz */
+int adsel_get_counters(adsel_handle *h, int64_t *c4);
+
+/* ---- element-wise helpers (tests) ----------------------------------------------------------- */
+/* out[i] = exp(x[i]) with the arithmetic of numpy's AVX512_SKX float64 exp (np.exp in
+ * spatial_temporal_selector.py:142-143); host buffers, computed on the device. */
+int adsel_exp_f64(adsel_handle *h, const double *x, int64_t n, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADSEL_B200_H */

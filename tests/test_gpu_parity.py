@@ -1,0 +1,189 @@
+"""GPU: parity of the sm_100a path against the oracle and the reference's goldens, through the C ABI."""
+import json
+import os
+import pickle
+import random
+
+import numpy as np
+import pytest
+
+import restatement as R
+from adsel_b200 import native, pool
+from adsel_b200.selectors import build_selector
+from conftest import KIND, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handle():
+    h = native.Handle(0)
+    yield h
+    h.close()
+
+
+def test_device_exp_is_numpys_exp_bit_for_bit(handle):
+    rng = np.random.default_rng(11)
+    xs = [rng.uniform(-40.0, 0.0, 4_000_000), rng.uniform(-707.0, 707.0, 1_000_000), rng.uniform(-1e-3, 1e-3, 500_000),
+          -np.arange(0, 700, dtype=np.float64), -np.arange(0, 640) / 16.0 * np.log(2.0), np.array([0.0, -0.0, -38.0, -37.43])]
+    for x in xs:
+        assert np.array_equal(handle.exp_f64(x).view(np.uint64), R.npexp(x).view(np.uint64))
+
+
+def _set_spatial_pool(handle, infos):
+    loc = pool.ego_locations(infos)
+    run_id, max_td = pool.consecutive_runs(pool.logfile_names(infos))
+    handle.set_pool(loc, run_id, pool.box_counts(infos))
+    return loc, run_id, max_td
+
+
+@pytest.mark.parametrize("pool_name,k", [("P300", 8), ("P2K", 8), ("P2K", 4), ("P2K", 11), ("P8K", 8)])
+def test_knn_matches_ckdtree(handle, pools, pool_name, k):
+    infos = pools(pool_name)["infos"]
+    loc, _, _ = _set_spatial_pool(handle, infos)
+    handle.build_knn_graph(k)
+    dist, idx = handle.get_knn()
+    ref_d, ref_i = R.knn_query(loc, k)
+    assert np.array_equal(dist.view(np.uint64), ref_d.view(np.uint64))      # bit-exact float64 distances
+    assert np.array_equal(idx, ref_i)
+
+
+@pytest.mark.parametrize("pool_name", ["P300", "P2K", "P8K"])
+def test_csr_matches_scipy_conversion(handle, pools, pool_name):
+    infos = pools(pool_name)["infos"]
+    loc, _, _ = _set_spatial_pool(handle, infos)
+    handle.build_knn_graph(8)
+    row_ptr, col, w = handle.get_csr()
+    ref = R.knn_graph_csr(loc, 8)
+    ref.sort_indices()
+    assert np.array_equal(row_ptr, ref.indptr)
+    for i in range(len(loc)):
+        o = np.argsort(col[row_ptr[i]:row_ptr[i + 1]])
+        assert np.array_equal(col[row_ptr[i]:row_ptr[i + 1]][o], ref.indices[ref.indptr[i]:ref.indptr[i + 1]])
+        assert np.array_equal(w[row_ptr[i]:row_ptr[i + 1]][o].view(np.uint64),
+                              ref.data[ref.indptr[i]:ref.indptr[i + 1]].view(np.uint64))
+
+
+def test_csr_drops_null_edges(handle):
+    loc = np.array([[0.0, 0.0], [5e-9, 0.0], [1.0, 0.0], [2.0, 0.0], [3.5, 0.0]])
+    handle.set_pool(loc, np.zeros(5, np.int32), np.ones(5, np.int32))
+    handle.build_knn_graph(2)
+    row_ptr, col, w = handle.get_csr()
+    ref = R.knn_graph_csr(loc, 2)
+    assert np.array_equal(row_ptr, ref.indptr)
+    assert 1 not in col[row_ptr[0]:row_ptr[1]].tolist()
+    rows = handle.geodesic_rows([0])
+    assert np.array_equal(rows.view(np.uint64), R.geodesic_rows(ref, [0]).view(np.uint64))
+
+
+@pytest.mark.parametrize("pool_name,m", [("P300", 300), ("P2K", 257), ("P8K", 64)])
+def test_geodesic_rows_match_scipy_dijkstra_bitwise(handle, pools, pool_name, m):
+    infos = pools(pool_name)["infos"]
+    loc, _, _ = _set_spatial_pool(handle, infos)
+    handle.build_knn_graph(8)
+    rng = np.random.default_rng(5)
+    src = rng.choice(len(loc), size=m, replace=False) if m < len(loc) else np.arange(len(loc))
+    got = handle.geodesic_rows(src)
+    ref = R.geodesic_rows(R.knn_graph_csr(loc, 8), src)
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    # truncated search: exact below the radius, "far" (inf) at or beyond it
+    got38 = handle.geodesic_rows(src, radius=38.0)
+    inside = ref < 38.0
+    assert np.array_equal(got38[inside].view(np.uint64), ref[inside].view(np.uint64))
+    assert np.all(np.isinf(got38[~inside]))
+
+
+def test_geodesic_max_finite(handle, pools):
+    infos = pools("P2K")["infos"]
+    loc, _, _ = _set_spatial_pool(handle, infos)
+    handle.build_knn_graph(8)
+    assert handle.geodesic_max_finite() == R.geodesic_max_finite(R.knn_graph_csr(loc, 8))
+
+
+def _run_case_through_selectors(pl, case, tmp_path):
+    """Drive the drop-in selector classes exactly like tools/active_select.py:152-163 does."""
+    buffer_file = str(tmp_path / "buffer.json")
+    json.dump({"0": []}, open(buffer_file, "w"), indent=4)
+    res = {}
+    for budget in case["rounds"]:
+        cfg = dict(type=case["selector"], budget=budget, buffer_file=buffer_file, infos_origin=pl["paths"]["infos"],
+                   detector=None, dataloader=None, logger=None, pred=False)
+        if case["selector"] != "TemporalSelector":
+            cfg.update(logs_file=pl["paths"]["logs"], distance_store_file=str(tmp_path / "unused.npy"))
+        cfg.update(case["kwargs"])
+        random.seed(3407)
+        sel = build_selector(cfg)
+        try:
+            sel.select_samples(local_rank=0)
+        except AssertionError as e:
+            res[sel.current_budget] = {"raises": "AssertionError", "message": str(e)}
+            break
+        sel.dump_file()
+        res.update(sel.get_selected_samples())
+    return res, buffer_file
+
+
+@pytest.mark.parametrize("pool_name", ["P300", "P2K", "P8K"])
+def test_selected_index_identical_to_reference(pools, tmp_path, pool_name):
+    golden = load_golden(f"{pool_name}_all.json")
+    pl = pools(pool_name)
+    for cid, case in golden["cases"].items():
+        res, buffer_file = _run_case_through_selectors(pl, case, tmp_path)
+        assert res == case["selected_index"], f"{pool_name}/{cid}"
+        if all(isinstance(v, list) for v in res.values()):
+            on_disk = json.load(open(buffer_file))
+            assert on_disk == {"0": [], **res}
+            last = max(res, key=int)
+            sub = pickle.load(open(pl["paths"]["infos"].replace(".pkl", f"_{last}.pkl"), "rb"))
+            assert [s["token"] for s in sub] == [pl["infos"][i]["token"] for i in res[last]]
+
+
+def test_p28k_budgets_600_1200_4800_identical_to_reference(pools, tmp_path):
+    """BASELINE.json target: identical selected-index JSON on the 28,130-frame pool."""
+    golden = load_golden("P28K_st.json")
+    pl = pools("P28K")
+    for cid, case in golden["cases"].items():
+        res, _ = _run_case_through_selectors(pl, case, tmp_path)
+        assert res == case["selected_index"], cid
+
+
+def test_fps_vector_matches_oracle(handle, pools):
+    pl = pools("P2K")
+    infos = pl["infos"]
+    loc, run_id, max_td = _set_spatial_pool(handle, infos)
+    handle.build_knn_graph(8)
+    sel, cost = handle.select(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0,
+                              budget=300, first_index=17)
+    prov = R.RowProvider("spatial_temporal", infos)
+    fps = np.stack([prov.row(i) for i in sel]).min(0)
+    assert np.array_equal(handle.get_fps().view(np.uint64), fps.view(np.uint64))
+    n_boxes = pool.box_counts(infos)
+    ref_sel = R.greedy_select(prov.row, len(infos), n_boxes, [], 17, "300")
+    assert sel == ref_sel
+
+
+def test_ragged_and_edge_inputs(handle):
+    # one long run + singleton runs, k larger than some components, every frame its own group
+    rng = np.random.default_rng(3)
+    n = 97
+    loc = np.cumsum(rng.normal(0, 3.0, size=(n, 2)), axis=0)
+    run_id = np.concatenate([np.zeros(60), np.arange(1, n - 60 + 1)]).astype(np.int32)
+    n_boxes = rng.integers(0, 5, size=n).astype(np.int32)
+    handle.set_pool(loc, run_id, n_boxes)
+    handle.build_knn_graph(3)
+    infos = [{"cam_front_path": f"a/L{r}__CAM_FRONT__{i}.jpg", "gt_names": np.zeros(b, dtype="<U3"),
+              "car_from_global": np.eye(4)} for i, (r, b) in enumerate(zip(run_id, n_boxes))]
+    csr = R.knn_graph_csr(loc, 3)
+
+    def row(i):
+        s = R.exp_normalize(R.geodesic_rows(csr, [i])[0])
+        t = R.exp_normalize(R.temporal_row(run_id, i))
+        return s + 1 * t
+    ref = R.greedy_select(row, n, n_boxes, [], 5, "9")
+    got, _ = handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=9, first_index=5)
+    assert got == ref
+    # zero-box frames and a budget that admits exactly the seed
+    got, cost = handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=0, first_index=5)
+    assert got == [5]
+    with pytest.raises(native.NativeError):
+        handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=5, first_index=n)

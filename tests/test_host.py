@@ -1,0 +1,129 @@
+"""CPU: host logic -- registry/builder API, file formats, buffer bookkeeping, C-ABI exports."""
+import ctypes
+import json
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+import restatement as R
+from adsel_b200 import fileio, native, pool
+from adsel_b200.selectors import SELECTORS, BaseSelector, SpatialTemporalSelector, build_selector
+from adsel_b200.utils import Registry, build_from_cfg
+from conftest import ROOT
+
+
+def test_registry_semantics():
+    reg = Registry("thing")
+
+    @reg.register_module
+    class A:
+        def __init__(self, x, y=2):
+            self.x, self.y = x, y
+
+    assert reg.get("A") is A and reg.name == "thing" and "A" in repr(reg)
+    with pytest.raises(KeyError):
+        reg.register_module(A)                       # duplicate name
+    with pytest.raises(TypeError):
+        reg.register_module(lambda: None)            # not a class
+    cfg = {"type": "A", "x": 1}
+    obj = build_from_cfg(cfg, reg, default_args={"y": 5, "x": 9})
+    assert (obj.x, obj.y) == (1, 5) and cfg == {"type": "A", "x": 1}
+    assert build_from_cfg({"type": A, "x": 3}, reg).x == 3
+    with pytest.raises(KeyError):
+        build_from_cfg({"type": "Nope"}, reg)
+    with pytest.raises(TypeError):
+        build_from_cfg({"type": 3}, reg)
+    with pytest.raises(TypeError):
+        build_from_cfg({"type": "A", "x": 1, "bogus": 2}, reg)   # unknown kwarg, as a normal ctor
+
+
+def test_selector_registry_names():
+    for name in ("BaseSelector", "SpatialSelector", "EuSpatialSelector", "TemporalSelector", "SpatialTemporalSelector"):
+        assert SELECTORS.get(name) is not None
+
+
+def test_fileio_formats(tmp_path):
+    obj = {"0": [], "600": [3, 1, 2]}
+    p = str(tmp_path / "b.json")
+    fileio.dump(obj, p, indent=4)
+    assert fileio.load(p) == obj and "\n" in open(p).read()
+    fileio.dump(obj, p)
+    assert open(p).read() == json.dumps(obj)         # the reference writes the buffer without indent
+    q = str(tmp_path / "i.pkl")
+    fileio.dump([{"a": np.arange(3)}], q)
+    raw = open(q, "rb").read()
+    assert raw[:2] == b"\x80\x02"                    # pickle protocol 2 (pickle_handler.py:13-19)
+    assert fileio.load(q)[0]["a"].tolist() == [0, 1, 2]
+    with pytest.raises(TypeError):
+        fileio.load(str(tmp_path / "x.txt"))
+    assert json.loads(fileio.dump(obj, file_format="json")) == obj
+
+
+def test_base_selector_bookkeeping(pools, tmp_path):
+    pl = pools("P300")
+    buf = str(tmp_path / "buffer.json")
+    json.dump({"0": [], "100": [5, 7, 9]}, open(buf, "w"))
+    sel = BaseSelector(budget=50, buffer_file=buf, infos_origin=pl["paths"]["infos"])
+    assert sel.get_max_key() == "100" and sel.current_budget == "150"
+    n_boxes = pool.box_counts(sel.infos_origin)
+    assert sel.get_cost_amount() == R.cost_of_sampled(n_boxes, [5, 7, 9], 0.04, 0.12)
+    sel.selected_index["150"] = [5, 7, 9, 11]
+    sel.dump_file()
+    assert json.load(open(buf)) == {"0": [], "100": [5, 7, 9], "150": [5, 7, 9, 11]}
+    sub = pickle.load(open(pl["paths"]["infos"].replace(".pkl", "_150.pkl"), "rb"))
+    assert [s["token"] for s in sub] == [sel.infos_origin[i]["token"] for i in (5, 7, 9, 11)]
+
+
+def test_spatial_temporal_ctor_contract(pools):
+    pl = pools("P300")
+    common = dict(budget=100, buffer_file=pl["paths"]["buffer"], infos_origin=pl["paths"]["infos"],
+                  logs_file=pl["paths"]["logs"])
+    sel = build_selector(dict(type="SpatialTemporalSelector", detector=None, dataloader=None, logger=None,
+                              pred=False, **common))
+    assert isinstance(sel, SpatialTemporalSelector)
+    assert (sel.k, sel.normalize, sel.aggregate, sel.lambda_t, sel.cost_b, sel.cost_f) == (8, "exp", "sum", 1, 0.04, 0.12)
+    with pytest.raises(AssertionError):
+        SpatialTemporalSelector(normalize="softmax", **common)
+    with pytest.raises(AssertionError):
+        SpatialTemporalSelector(aggregate="mean", **common)
+    with pytest.raises(TypeError):
+        SpatialTemporalSelector(unknown_kwarg=1, **common)
+
+
+def test_pool_extraction_matches_reference_loops(pools):
+    pl = pools("P2K")
+    infos, logs = pl["infos"], pl["logs"]
+    assert np.array_equal(pool.ego_locations(infos).view(np.uint64), R.ego_locations(infos).view(np.uint64))
+    names = pool.logfile_names(infos)
+    run_id, max_td = pool.consecutive_runs(names)
+    ref_run, ref_max = R.consecutive_runs(infos)
+    assert np.array_equal(run_id, ref_run) and max_td == ref_max
+    assert np.array_equal(pool.name_groups(names), R.logfile_groups(infos))
+    assert np.array_equal(pool.city_groups(names, logs), R.city_ids(infos, logs))
+    with pytest.raises(KeyError):
+        pool.city_groups(names, logs[1:])
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "adsel_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char \*)\s*(adsel_[a-z0-9_]+)\s*\(", header, re.M))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(native.library_path()) if os.path.exists(native.library_path()) else native.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/adsel_b200.h but not exported"
+    assert set(native.exported_symbols()) <= declared
+    assert b"sm_100a" in native.load().adsel_version()
+
+
+def test_no_cpu_fallback_without_a_device():
+    try:
+        count = native.device_count()
+    except native.NativeError:
+        count = 0
+    if count > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(native.NativeError):
+        native.Handle(0)
