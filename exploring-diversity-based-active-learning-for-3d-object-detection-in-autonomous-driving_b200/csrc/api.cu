@@ -59,6 +59,8 @@ int adsel_create(int device, adsel_handle **out) {
     ADSEL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     ADSEL_CUDA(cudaEventCreate(&h->ev[0]));
     ADSEL_CUDA(cudaEventCreate(&h->ev[1]));
+    ADSEL_CUDA(cudaEventCreate(&h->timer_ev[0]));
+    ADSEL_CUDA(cudaEventCreate(&h->timer_ev[1]));
     *out = h;
     return ADSEL_OK;
 }
@@ -76,6 +78,8 @@ int adsel_destroy(adsel_handle *h) {
     h->d_sampled.release(); h->d_out.release(); h->d_result.release();
     cudaEventDestroy(h->ev[0]);
     cudaEventDestroy(h->ev[1]);
+    cudaEventDestroy(h->timer_ev[0]);
+    cudaEventDestroy(h->timer_ev[1]);
     cudaStreamDestroy(h->stream);
     delete h;
     return ADSEL_OK;
@@ -91,6 +95,23 @@ int adsel_synchronize(adsel_handle *h) {
     ADSEL_REQUIRE(h, "adsel_synchronize: null handle");
     ADSEL_CUDA(cudaSetDevice(h->device));
     ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    return ADSEL_OK;
+}
+
+int adsel_timer_start(adsel_handle *h) {
+    ADSEL_REQUIRE(h, "adsel_timer_start: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    ADSEL_CUDA(cudaEventRecord(h->timer_ev[0], h->stream));
+    return ADSEL_OK;
+}
+
+int adsel_timer_stop(adsel_handle *h, float *elapsed_ms) {
+    ADSEL_REQUIRE(h && elapsed_ms, "adsel_timer_stop: null argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    ADSEL_CUDA(cudaEventRecord(h->timer_ev[1], h->stream));
+    ADSEL_CUDA(cudaEventSynchronize(h->timer_ev[1]));
+    ADSEL_CUDA(cudaEventElapsedTime(elapsed_ms, h->timer_ev[0], h->timer_ev[1]));
     return ADSEL_OK;
 }
 

@@ -69,6 +69,7 @@ struct adsel_handle {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t timer_ev[2] = {nullptr, nullptr};
     float stage_ms[5] = {0, 0, 0, 0, 0};
     int64_t launches = 0, last_steps = 0;
 

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "adsel_destroy": (ctypes.c_int, [_P]),
     "adsel_get_stream": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     "adsel_synchronize": (ctypes.c_int, [_P]),
+    "adsel_timer_start": (ctypes.c_int, [_P]),
+    "adsel_timer_stop": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
     "adsel_set_pool": (ctypes.c_int, [_P, ctypes.c_int32, _P, _P, _P]),
     "adsel_build_knn_graph": (ctypes.c_int, [_P, ctypes.c_int32]),
     "adsel_get_knn": (ctypes.c_int, [_P, _P, _P]),
@@ -202,6 +204,14 @@ class Handle:
         s = _P()
         _check(load().adsel_get_stream(self._h, ctypes.byref(s)))
         return s.value or 0
+
+    def timer_start(self):
+        _check(load().adsel_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_float(0.0)
+        _check(load().adsel_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
 
     def synchronize(self):
         _check(load().adsel_synchronize(self._h))

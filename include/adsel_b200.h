@@ -69,6 +69,9 @@ int adsel_destroy(adsel_handle *h);
 /* cudaStream_t all of the handle's work is enqueued on (returned as void*). */
 int adsel_get_stream(adsel_handle *h, void **stream);
 int adsel_synchronize(adsel_handle *h);
+/* Device timer: CUDA events recorded on the handle's stream (bench.py's timed region). */
+int adsel_timer_start(adsel_handle *h);
+int adsel_timer_stop(adsel_handle *h, float *elapsed_ms);
 
 /* ---- pool (replaces the per-frame python loops, spatial_temporal_selector.py:78-91,114-129) ---
  * loc_xy   [n,2] float64  ego x,y per frame (the host keeps the reference's own expression

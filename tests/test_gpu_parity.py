@@ -187,3 +187,21 @@ def test_ragged_and_edge_inputs(handle):
     assert got == [5]
     with pytest.raises(native.NativeError):
         handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=5, first_index=n)
+
+
+def test_cli_two_invocations_match_reference(pools, tmp_path):
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("active_select_cli", os.path.join(ROOT, "tools", "active_select.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    pl = pools("P2K")
+    golden = load_golden("P2K_all.json")["cases"]["st_exp_sum_rounds"]
+    buf = str(tmp_path / "cli_buffer.json")
+    cfg = tmp_path / "cfg.py"
+    cfg.write_text(f"selector = dict(type='SpatialTemporalSelector', budget=1, buffer_file={buf!r}, "
+                   f"infos_origin={pl['paths']['infos']!r}, logs_file={pl['paths']['logs']!r})\n")
+    assert cli.main(["--config", str(cfg), "--budget", "300"]) == 0      # first run: empty buffer only
+    for b in golden["rounds"]:
+        assert cli.main(["--config", str(cfg), "--budget", str(b)]) == 0
+    assert json.load(open(buf)) == {"0": [], **golden["selected_index"]}

@@ -127,3 +127,18 @@ def test_no_cpu_fallback_without_a_device():
         pytest.skip("a CUDA device is present")
     with pytest.raises(native.NativeError):
         native.Handle(0)
+
+
+def test_cli_first_invocation_writes_indented_empty_buffer(pools, tmp_path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("active_select_cli", os.path.join(ROOT, "tools", "active_select.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    pl = pools("P300")
+    buf = str(tmp_path / "cli_buffer.json")
+    cfg = tmp_path / "cfg.py"
+    cfg.write_text(f"selector = dict(type='SpatialTemporalSelector', budget=4800, buffer_file={buf!r}, "
+                   f"infos_origin={pl['paths']['infos']!r}, logs_file={pl['paths']['logs']!r})\n")
+    assert cli.main(["--config", str(cfg), "--budget", "100"]) == 0
+    assert open(buf).read() == json.dumps({"0": []}, indent=4)      # tools/active_select.py:68-71
+    assert cli.load_selector_cfg(str(cfg))["type"] == "SpatialTemporalSelector"
