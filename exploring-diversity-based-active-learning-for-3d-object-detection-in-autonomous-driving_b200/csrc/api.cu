@@ -27,6 +27,10 @@ int geodesic_max_finite(adsel_handle *h, double *out);
 int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
                   int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
 
+int bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_off_host, int32_t n_sweeps, uint64_t seed);
+int bev_set_points(adsel_handle *h, const float *pts_host, const int64_t *frame_off_host, int32_t n_frames);
+int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics);
+
 __global__ void exp_f64_kernel(const double *__restrict__ x, long long n, double *__restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = np_exp_f64(x[i]);
@@ -76,6 +80,7 @@ int adsel_destroy(adsel_handle *h) {
     h->list_off.release(); h->list_len.release(); h->list_idx.release(); h->list_val.release(); h->cursor.release();
     h->fps.release(); h->blk_val.release(); h->blk_idx.release(); h->is_selected.release(); h->tlut.release();
     h->d_sampled.release(); h->d_out.release(); h->d_result.release();
+    h->bev_pts.release(); h->bev_off.release(); h->bev_counts.release(); h->bev_norm2.release(); h->bev_levels.release();
     cudaEventDestroy(h->ev[0]);
     cudaEventDestroy(h->ev[1]);
     cudaEventDestroy(h->timer_ev[0]);
@@ -201,9 +206,9 @@ int adsel_get_fps(adsel_handle *h, double *fps) {
     return ADSEL_OK;
 }
 
-int adsel_get_stage_ms(adsel_handle *h, float *ms5) {
-    ADSEL_REQUIRE(h && ms5, "adsel_get_stage_ms: null argument");
-    memcpy(ms5, h->stage_ms, sizeof(h->stage_ms));
+int adsel_get_stage_ms(adsel_handle *h, float *ms8) {
+    ADSEL_REQUIRE(h && ms8, "adsel_get_stage_ms: null argument");
+    memcpy(ms8, h->stage_ms, sizeof(h->stage_ms));
     return ADSEL_OK;
 }
 
@@ -213,6 +218,42 @@ int adsel_get_counters(adsel_handle *h, int64_t *c4) {
     c4[1] = h->last_steps;
     c4[2] = h->list_total;
     c4[3] = h->nnz;
+    return ADSEL_OK;
+}
+
+int adsel_bev_set_points(adsel_handle *h, const float *points, const int64_t *frame_off, int32_t n_frames) {
+    ADSEL_REQUIRE(h, "adsel_bev_set_points: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return bev_set_points(h, points, frame_off, n_frames);
+}
+
+int adsel_bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_off, int32_t n_sweeps, uint64_t seed) {
+    ADSEL_REQUIRE(h, "adsel_bev_generate: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return bev_generate(h, n_frames, frame_off, n_sweeps, seed);
+}
+
+int adsel_bev_get_points(adsel_handle *h, float *points) {
+    ADSEL_REQUIRE(h && points && h->bev_frames > 0, "adsel_bev_get_points: no points / null argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    ADSEL_CUDA(cudaMemcpy(points, h->bev_pts.p, sizeof(float) * 5 * (size_t)h->bev_points, cudaMemcpyDeviceToHost));
+    return ADSEL_OK;
+}
+
+int adsel_bev_build(adsel_handle *h, const adsel_bev_params *p, int32_t aggregate_atomics) {
+    ADSEL_REQUIRE(h && p, "adsel_bev_build: null argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return bev_build(h, p, aggregate_atomics);
+}
+
+int adsel_bev_get_descriptors(adsel_handle *h, int32_t *counts, uint16_t *levels, int32_t *norm2, int32_t *cells) {
+    ADSEL_REQUIRE(h && h->bev_cells > 0, "adsel_bev_get_descriptors: call adsel_bev_build first");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    const size_t tot = (size_t)h->bev_frames * h->bev_cells;
+    if (cells) *cells = h->bev_cells;
+    if (counts) ADSEL_CUDA(cudaMemcpy(counts, h->bev_counts.p, sizeof(int32_t) * tot, cudaMemcpyDeviceToHost));
+    if (levels) ADSEL_CUDA(cudaMemcpy(levels, h->bev_levels.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost));
+    if (norm2) ADSEL_CUDA(cudaMemcpy(norm2, h->bev_norm2.p, sizeof(int32_t) * h->bev_frames, cudaMemcpyDeviceToHost));
     return ADSEL_OK;
 }
 

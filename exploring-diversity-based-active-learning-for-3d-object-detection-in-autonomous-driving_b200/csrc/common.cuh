@@ -70,7 +70,7 @@ struct adsel_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t timer_ev[2] = {nullptr, nullptr};
-    float stage_ms[5] = {0, 0, 0, 0, 0};
+    float stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int64_t launches = 0, last_steps = 0;
 
     // pool
@@ -103,6 +103,14 @@ struct adsel_handle {
     int64_t list_total = 0;
     int lists_mode = -1;                         // normalize mode the lists were built for
     double lists_max_spatial = 0.0;
+
+    // BEV descriptors
+    int32_t bev_frames = 0, bev_cells = 0;
+    int64_t bev_points = 0;
+    adsel::DevBuf<float> bev_pts;
+    adsel::DevBuf<int64_t> bev_off;
+    adsel::DevBuf<int32_t> bev_counts, bev_norm2;
+    adsel::DevBuf<uint16_t> bev_levels;          // bf16 bits
 
     // greedy state
     adsel::DevBuf<unsigned long long> fps;       // ordered-u64 view of non-negative doubles

@@ -23,6 +23,10 @@ class NativeError(RuntimeError):
         self.message = message
 
 
+class BevParams(ctypes.Structure):
+    _fields_ = [("range", ctypes.c_float * 6), ("voxel", ctypes.c_float * 3), ("reserved", ctypes.c_int32)]
+
+
 class SelectParams(ctypes.Structure):
     _fields_ = [
         ("spatial", ctypes.c_int32), ("temporal", ctypes.c_int32), ("normalize", ctypes.c_int32),
@@ -56,6 +60,11 @@ _SIGNATURES = {
     "adsel_get_stage_ms": (ctypes.c_int, [_P, _P]),
     "adsel_get_counters": (ctypes.c_int, [_P, _P]),
     "adsel_exp_f64": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P]),
+    "adsel_bev_set_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32]),
+    "adsel_bev_generate": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_uint64]),
+    "adsel_bev_get_points": (ctypes.c_int, [_P, _P]),
+    "adsel_bev_build": (ctypes.c_int, [_P, ctypes.POINTER(BevParams), ctypes.c_int32]),
+    "adsel_bev_get_descriptors": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ctypes.c_int32)]),
 }
 _lib = None
 
@@ -191,14 +200,48 @@ class Handle:
         return fps
 
     def stage_ms(self):
-        ms = np.zeros(5, dtype=np.float32)
+        ms = np.zeros(8, dtype=np.float32)
         _check(load().adsel_get_stage_ms(self._h, _ptr(ms)))
-        return dict(zip(("knn", "csr", "geodesic_lists", "greedy", "geodesic_max"), ms.tolist()))
+        return dict(zip(("knn", "csr", "geodesic_lists", "greedy", "geodesic_max", "bev_histogram", "pairdist",
+                         "dense_greedy"), ms.tolist()))
 
     def counters(self):
         c = np.zeros(4, dtype=np.int64)
         _check(load().adsel_get_counters(self._h, _ptr(c)))
         return dict(zip(("launches", "steps", "list_entries", "nnz"), c.tolist()))
+
+    # -- BEV descriptors ------------------------------------------------------------------------
+    NUSC_RANGE = (-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)     # examples/active/cbgs_spatial_temporal.py:280
+
+    def bev_set_points(self, points, frame_off):
+        points = np.ascontiguousarray(points, dtype=np.float32)
+        frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
+        assert points.ndim == 2 and points.shape[1] == 5 and frame_off[-1] == len(points)
+        self.bev_frames, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
+        _check(load().adsel_bev_set_points(self._h, _ptr(points), _ptr(frame_off), self.bev_frames))
+
+    def bev_generate(self, frame_off, n_sweeps=10, seed=20221107):
+        frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
+        self.bev_frames, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
+        _check(load().adsel_bev_generate(self._h, self.bev_frames, _ptr(frame_off), n_sweeps, seed))
+
+    def bev_get_points(self):
+        pts = np.empty((self.bev_points, 5), dtype=np.float32)
+        _check(load().adsel_bev_get_points(self._h, _ptr(pts)))
+        return pts
+
+    def bev_build(self, point_range=NUSC_RANGE, voxel=(0.8, 0.8, 8.0), aggregate_atomics=True):
+        p = BevParams((ctypes.c_float * 6)(*point_range), (ctypes.c_float * 3)(*voxel), 0)
+        _check(load().adsel_bev_build(self._h, ctypes.byref(p), int(bool(aggregate_atomics))))
+
+    def bev_get_descriptors(self, counts=True, levels=True):
+        cells = ctypes.c_int32(0)
+        _check(load().adsel_bev_get_descriptors(self._h, None, None, None, ctypes.byref(cells)))
+        c = np.empty((self.bev_frames, cells.value), dtype=np.int32) if counts else None
+        lv = np.empty((self.bev_frames, cells.value), dtype=np.uint16) if levels else None
+        n2 = np.empty(self.bev_frames, dtype=np.int32)
+        _check(load().adsel_bev_get_descriptors(self._h, _ptr(c), _ptr(lv), _ptr(n2), ctypes.byref(cells)))
+        return c, lv, n2
 
     def stream_ptr(self) -> int:
         s = _P()

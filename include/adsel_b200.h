@@ -108,11 +108,31 @@ int adsel_select(adsel_handle *h, const adsel_select_params *p, const int32_t *s
 /* Read back the final min-distance-to-selected vector fps [n] float64 (tests). */
 int adsel_get_fps(adsel_handle *h, double *fps);
 /* Device-time of the stages of the last build/select calls, milliseconds (CUDA events on the
- * handle's stream): [0] knn, [1] csr build, [2] geodesic lists, [3] greedy loop, [4] geodesic max. */
-int adsel_get_stage_ms(adsel_handle *h, float *ms5);
+ * handle's stream): [0] knn, [1] csr build, [2] geodesic lists, [3] greedy loop, [4] geodesic max,
+ * [5] bev histogram, [6] pairwise distance tiles, [7] dense greedy loop. */
+int adsel_get_stage_ms(adsel_handle *h, float *ms8);
 /* counters of the last select: [0] kernels launched since adsel_create, [1] greedy steps,
  * [2] total neighbour-list entries, [3] csr nnz */
 int adsel_get_counters(adsel_handle *h, int64_t *c4);
+
+/* ---- BEV density descriptor from LiDAR points (north_star kernel 1; no reference function -- the
+ *      binning semantics are those of det3d/ops/point_cloud/bev_ops.py:27-53, see csrc/bev.cu) -------
+ * points: float32 [P,5] = x,y,z,intensity,dt (det3d/datasets/pipelines/loading.py:121-126), frames
+ * concatenated; frame_off int64 [n_frames+1] point offsets (ragged frames allowed, frame_off[0] = 0). */
+typedef struct adsel_bev_params {
+    float range[6];   /* xmin,ymin,zmin,xmax,ymax,zmax  (examples/active/cbgs_spatial_temporal.py:280) */
+    float voxel[3];   /* cell size; grid = round((max-min)/voxel) (bev_ops.py:27-30) */
+    int32_t reserved;
+} adsel_bev_params;
+int adsel_bev_set_points(adsel_handle *h, const float *points, const int64_t *frame_off, int32_t n_frames);
+/* synthetic multi-sweep LiDAR generated directly in HBM (counter-based hash keyed by frame/sweep) */
+int adsel_bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_off, int32_t n_sweeps, uint64_t seed);
+int adsel_bev_get_points(adsel_handle *h, float *points);
+/* histogram + density level + squared norm for every frame; aggregate_atomics: 1 = warp-aggregated */
+int adsel_bev_build(adsel_handle *h, const adsel_bev_params *p, int32_t aggregate_atomics);
+/* read-backs: counts int32 [n_frames,cells], levels uint16 (bf16 bits) [n_frames,cells], norm2 int32 [n_frames];
+ * any pointer may be NULL; *cells receives ny*nx */
+int adsel_bev_get_descriptors(adsel_handle *h, int32_t *counts, uint16_t *levels, int32_t *norm2, int32_t *cells);
 
 /* ---- element-wise helpers (tests) ----------------------------------------------------------- */
 /* out[i] = exp(x[i]) with the arithmetic of numpy's AVX512_SKX float64 exp (np.exp in
