@@ -31,6 +31,11 @@ int bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_off_hos
 int bev_set_points(adsel_handle *h, const float *pts_host, const int64_t *frame_off_host, int32_t n_frames);
 int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics);
 
+int pairdist_build(adsel_handle *h);
+int pairdist_set_descriptors(adsel_handle *h, const uint16_t *levels_host, int32_t n, int32_t dim);
+int dense_select(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
+                 int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
+
 __global__ void exp_f64_kernel(const double *__restrict__ x, long long n, double *__restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = np_exp_f64(x[i]);
@@ -80,6 +85,7 @@ int adsel_destroy(adsel_handle *h) {
     h->list_off.release(); h->list_len.release(); h->list_idx.release(); h->list_val.release(); h->cursor.release();
     h->fps.release(); h->blk_val.release(); h->blk_idx.release(); h->is_selected.release(); h->tlut.release();
     h->d_sampled.release(); h->d_out.release(); h->d_result.release();
+    h->pd_d2.release(); h->pd_norm.release(); h->pd_fps.release(); h->pd_boxes.release();
     h->bev_pts.release(); h->bev_off.release(); h->bev_counts.release(); h->bev_norm2.release(); h->bev_levels.release();
     cudaEventDestroy(h->ev[0]);
     cudaEventDestroy(h->ev[1]);
@@ -255,6 +261,35 @@ int adsel_bev_get_descriptors(adsel_handle *h, int32_t *counts, uint16_t *levels
     if (levels) ADSEL_CUDA(cudaMemcpy(levels, h->bev_levels.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost));
     if (norm2) ADSEL_CUDA(cudaMemcpy(norm2, h->bev_norm2.p, sizeof(int32_t) * h->bev_frames, cudaMemcpyDeviceToHost));
     return ADSEL_OK;
+}
+
+int adsel_pairdist_set_descriptors(adsel_handle *h, const uint16_t *levels_bf16, int32_t n, int32_t dim) {
+    ADSEL_REQUIRE(h, "adsel_pairdist_set_descriptors: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return pairdist_set_descriptors(h, levels_bf16, n, dim);
+}
+
+int adsel_pairdist_build(adsel_handle *h) {
+    ADSEL_REQUIRE(h, "adsel_pairdist_build: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return pairdist_build(h);
+}
+
+int adsel_pairdist_get_rows(adsel_handle *h, int32_t row0, int32_t rows, int32_t *out) {
+    ADSEL_REQUIRE(h && out && h->pd_n > 0, "adsel_pairdist_get_rows: call adsel_pairdist_build first");
+    ADSEL_REQUIRE(row0 >= 0 && rows > 0 && row0 + rows <= h->pd_n, "adsel_pairdist_get_rows: rows out of range");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    ADSEL_CUDA(cudaMemcpy2D(out, sizeof(int32_t) * h->pd_n, h->pd_d2.p + (size_t)row0 * h->pd_ld, sizeof(int32_t) * h->pd_ld,
+                            sizeof(int32_t) * h->pd_n, rows, cudaMemcpyDeviceToHost));
+    return ADSEL_OK;
+}
+
+int adsel_select_dense(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes, const int32_t *sampled,
+                       int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m,
+                       double *out_cost) {
+    ADSEL_REQUIRE(h, "adsel_select_dense: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return dense_select(h, p, n_boxes, sampled, n_sampled, first_index, out_idx, out_cap, out_m, out_cost);
 }
 
 int adsel_exp_f64(adsel_handle *h, const double *x, int64_t n, double *out) {

@@ -112,6 +112,10 @@ struct adsel_handle {
     adsel::DevBuf<int32_t> bev_counts, bev_norm2;
     adsel::DevBuf<uint16_t> bev_levels;          // bf16 bits
 
+    // pairwise squared distances of the descriptors (dense path)
+    int32_t pd_n = 0, pd_ld = 0;
+    adsel::DevBuf<int32_t> pd_d2, pd_norm, pd_fps, pd_boxes;
+
     // greedy state
     adsel::DevBuf<unsigned long long> fps;       // ordered-u64 view of non-negative doubles
     adsel::DevBuf<unsigned long long> blk_val;

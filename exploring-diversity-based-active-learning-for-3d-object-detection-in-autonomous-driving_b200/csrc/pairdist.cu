@@ -1,0 +1,518 @@
+// pairdist.cu -- pool-wide pairwise squared distances of the BEV density descriptors in GEMM form
+// (north_star kernel 3):  d2(i,j) = |x_i|^2 + |x_j|^2 - 2 x_i.x_j,  Gram tiles on tcgen05.
+//
+// Nearest reference code: the row-loop distance maps of det3d/selectors/euclidean_spatial_selector.py:96
+// and feature_selector.py:96-105, and the unused scalar CUDA op det3d/ops/distance/src/cdist_gpu.cu:31-50
+// (one thread per (i,j), no tensor cores).  No selector of the reference computes this on descriptors.
+//
+// Exactness: descriptor entries are integers in 0..31 (bev.cu), exactly representable in bf16; with
+// D <= 16,384 every partial sum of a dot product is an integer below 31*31*16,384 < 2^24, so the
+// fp32 accumulation in TMEM is exact whatever the hardware's summation order.  The epilogue converts
+// to int32 and forms n_i + n_j - 2g in integers: the distance matrix equals the int64 oracle bit for
+// bit, and argmax ties downstream resolve by index exactly as in the oracle.
+//
+// Kernel: persistent, warp-specialised, one CTA per SM.
+//   warp 0   TMA producer   X[rows, k..k+64) tiles (SWIZZLE_128B) -> 4-stage smem ring, mbarrier tx
+//   warp 1   MMA issuer     tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, fp32 accum in TMEM
+//   warp 2   TMEM allocator 512 columns = two 128x256 fp32 accumulators (MMA of tile t+1 overlaps
+//                           the epilogue of tile t)
+//   warps 4-7 epilogue      tcgen05.ld 32x32b -> int32 -> n_i + n_j - 2g -> 128-byte row segments
+// Tiles are visited in groups of 16 row-blocks so the ~148 concurrently resident tiles share rows
+// and columns of X through L2 (X itself is 0.92 GB at N=28,130, L2 is 126 MB).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace adsel {
+
+constexpr int PD_BLOCK_M = 128, PD_BLOCK_N = 256, PD_BLOCK_K = 64, PD_UMMA_K = 16;
+constexpr int PD_STAGES = 4;
+constexpr int PD_A_BYTES = PD_BLOCK_M * PD_BLOCK_K * 2;       // 16 KB
+constexpr int PD_B_BYTES = PD_BLOCK_N * PD_BLOCK_K * 2;       // 32 KB
+constexpr int PD_STAGE_BYTES = PD_A_BYTES + PD_B_BYTES;       // 48 KB
+constexpr int PD_THREADS = 256;
+constexpr int PD_GROUP_M = 16;
+constexpr int PD_TMEM_COLS = 512;
+constexpr size_t PD_SMEM = 1024 + (size_t)PD_STAGES * PD_STAGE_BYTES + 2 * PD_BLOCK_N * sizeof(int) + 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 in [0,14), LBO = 1 in [16,30), SBO = 1024 B >> 4 in [32,46), version 1 in
+// [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct PdTile {
+    int m_blk, n_blk;
+};
+__device__ __forceinline__ PdTile pd_tile(int t, int blocks_m, int blocks_n) {
+    const int per_group = PD_GROUP_M * blocks_n;
+    const int group = t / per_group, in_group = t - group * per_group;
+    const int first_m = group * PD_GROUP_M;
+    const int gsz = min(PD_GROUP_M, blocks_m - first_m);
+    return PdTile{first_m + in_group % gsz, in_group / gsz};
+}
+
+__global__ void __launch_bounds__(PD_THREADS, 1)
+pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ norm2,
+                        int32_t *__restrict__ out, int ld, int blocks_m, int blocks_n, int k_blocks) {
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t *stage_mem = base;                                             // PD_STAGES x (A | B)
+    int *norm_n = reinterpret_cast<int *>(base + (size_t)PD_STAGES * PD_STAGE_BYTES);   // [2][PD_BLOCK_N]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(norm_n + 2 * PD_BLOCK_N);
+    uint64_t *full = bars, *empty = bars + PD_STAGES, *tmem_full = bars + 2 * PD_STAGES, *tmem_empty = bars + 2 * PD_STAGES + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * PD_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = blocks_m * blocks_n;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+        for (int s = 0; s < PD_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(PD_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const PdTile tl = pd_tile(t, blocks_m, blocks_n);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t *a = stage_mem + (size_t)stage * PD_STAGE_BYTES, *b = a + PD_A_BYTES;
+                    mbar_expect_tx(&full[stage], PD_STAGE_BYTES);
+                    tma_load_2d(a, &tmap, &full[stage], kb * PD_BLOCK_K, tl.m_blk * PD_BLOCK_M);
+                    tma_load_2d(b, &tmap, &full[stage], kb * PD_BLOCK_K, tl.n_blk * PD_BLOCK_N);
+                    tma_load_2d(b + PD_A_BYTES, &tmap, &full[stage], kb * PD_BLOCK_K, tl.n_blk * PD_BLOCK_N + 128);
+                    if (++stage == PD_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            // instruction descriptor: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), K-major both, N>>3 at 17, M>>4 at 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PD_BLOCK_N >> 3) << 17) |
+                                   ((uint32_t)(PD_BLOCK_M >> 4) << 24);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)acc * PD_BLOCK_N;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(stage_mem + (size_t)stage * PD_STAGE_BYTES);
+                    const uint64_t da = make_kmajor_sw128_desc(a_addr), db = make_kmajor_sw128_desc(a_addr + PD_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < PD_BLOCK_K / PD_UMMA_K; ++k) {
+                        // advance 16 bf16 = 32 B inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+                    if (++stage == PD_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> int32 distances -> global =====
+        const int quarter = warp & 3;                    // TMEM lane quarter this warp may read
+        const int row_in_tile = quarter * 32 + lane;
+        const int et = threadIdx.x - 128;                // 0..127
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const PdTile tl = pd_tile(t, blocks_m, blocks_n);
+            const int m0 = tl.m_blk * PD_BLOCK_M, n0 = tl.n_blk * PD_BLOCK_N;
+            int *nn = norm_n + acc * PD_BLOCK_N;
+            nn[et] = norm2[n0 + et];
+            nn[et + 128] = norm2[n0 + et + 128];
+            const int ni = norm2[m0 + row_in_tile];
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // norm_n visible to the 4 epilogue warps
+            mbar_wait(&tmem_full[acc], acc_phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int32_t *orow = out + (size_t)(m0 + row_in_tile) * ld + n0;
+#pragma unroll 1
+            for (int c = 0; c < PD_BLOCK_N / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * PD_BLOCK_N + c * 32), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    int4 o;
+                    o.x = ni + nn[c * 32 + 4 * v + 0] - 2 * __float2int_rn(__uint_as_float(r[4 * v + 0]));
+                    o.y = ni + nn[c * 32 + 4 * v + 1] - 2 * __float2int_rn(__uint_as_float(r[4 * v + 1]));
+                    o.z = ni + nn[c * 32 + 4 * v + 2] - 2 * __float2int_rn(__uint_as_float(r[4 * v + 2]));
+                    o.w = ni + nn[c * 32 + 4 * v + 3] - 2 * __float2int_rn(__uint_as_float(r[4 * v + 3]));
+                    __stcs(reinterpret_cast<int4 *>(orow + c * 32) + v, o);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(PD_TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The driver entry point is resolved at run time so the library does not link libcuda (it must
+// load on the CPU-only build box for the symbol-export test).
+static int get_encode_fn(EncodeTiledFn *fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ADSEL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    ADSEL_REQUIRE(p && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    *fn = reinterpret_cast<EncodeTiledFn>(p);
+    return ADSEL_OK;
+}
+
+// d2 [n_pad, ld] int32 from levels bf16 [n, dim] and norm2 int32 [n] (both device buffers of the handle).
+int pairdist_build(adsel_handle *h) {
+    ADSEL_REQUIRE(h->bev_cells > 0 && h->bev_frames > 0, "adsel_pairdist_build: call adsel_bev_build (or adsel_pairdist_set_descriptors) first");
+    const int n = h->bev_frames, dim = h->bev_cells;
+    ADSEL_REQUIRE(dim % 8 == 0, "adsel_pairdist_build: descriptor length must be a multiple of 8 (16-byte TMA rows)");
+    ADSEL_REQUIRE((long long)dim * 31 * 31 < (1ll << 24), "adsel_pairdist_build: descriptor too long for exact fp32 accumulation");
+    const int blocks_m = (n + PD_BLOCK_M - 1) / PD_BLOCK_M, blocks_n = (n + PD_BLOCK_N - 1) / PD_BLOCK_N;
+    const int k_blocks = (dim + PD_BLOCK_K - 1) / PD_BLOCK_K;
+    const int ld = blocks_n * PD_BLOCK_N, rows = blocks_m * PD_BLOCK_M;
+    h->pd_n = n;
+    h->pd_ld = ld;
+    ADSEL_TRY(h->pd_d2.reserve((size_t)rows * ld));
+    // padded norms (zeros beyond n) so the epilogue needs no bounds checks
+    ADSEL_TRY(h->pd_norm.reserve((size_t)max(rows, ld)));
+    ADSEL_CUDA(cudaMemsetAsync(h->pd_norm.p, 0, sizeof(int32_t) * (size_t)max(rows, ld), h->stream));
+    ADSEL_CUDA(cudaMemcpyAsync(h->pd_norm.p, h->bev_norm2.p, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, h->stream));
+
+    EncodeTiledFn encode = nullptr;
+    ADSEL_TRY(get_encode_fn(&encode));
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)n};
+    const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+    const cuuint32_t box[2] = {PD_BLOCK_K, 128};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->bev_levels.p, gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ADSEL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+    ADSEL_CUDA(cudaFuncSetAttribute(pairdist_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM));
+    const int grid = min(h->num_sms, blocks_m * blocks_n);
+    ADSEL_TRY(begin_stage(h));
+    pairdist_tcgen05_kernel<<<grid, PD_THREADS, PD_SMEM, h->stream>>>(tmap, h->pd_norm.p, h->pd_d2.p, ld, blocks_m, blocks_n, k_blocks);
+    h->launches += 1;
+    ADSEL_CUDA(cudaGetLastError());
+    ADSEL_TRY(end_stage(h, 6));
+    return ADSEL_OK;
+}
+
+// ---- descriptors supplied by the caller (tests, feature-style inputs) ---------------------------
+__global__ void levels_norm_kernel(const uint16_t *__restrict__ levels, int n, int dim, int32_t *__restrict__ norm2) {
+    const int row = blockIdx.x;
+    int local = 0;
+    for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+        const int v = (int)__bfloat162float(__ushort_as_bfloat16(levels[(size_t)row * dim + c]));
+        local += v * v;
+    }
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s, local);
+    __syncthreads();
+    if (threadIdx.x == 0) norm2[row] = s;
+}
+
+int pairdist_set_descriptors(adsel_handle *h, const uint16_t *levels_host, int32_t n, int32_t dim) {
+    ADSEL_REQUIRE(levels_host && n > 0 && dim > 0, "adsel_pairdist_set_descriptors: null/empty argument");
+    h->bev_frames = n;
+    h->bev_cells = dim;
+    ADSEL_TRY(h->bev_levels.reserve((size_t)n * dim));
+    ADSEL_TRY(h->bev_norm2.reserve(n));
+    ADSEL_CUDA(cudaMemcpyAsync(h->bev_levels.p, levels_host, sizeof(uint16_t) * (size_t)n * dim, cudaMemcpyHostToDevice, h->stream));
+    levels_norm_kernel<<<n, 256, 0, h->stream>>>(h->bev_levels.p, n, dim, h->bev_norm2.p);
+    h->launches += 1;
+    ADSEL_CUDA(cudaGetLastError());
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    return ADSEL_OK;
+}
+
+// ---- dense greedy k-center over the rows of d2 (spatial_selector.py:101-138 loop on the BEV term) --
+constexpr int DG_THREADS = 1024;
+
+struct DenseArgs {
+    int n, ld;
+    const int32_t *d2, *n_boxes, *sampled;
+    int32_t *fps, *out;
+    unsigned char *is_selected;
+    double cost_b, cost_f, cost_start, budget;
+    int forbid_sampled, n_sampled, first_index, out_cap;
+    double *result;
+};
+
+struct BestI {
+    int v, i;
+};
+__device__ __forceinline__ BestI better_i(BestI a, BestI b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+
+__global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const DenseArgs a) {
+    __shared__ BestI warp_res[DG_THREADS / 32];
+    __shared__ int s_cur, s_stop, s_m;
+    __shared__ double s_cost;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_stop = 0;
+        s_m = 0;
+        s_cur = -1;
+        s_cost = a.cost_start;
+        if (a.n_sampled == 0) {
+            s_cur = a.first_index;
+            a.out[0] = s_cur;
+            s_m = 1;
+            a.is_selected[s_cur] = 1;
+            s_cost = __dadd_rn(s_cost, a.cost_f);
+            s_cost = __dadd_rn(s_cost, __dmul_rn((double)a.n_boxes[s_cur], a.cost_b));
+        }
+    }
+    if (a.forbid_sampled)
+        for (int t = threadIdx.x; t < a.n_sampled; t += DG_THREADS) a.is_selected[a.sampled[t]] = 1;
+    // fps = min over the rows of the frames already in the buffer (INT_MAX when there are none)
+    for (int j = threadIdx.x; j < a.n; j += DG_THREADS) {
+        int v = 0x7fffffff;
+        for (int t = 0; t < a.n_sampled; ++t) v = min(v, a.d2[(size_t)a.sampled[t] * a.ld + j]);
+        a.fps[j] = v;
+    }
+    __syncthreads();
+    long long steps = 0;
+    bool seeding = a.n_sampled > 0;
+    while (true) {
+        const int32_t *row = seeding ? nullptr : a.d2 + (size_t)s_cur * a.ld;
+        BestI x{-1, 0x7fffffff};
+        for (int j = threadIdx.x; j < a.n; j += DG_THREADS) {
+            int v = a.fps[j];
+            if (row) {
+                v = min(v, __ldcs(row + j));
+                a.fps[j] = v;
+            }
+            if (v > x.v) {          // ascending j per thread: strict '>' keeps the first maximum
+                x.v = v;
+                x.i = j;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            BestI y{__shfl_xor_sync(0xffffffffu, x.v, o), __shfl_xor_sync(0xffffffffu, x.i, o)};
+            x = better_i(x, y);
+        }
+        if (lane == 0) warp_res[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            BestI y = warp_res[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                BestI z{__shfl_xor_sync(0xffffffffu, y.v, o), __shfl_xor_sync(0xffffffffu, y.i, o)};
+                y = better_i(y, z);
+            }
+            if (lane == 0) {
+                const int nxt = y.i;
+                if (seeding) {
+                    a.out[0] = nxt;
+                    s_m = 1;
+                    a.is_selected[nxt] = 1;
+                    s_cost = __dadd_rn(s_cost, a.cost_f);
+                    s_cost = __dadd_rn(s_cost, __dmul_rn((double)a.n_boxes[nxt], a.cost_b));
+                    s_cur = nxt;
+                } else if (a.is_selected[nxt]) {
+                    a.result[1] = (double)ADSEL_ERR_RESELECTED;
+                    a.result[4] = (double)nxt;
+                    s_stop = 1;
+                } else {
+                    s_cost = __dadd_rn(s_cost, a.cost_f);
+                    s_cost = __dadd_rn(s_cost, __dmul_rn((double)a.n_boxes[nxt], a.cost_b));
+                    if (s_cost > a.budget) {
+                        s_stop = 1;
+                    } else if (s_m >= a.out_cap) {
+                        a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                        s_stop = 1;
+                    } else {
+                        a.out[s_m] = nxt;
+                        s_m += 1;
+                        a.is_selected[nxt] = 1;
+                        s_cur = nxt;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        ++steps;
+        if (seeding) {
+            seeding = false;
+            continue;
+        }
+        if (s_stop) break;
+    }
+    if (threadIdx.x == 0) {
+        a.result[0] = s_cost;
+        a.result[2] = (double)s_m;
+        a.result[3] = (double)steps;
+    }
+}
+
+int dense_select(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
+                 int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {
+    ADSEL_REQUIRE(h->pd_n > 0, "adsel_select_dense: call adsel_pairdist_build first");
+    ADSEL_REQUIRE(p && n_boxes_host && out_idx && out_m && out_cap > 0, "adsel_select_dense: null argument");
+    const int n = h->pd_n;
+    ADSEL_REQUIRE(n_sampled >= 0 && (n_sampled == 0 || sampled), "adsel_select_dense: bad sampled list");
+    ADSEL_REQUIRE(n_sampled > 0 || (first_index >= 0 && first_index < n), "adsel_select_dense: first_index out of range");
+    for (int i = 0; i < n_sampled; ++i) ADSEL_REQUIRE(sampled[i] >= 0 && sampled[i] < n, "adsel_select_dense: sampled index out of range");
+    ADSEL_TRY(h->pd_fps.reserve(n));
+    ADSEL_TRY(h->pd_boxes.reserve(n));
+    ADSEL_TRY(h->is_selected.reserve(n));
+    ADSEL_TRY(h->d_sampled.reserve(n_sampled > 0 ? n_sampled : 1));
+    ADSEL_TRY(h->d_out.reserve(out_cap));
+    ADSEL_TRY(h->d_result.reserve(8));
+    DenseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n;
+    a.ld = h->pd_ld;
+    a.d2 = h->pd_d2.p;
+    a.n_boxes = h->pd_boxes.p;
+    a.sampled = h->d_sampled.p;
+    a.fps = h->pd_fps.p;
+    a.out = h->d_out.p;
+    a.is_selected = h->is_selected.p;
+    a.cost_b = p->cost_b;
+    a.cost_f = p->cost_f;
+    a.cost_start = p->cost_start;
+    a.budget = p->budget;
+    a.forbid_sampled = p->forbid_sampled;
+    a.n_sampled = n_sampled;
+    a.first_index = first_index;
+    a.out_cap = out_cap;
+    a.result = h->d_result.p;
+    ADSEL_TRY(begin_stage(h));
+    ADSEL_CUDA(cudaMemcpyAsync(h->pd_boxes.p, n_boxes_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    if (n_sampled > 0)
+        ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyHostToDevice, h->stream));
+    ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, n, h->stream));
+    ADSEL_CUDA(cudaMemsetAsync(h->d_result.p, 0, sizeof(double) * 8, h->stream));
+    dense_greedy_kernel<<<1, DG_THREADS, 0, h->stream>>>(a);
+    h->launches += 1;
+    ADSEL_CUDA(cudaGetLastError());
+    double result[8];
+    ADSEL_CUDA(cudaMemcpyAsync(result, h->d_result.p, sizeof(result), cudaMemcpyDeviceToHost, h->stream));
+    ADSEL_TRY(end_stage(h, 7));
+    const int m = (int)result[2], status = (int)result[1];
+    h->last_steps = (int64_t)result[3];
+    if (m > 0) ADSEL_CUDA(cudaMemcpy(out_idx, h->d_out.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
+    *out_m = m;
+    if (out_cost) *out_cost = result[0];
+    if (status == ADSEL_ERR_RESELECTED) {
+        set_error("id: " + std::to_string((int)result[4]) + " has been selected");
+        return ADSEL_ERR_RESELECTED;
+    }
+    if (status == ADSEL_ERR_CAPACITY) {
+        set_error("adsel_select_dense: out_idx capacity exhausted");
+        return ADSEL_ERR_CAPACITY;
+    }
+    return ADSEL_OK;
+}
+
+}  // namespace adsel

@@ -60,6 +60,11 @@ _SIGNATURES = {
     "adsel_get_stage_ms": (ctypes.c_int, [_P, _P]),
     "adsel_get_counters": (ctypes.c_int, [_P, _P]),
     "adsel_exp_f64": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P]),
+    "adsel_pairdist_set_descriptors": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
+    "adsel_pairdist_build": (ctypes.c_int, [_P]),
+    "adsel_pairdist_get_rows": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P]),
+    "adsel_select_dense": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, _P, ctypes.c_int32, ctypes.c_int32, _P,
+                                          ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
     "adsel_bev_set_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32]),
     "adsel_bev_generate": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_uint64]),
     "adsel_bev_get_points": (ctypes.c_int, [_P, _P]),
@@ -242,6 +247,40 @@ class Handle:
         n2 = np.empty(self.bev_frames, dtype=np.int32)
         _check(load().adsel_bev_get_descriptors(self._h, _ptr(c), _ptr(lv), _ptr(n2), ctypes.byref(cells)))
         return c, lv, n2
+
+    # -- pairwise distances + dense greedy ------------------------------------------------------
+    def pairdist_set_descriptors(self, levels_bf16_bits):
+        lv = np.ascontiguousarray(levels_bf16_bits, dtype=np.uint16)
+        assert lv.ndim == 2
+        self.pd_n = lv.shape[0]
+        _check(load().adsel_pairdist_set_descriptors(self._h, _ptr(lv), lv.shape[0], lv.shape[1]))
+
+    def pairdist_build(self):
+        if getattr(self, "bev_frames", 0):
+            self.pd_n = self.bev_frames if not getattr(self, "pd_n", 0) else self.pd_n
+        _check(load().adsel_pairdist_build(self._h))
+
+    def pairdist_get_rows(self, row0, rows):
+        out = np.empty((rows, self.pd_n), dtype=np.int32)
+        _check(load().adsel_pairdist_get_rows(self._h, int(row0), int(rows), _ptr(out)))
+        return out
+
+    def select_dense(self, n_boxes, *, cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=0.0, forbid_sampled=True,
+                     sampled=(), first_index=-1, out_cap=None):
+        p = SelectParams(0, 0, 0, 0, 0.0, 0.0, 0.0, float(cost_b), float(cost_f), float(cost_start), float(budget),
+                         int(bool(forbid_sampled)), 0)
+        n_boxes = np.ascontiguousarray(n_boxes, dtype=np.int32)
+        sampled = np.ascontiguousarray(sampled, dtype=np.int32)
+        out_cap = len(n_boxes) if out_cap is None else out_cap
+        out = np.empty(out_cap, dtype=np.int32)
+        m, cost = ctypes.c_int32(0), ctypes.c_double(0.0)
+        status = load().adsel_select_dense(self._h, ctypes.byref(p), _ptr(n_boxes), _ptr(sampled) if len(sampled) else None,
+                                           len(sampled), int(first_index), _ptr(out), out_cap, ctypes.byref(m),
+                                           ctypes.byref(cost))
+        if status == ERR_RESELECTED:
+            raise AssertionError(load().adsel_last_error().decode())
+        _check(status)
+        return out[: m.value].tolist(), cost.value
 
     def stream_ptr(self) -> int:
         s = _P()

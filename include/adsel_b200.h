@@ -134,6 +134,22 @@ int adsel_bev_build(adsel_handle *h, const adsel_bev_params *p, int32_t aggregat
  * any pointer may be NULL; *cells receives ny*nx */
 int adsel_bev_get_descriptors(adsel_handle *h, int32_t *counts, uint16_t *levels, int32_t *norm2, int32_t *cells);
 
+/* ---- pairwise squared distances of the descriptors + dense greedy (north_star kernel 3; nearest
+ *      reference code: euclidean_spatial_selector.py:96, feature_selector.py:96-105, the unused
+ *      det3d/ops/distance/src/cdist_gpu.cu:31-50) -------------------------------------------------
+ * descriptors: bf16 bit patterns [n,dim] of integers 0..31 (adsel_bev_build leaves them on the device;
+ * adsel_pairdist_set_descriptors uploads caller-supplied ones). */
+int adsel_pairdist_set_descriptors(adsel_handle *h, const uint16_t *levels_bf16, int32_t n, int32_t dim);
+/* d2[i,j] = |x_i|^2 + |x_j|^2 - 2 x_i.x_j as exact int32, Gram tiles on tcgen05 (TMEM accumulators, TMA loads) */
+int adsel_pairdist_build(adsel_handle *h);
+/* read back rows [row0,row0+rows) of d2 as int32 [rows,n] (tests) */
+int adsel_pairdist_get_rows(adsel_handle *h, int32_t row0, int32_t rows, int32_t *out);
+/* greedy k-center over the rows of d2 with the reference's cost-budget loop (spatial_selector.py:101-138);
+ * only the cost fields and forbid_sampled of the params are used; n_boxes [n] host array. */
+int adsel_select_dense(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes, const int32_t *sampled,
+                       int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m,
+                       double *out_cost);
+
 /* ---- element-wise helpers (tests) ----------------------------------------------------------- */
 /* out[i] = exp(x[i]) with the arithmetic of numpy's AVX512_SKX float64 exp (np.exp in
  * spatial_temporal_selector.py:142-143); host buffers, computed on the device. */
