@@ -177,6 +177,59 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# BEV-descriptor configuration (BASELINE.json configs[1]/[2]: north_star kernels 1 and 3)
+# ------------------------------------------------------------------------------------------------
+def bev_extras(native, device, n_frames, n_boxes, first, peaks, reps=3, batch=2048, pts_per_frame=300_000):
+    """28,130 frames x ~300k points (10 sweeps): descriptor build streamed through HBM in batches of
+    `batch` frames (12 GB of points resident per batch, far larger than L2), then the tcgen05 distance
+    tiles over all descriptors and the dense greedy loop at budget 1200."""
+    import numpy as np
+    h = native.Handle(device)
+    out = {}
+    try:
+        sizes = pts_per_frame + (np.arange(n_frames, dtype=np.int64) * 977) % 4001 - 2000      # ragged frames
+        hist_ms, total_pts = [0.0] * (reps + 1), int(sizes.sum())
+        for rep in range(reps + 1):                                  # rep 0 = warm-up
+            for lo in range(0, n_frames, batch):
+                hi = min(n_frames, lo + batch)
+                off = np.concatenate([[0], np.cumsum(sizes[lo:hi])]).astype(np.int64)
+                h.bev_generate(off, n_sweeps=10, seed=20221107 + lo)  # synthetic LiDAR generated in HBM (untimed)
+                h.bev_build(frame_base=lo, total_frames=n_frames)
+                hist_ms[rep] += h.stage_ms()["bev_histogram"]
+        ms = sum(hist_ms[1:]) / reps
+        alg_bytes = 20.0 * total_pts + n_frames * (16384 * 6 + 4)    # 20 B/point read; counts+levels+norm written
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        out["bev_descriptor_build"] = {
+            "frames": n_frames, "points": total_pts, "ms": ms, "frames_per_s": n_frames / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "bev_histogram_kernel", "achieved": gbs, "peak": peaks["hbm"],
+                         "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": None}}
+        pd_ms = []
+        for rep in range(reps + 1):
+            h.pairdist_build()
+            pd_ms.append(h.stage_ms()["pairdist"])
+        ms_pd = sum(pd_ms[1:]) / reps
+        tf = 2.0 * n_frames * n_frames * 16384 / (ms_pd * 1e-3) / 1e12
+        out["pairdist_tiles"] = {
+            "n": n_frames, "dim": 16384, "ms": ms_pd,
+            "roofline": {"bound": "tensor", "kernel": "pairdist_tcgen05_kernel", "achieved": tf, "peak": peaks["bf16"],
+                         "unit": "TFLOP/s", "frac": tf / peaks["bf16"], "traffic": None,
+                         "peak_source": peaks["bf16_source"]}}
+        g_ms = []
+        for rep in range(reps + 1):
+            sel, _ = h.select_dense(n_boxes, budget=1200, first_index=first)
+            g_ms.append(h.stage_ms()["dense_greedy"])
+        ms_g = sum(g_ms[1:]) / reps
+        total = ms + ms_pd + ms_g
+        out["bev_selection_budget1200"] = {
+            "workload": "BevSpatialSelector/budget1200/%d frames x ~300k points" % n_frames, "selected_frames": len(sel),
+            "greedy_ms": ms_g, "us_per_step": ms_g * 1e3 / max(len(sel), 1), "ms_total": total,
+            "frames_per_s": n_frames / (total * 1e-3)}
+    finally:
+        h.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
@@ -295,6 +348,16 @@ def run_b200_arm(args):
                              f"numpy/scipy on a {os.cpu_count()}-core host; selected list identical: {cpu_sel == sel}"}
         h.close()
 
+        # ---- BEV-descriptor configuration: HBM-bound histogram and tensor-core distance tiles ----
+        extras = None
+        if rank == 0 and world == 1 and not args.no_bev:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+                os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            peaks = {"hbm": float(pk.get("hbm_gbs", 6650.0)), "bf16": float(pk.get("bf16_tflops", 1590.0)),
+                     "bf16_source": ("measured burst (MEASURED_PEAKS.json bf16_tflops): kernel timed alone"
+                                     if pk else "fallback (B200_PROFILING.md)")}
+            extras = bev_extras(native, local_rank, n, n_boxes, first, peaks)
+
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -334,6 +397,7 @@ def run_b200_arm(args):
             "e2e": {"value": world * n / e2e_sec, "unit": "frames/s", "ms_per_step": e2e_sec * 1e3,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clock_info,
+            "extras": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -349,6 +413,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--port", action="store_true", help="--impl reference: force the oracle port even if /root/reference exists")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bev", action="store_true", help="skip the BEV-descriptor extras (histogram / tcgen05 tiles)")
     args = ap.parse_args()
     logging.basicConfig(level=logging.WARNING)
     if args.impl == "reference":

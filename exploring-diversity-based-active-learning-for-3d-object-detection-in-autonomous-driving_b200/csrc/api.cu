@@ -29,7 +29,7 @@ int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *
 
 int bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_off_host, int32_t n_sweeps, uint64_t seed);
 int bev_set_points(adsel_handle *h, const float *pts_host, const int64_t *frame_off_host, int32_t n_frames);
-int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics);
+int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics, int32_t frame_base, int32_t total_frames);
 
 int pairdist_build(adsel_handle *h);
 int pairdist_set_descriptors(adsel_handle *h, const uint16_t *levels_host, int32_t n, int32_t dim);
@@ -240,16 +240,17 @@ int adsel_bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_o
 }
 
 int adsel_bev_get_points(adsel_handle *h, float *points) {
-    ADSEL_REQUIRE(h && points && h->bev_frames > 0, "adsel_bev_get_points: no points / null argument");
+    ADSEL_REQUIRE(h && points && h->bev_batch > 0, "adsel_bev_get_points: no points / null argument");
     ADSEL_CUDA(cudaSetDevice(h->device));
     ADSEL_CUDA(cudaMemcpy(points, h->bev_pts.p, sizeof(float) * 5 * (size_t)h->bev_points, cudaMemcpyDeviceToHost));
     return ADSEL_OK;
 }
 
-int adsel_bev_build(adsel_handle *h, const adsel_bev_params *p, int32_t aggregate_atomics) {
+int adsel_bev_build(adsel_handle *h, const adsel_bev_params *p, int32_t aggregate_atomics, int32_t frame_base,
+                    int32_t total_frames) {
     ADSEL_REQUIRE(h && p, "adsel_bev_build: null argument");
     ADSEL_CUDA(cudaSetDevice(h->device));
-    return bev_build(h, p, aggregate_atomics);
+    return bev_build(h, p, aggregate_atomics, frame_base, total_frames);
 }
 
 int adsel_bev_get_descriptors(adsel_handle *h, int32_t *counts, uint16_t *levels, int32_t *norm2, int32_t *cells) {

@@ -189,7 +189,7 @@ static int bev_grid_from_params(const adsel_bev_params *p, BevGrid *g) {
 int bev_layout(adsel_handle *h, int32_t n_frames, const int64_t *frame_off_host) {
     ADSEL_REQUIRE(n_frames > 0 && frame_off_host && frame_off_host[0] == 0, "adsel_bev: bad frame offsets");
     for (int f = 0; f < n_frames; ++f) ADSEL_REQUIRE(frame_off_host[f + 1] >= frame_off_host[f], "adsel_bev: offsets must be non-decreasing");
-    h->bev_frames = n_frames;
+    h->bev_batch = n_frames;
     h->bev_points = frame_off_host[n_frames];
     ADSEL_TRY(h->bev_off.reserve(n_frames + 1));
     ADSEL_TRY(h->bev_pts.reserve((size_t)h->bev_points * 5 + 4));
@@ -216,22 +216,36 @@ int bev_set_points(adsel_handle *h, const float *pts_host, const int64_t *frame_
     return ADSEL_OK;
 }
 
-int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics) {
-    ADSEL_REQUIRE(h->bev_frames > 0, "adsel_bev_build: no points (call adsel_bev_set_points / adsel_bev_generate)");
+// Descriptors of the current point batch are written at frame `frame_base` of a pool of
+// `total_frames` frames (a 28,130-frame pool at ~6 MB of points per frame is streamed through HBM in
+// batches; the descriptors of all batches stay resident).
+int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics, int32_t frame_base, int32_t total_frames) {
+    ADSEL_REQUIRE(h->bev_batch > 0, "adsel_bev_build: no points (call adsel_bev_set_points / adsel_bev_generate)");
+    if (total_frames <= 0) {
+        frame_base = 0;
+        total_frames = h->bev_batch;
+    }
+    ADSEL_REQUIRE(frame_base >= 0 && frame_base + h->bev_batch <= total_frames, "adsel_bev_build: batch does not fit the pool");
     BevGrid g;
     ADSEL_TRY(bev_grid_from_params(p, &g));
     const int cells = g.nx * g.ny;
+    ADSEL_REQUIRE(frame_base == 0 || (h->bev_cells == cells && h->bev_frames == total_frames),
+                  "adsel_bev_build: grid / pool size changed between batches");
     h->bev_cells = cells;
-    ADSEL_TRY(h->bev_counts.reserve((size_t)h->bev_frames * cells));
-    ADSEL_TRY(h->bev_levels.reserve((size_t)h->bev_frames * cells));
-    ADSEL_TRY(h->bev_norm2.reserve(h->bev_frames));
+    h->bev_frames = total_frames;
+    if (frame_base == 0) {
+        ADSEL_TRY(h->bev_counts.reserve((size_t)total_frames * cells));
+        ADSEL_TRY(h->bev_levels.reserve((size_t)total_frames * cells));
+        ADSEL_TRY(h->bev_norm2.reserve(total_frames));
+    }
     const size_t smem = (size_t)((cells + 3) & ~3) * sizeof(int) + (size_t)BEV_WARPS * CHUNK_VEC4 * sizeof(float4);
     auto kern = aggregate_atomics ? bev_histogram_kernel<true> : bev_histogram_kernel<false>;
     ADSEL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = min(h->bev_frames, 2 * h->num_sms);
+    const int grid = min(h->bev_batch, 2 * h->num_sms);
+    const size_t o = (size_t)frame_base * cells;
     ADSEL_TRY(begin_stage(h));
-    kern<<<grid, BEV_THREADS, smem, h->stream>>>(h->bev_pts.p, h->bev_off.p, h->bev_frames, g, h->bev_counts.p,
-                                                  reinterpret_cast<__nv_bfloat16 *>(h->bev_levels.p), h->bev_norm2.p);
+    kern<<<grid, BEV_THREADS, smem, h->stream>>>(h->bev_pts.p, h->bev_off.p, h->bev_batch, g, h->bev_counts.p + o,
+                                                  reinterpret_cast<__nv_bfloat16 *>(h->bev_levels.p) + o, h->bev_norm2.p + frame_base);
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     ADSEL_TRY(end_stage(h, 5));

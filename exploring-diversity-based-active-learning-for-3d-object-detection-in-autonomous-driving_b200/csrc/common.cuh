@@ -105,7 +105,7 @@ struct adsel_handle {
     double lists_max_spatial = 0.0;
 
     // BEV descriptors
-    int32_t bev_frames = 0, bev_cells = 0;
+    int32_t bev_frames = 0, bev_cells = 0, bev_batch = 0;   // pool frames, cells per frame, frames of the resident point batch
     int64_t bev_points = 0;
     adsel::DevBuf<float> bev_pts;
     adsel::DevBuf<int64_t> bev_off;

@@ -351,17 +351,23 @@ struct BestI {
 };
 __device__ __forceinline__ BestI better_i(BestI a, BestI b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
 
+// fps lives in registers (ITEMS columns per thread, column j = threadIdx.x + 1024*i), so a step is one
+// fully unrolled wave of independent streaming row loads (one memory latency) plus the arg-reduce.
+// ITEMS == 0: generic variant with fps in global memory for pools beyond 32,768 columns per GPU.
+template <int ITEMS>
 __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const DenseArgs a) {
     __shared__ BestI warp_res[DG_THREADS / 32];
     __shared__ int s_cur, s_stop, s_m;
     __shared__ double s_cost;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NREG = ITEMS > 0 ? ITEMS : 1;
+    int fps_reg[NREG];
     if (threadIdx.x == 0) {
         s_stop = 0;
         s_m = 0;
         s_cur = -1;
         s_cost = a.cost_start;
-        if (a.n_sampled == 0) {
+        if (a.n_sampled == 0) {   // empty buffer: the caller's random.choice, costed up front (spatial_selector.py:112-117)
             s_cur = a.first_index;
             a.out[0] = s_cur;
             s_m = 1;
@@ -373,10 +379,21 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
     if (a.forbid_sampled)
         for (int t = threadIdx.x; t < a.n_sampled; t += DG_THREADS) a.is_selected[a.sampled[t]] = 1;
     // fps = min over the rows of the frames already in the buffer (INT_MAX when there are none)
-    for (int j = threadIdx.x; j < a.n; j += DG_THREADS) {
-        int v = 0x7fffffff;
-        for (int t = 0; t < a.n_sampled; ++t) v = min(v, a.d2[(size_t)a.sampled[t] * a.ld + j]);
-        a.fps[j] = v;
+    if (ITEMS > 0) {
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) {
+            const int j = threadIdx.x + DG_THREADS * i;
+            int v = 0x7fffffff;
+            if (j < a.n)
+                for (int t = 0; t < a.n_sampled; ++t) v = min(v, a.d2[(size_t)a.sampled[t] * a.ld + j]);
+            fps_reg[i] = v;
+        }
+    } else {
+        for (int j = threadIdx.x; j < a.n; j += DG_THREADS) {
+            int v = 0x7fffffff;
+            for (int t = 0; t < a.n_sampled; ++t) v = min(v, a.d2[(size_t)a.sampled[t] * a.ld + j]);
+            a.fps[j] = v;
+        }
     }
     __syncthreads();
     long long steps = 0;
@@ -384,15 +401,33 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
     while (true) {
         const int32_t *row = seeding ? nullptr : a.d2 + (size_t)s_cur * a.ld;
         BestI x{-1, 0x7fffffff};
-        for (int j = threadIdx.x; j < a.n; j += DG_THREADS) {
-            int v = a.fps[j];
-            if (row) {
-                v = min(v, __ldcs(row + j));
-                a.fps[j] = v;
+        if (ITEMS > 0) {
+            int r[NREG];
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) {
+                const int j = threadIdx.x + DG_THREADS * i;
+                r[i] = (row && j < a.n) ? __ldcs(row + j) : 0x7fffffff;
             }
-            if (v > x.v) {          // ascending j per thread: strict '>' keeps the first maximum
-                x.v = v;
-                x.i = j;
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) {
+                const int j = threadIdx.x + DG_THREADS * i;
+                fps_reg[i] = min(fps_reg[i], r[i]);
+                if (j < a.n && fps_reg[i] > x.v) {      // ascending j per thread: strict '>' keeps the first maximum
+                    x.v = fps_reg[i];
+                    x.i = j;
+                }
+            }
+        } else {
+            for (int j = threadIdx.x; j < a.n; j += DG_THREADS) {
+                int v = a.fps[j];
+                if (row) {
+                    v = min(v, __ldcs(row + j));
+                    a.fps[j] = v;
+                }
+                if (v > x.v) {
+                    x.v = v;
+                    x.i = j;
+                }
             }
         }
 #pragma unroll
@@ -447,6 +482,13 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
         }
         if (s_stop) break;
     }
+    if (ITEMS > 0) {
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) {
+            const int j = threadIdx.x + DG_THREADS * i;
+            if (j < a.n) a.fps[j] = fps_reg[i];
+        }
+    }
     if (threadIdx.x == 0) {
         a.result[0] = s_cost;
         a.result[2] = (double)s_m;
@@ -493,7 +535,10 @@ int dense_select(adsel_handle *h, const adsel_select_params *p, const int32_t *n
         ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyHostToDevice, h->stream));
     ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, n, h->stream));
     ADSEL_CUDA(cudaMemsetAsync(h->d_result.p, 0, sizeof(double) * 8, h->stream));
-    dense_greedy_kernel<<<1, DG_THREADS, 0, h->stream>>>(a);
+    if (n <= 8 * DG_THREADS) dense_greedy_kernel<8><<<1, DG_THREADS, 0, h->stream>>>(a);
+    else if (n <= 16 * DG_THREADS) dense_greedy_kernel<16><<<1, DG_THREADS, 0, h->stream>>>(a);
+    else if (n <= 32 * DG_THREADS) dense_greedy_kernel<32><<<1, DG_THREADS, 0, h->stream>>>(a);
+    else dense_greedy_kernel<0><<<1, DG_THREADS, 0, h->stream>>>(a);
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     double result[8];

@@ -68,7 +68,7 @@ _SIGNATURES = {
     "adsel_bev_set_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32]),
     "adsel_bev_generate": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_uint64]),
     "adsel_bev_get_points": (ctypes.c_int, [_P, _P]),
-    "adsel_bev_build": (ctypes.c_int, [_P, ctypes.POINTER(BevParams), ctypes.c_int32]),
+    "adsel_bev_build": (ctypes.c_int, [_P, ctypes.POINTER(BevParams), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "adsel_bev_get_descriptors": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ctypes.c_int32)]),
 }
 _lib = None
@@ -222,12 +222,12 @@ class Handle:
         points = np.ascontiguousarray(points, dtype=np.float32)
         frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
         assert points.ndim == 2 and points.shape[1] == 5 and frame_off[-1] == len(points)
-        self.bev_frames, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
+        self.bev_batch, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
         _check(load().adsel_bev_set_points(self._h, _ptr(points), _ptr(frame_off), self.bev_frames))
 
     def bev_generate(self, frame_off, n_sweeps=10, seed=20221107):
         frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
-        self.bev_frames, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
+        self.bev_batch, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
         _check(load().adsel_bev_generate(self._h, self.bev_frames, _ptr(frame_off), n_sweeps, seed))
 
     def bev_get_points(self):
@@ -235,9 +235,14 @@ class Handle:
         _check(load().adsel_bev_get_points(self._h, _ptr(pts)))
         return pts
 
-    def bev_build(self, point_range=NUSC_RANGE, voxel=(0.8, 0.8, 8.0), aggregate_atomics=True):
+    def bev_build(self, point_range=NUSC_RANGE, voxel=(0.8, 0.8, 8.0), aggregate_atomics=False, frame_base=0,
+                  total_frames=0):
+        """Descriptors of the resident point batch -> frames [frame_base, frame_base+batch) of the pool."""
         p = BevParams((ctypes.c_float * 6)(*point_range), (ctypes.c_float * 3)(*voxel), 0)
-        _check(load().adsel_bev_build(self._h, ctypes.byref(p), int(bool(aggregate_atomics))))
+        _check(load().adsel_bev_build(self._h, ctypes.byref(p), int(bool(aggregate_atomics)), int(frame_base),
+                                      int(total_frames)))
+        self.bev_frames = int(total_frames) if total_frames > 0 else self.bev_batch
+        self.pd_n = self.bev_frames
 
     def bev_get_descriptors(self, counts=True, levels=True):
         cells = ctypes.c_int32(0)
@@ -256,8 +261,6 @@ class Handle:
         _check(load().adsel_pairdist_set_descriptors(self._h, _ptr(lv), lv.shape[0], lv.shape[1]))
 
     def pairdist_build(self):
-        if getattr(self, "bev_frames", 0):
-            self.pd_n = self.bev_frames if not getattr(self, "pd_n", 0) else self.pd_n
         _check(load().adsel_pairdist_build(self._h))
 
     def pairdist_get_rows(self, row0, rows):

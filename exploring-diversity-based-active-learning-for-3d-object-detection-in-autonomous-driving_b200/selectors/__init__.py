@@ -4,6 +4,7 @@ Only the data-only diversity selectors are provided; the detector-driven ones (f
 badge, ...) need a trained model and are out of this hot path's scope.
 """
 from .base_selector import BaseSelector
+from .bev_spatial_selector import BevSpatialSelector
 from .builder import build_selector
 from .euclidean_spatial_selector import EuSpatialSelector
 from .registry import SELECTORS
@@ -12,4 +13,4 @@ from .spatial_temporal_selector import SpatialTemporalSelector
 from .temporal_selector import TemporalSelector
 
 __all__ = ["BaseSelector", "SpatialSelector", "EuSpatialSelector", "TemporalSelector",
-           "SpatialTemporalSelector", "SELECTORS", "build_selector"]
+           "SpatialTemporalSelector", "BevSpatialSelector", "SELECTORS", "build_selector"]

@@ -132,3 +132,35 @@ def write_pool(spec: PoolSpec, out_dir: str, box_m: float = 1600.0) -> dict:
     with open(paths["buffer"], "w") as f:
         json.dump({"0": []}, f, indent=4)
     return paths
+
+
+def synthetic_lidar_points(index: int, n_points: int = 3000, seed: int = 7) -> np.ndarray:
+    """Deterministic multi-sweep-shaped points float32 [n_points,5] for frame ``index`` (tests)."""
+    rng = np.random.default_rng(seed * 1_000_003 + index)
+    ang = rng.uniform(0.0, 2.0 * np.pi, n_points)
+    rad = 1.5 + 68.5 * rng.random(n_points) ** 2
+    centre = 6.0 * np.array([np.cos(index * 0.7), np.sin(index * 1.3)])          # frame-dependent scene layout
+    pts = np.empty((n_points, 5), dtype=np.float32)
+    pts[:, 0] = rad * np.cos(ang) + centre[0] * (rng.random(n_points) < 0.3)
+    pts[:, 1] = rad * np.sin(ang) + centre[1] * (rng.random(n_points) < 0.3)
+    pts[:, 2] = -1.84 + rad * rng.uniform(-0.5, 0.2, n_points)
+    pts[:, 3] = rng.uniform(0, 255, n_points)
+    pts[:, 4] = 0.05 * rng.integers(0, 10, n_points)
+    return pts
+
+
+def write_lidar_files(infos, out_dir: str, n_points: int = 1500, nsweeps: int = 3, seed: int = 7) -> None:
+    """Write nuScenes-style ``.pcd.bin`` files (5 float32 per point) and fill ``lidar_path`` / ``sweeps``."""
+    os.makedirs(os.path.join(out_dir, "samples"), exist_ok=True)
+    os.makedirs(os.path.join(out_dir, "sweeps"), exist_ok=True)
+    for i, info in enumerate(infos):
+        pts = synthetic_lidar_points(i, n_points * nsweeps, seed)
+        info["lidar_path"] = f"samples/f{i:06d}.pcd.bin"
+        pts[:n_points].tofile(os.path.join(out_dir, info["lidar_path"]))
+        info["sweeps"] = []
+        for s in range(1, nsweeps):
+            path = f"sweeps/f{i:06d}_s{s}.pcd.bin"
+            pts[s * n_points:(s + 1) * n_points].tofile(os.path.join(out_dir, path))
+            tm = np.eye(4)
+            tm[:2, 3] = 0.3 * s, -0.2 * s
+            info["sweeps"].append({"lidar_path": path, "transform_matrix": tm, "time_lag": 0.05 * s})

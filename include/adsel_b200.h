@@ -128,8 +128,12 @@ int adsel_bev_set_points(adsel_handle *h, const float *points, const int64_t *fr
 /* synthetic multi-sweep LiDAR generated directly in HBM (counter-based hash keyed by frame/sweep) */
 int adsel_bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_off, int32_t n_sweeps, uint64_t seed);
 int adsel_bev_get_points(adsel_handle *h, float *points);
-/* histogram + density level + squared norm for every frame; aggregate_atomics: 1 = warp-aggregated */
-int adsel_bev_build(adsel_handle *h, const adsel_bev_params *p, int32_t aggregate_atomics);
+/* histogram + density level + squared norm for every frame of the resident point batch;
+ * aggregate_atomics: 1 = warp-aggregated shared atomics.  The batch's descriptors are written at frame
+ * `frame_base` of a pool of `total_frames` frames (total_frames <= 0: the batch is the whole pool), so a
+ * pool larger than HBM's share for points can be streamed batch by batch (first batch: frame_base 0). */
+int adsel_bev_build(adsel_handle *h, const adsel_bev_params *p, int32_t aggregate_atomics, int32_t frame_base,
+                    int32_t total_frames);
 /* read-backs: counts int32 [n_frames,cells], levels uint16 (bf16 bits) [n_frames,cells], norm2 int32 [n_frames];
  * any pointer may be NULL; *cells receives ny*nx */
 int adsel_bev_get_descriptors(adsel_handle *h, int32_t *counts, uint16_t *levels, int32_t *norm2, int32_t *cells);

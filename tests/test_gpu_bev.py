@@ -62,6 +62,23 @@ def test_other_grid(handle):
         handle.bev_build(voxel=(0.1, 0.1, 8.0))      # 1024x1024 cells do not fit the shared histogram
 
 
+def test_pool_streamed_in_batches(handle):
+    # descriptors of successive point batches land at their frame offset of one resident pool
+    sizes = 5000 + (np.arange(10) * 37) % 211
+    ref, all_pts = [], []
+    for b, (lo, hi) in enumerate([(0, 4), (4, 7), (7, 10)]):
+        off = np.concatenate([[0], np.cumsum(sizes[lo:hi])]).astype(np.int64)
+        handle.bev_generate(off, n_sweeps=2, seed=100 + b)
+        ref.append(B.bev_counts(handle.bev_get_points(), off))
+        handle.bev_build(frame_base=lo, total_frames=10)
+    counts, levels, norm2 = handle.bev_get_descriptors()
+    want = np.concatenate(ref)
+    assert np.array_equal(counts, want)
+    assert np.array_equal(norm2, (B.density_levels(want).astype(np.int64) ** 2).sum(1))
+    with pytest.raises(native.NativeError):
+        handle.bev_build(frame_base=9, total_frames=10)      # batch of 3 does not fit at frame 9
+
+
 def test_full_size_frames_conservation(handle):
     # BASELINE-sized frames (10 sweeps x ~30k returns), compared against numpy on the downloaded points
     sizes = 300_000 + (np.arange(6) * 977) % 4001 - 2000

@@ -88,7 +88,6 @@ def test_bev_to_selection_pipeline(handle):
     ref_counts = B.bev_counts(pts, off)
     assert np.array_equal(counts, ref_counts)
     lv = B.density_levels(ref_counts)
-    handle.pd_n = 0
     handle.pairdist_build()
     d2 = B.sq_distance_matrix(lv, lv)
     assert np.array_equal(handle.pairdist_get_rows(0, len(sizes)).astype(np.int64), d2)
@@ -96,3 +95,40 @@ def test_bev_to_selection_pipeline(handle):
     ref = R.greedy_select(lambda i: d2[i].astype(np.float64), len(sizes), n_boxes, [], 11, "60", forbid_sampled=True)
     got, _ = handle.select_dense(n_boxes, budget=60, first_index=11)
     assert got == ref
+
+
+def test_bev_spatial_selector_drop_in(pools, tmp_path):
+    """Registry-level use: files on disk -> multi-sweep load -> descriptors -> distances -> selection."""
+    import json
+    import pickle
+    import random
+    from adsel_b200 import synthetic
+    from adsel_b200.selectors import build_selector
+    from adsel_b200.selectors.bev_spatial_selector import load_multisweep_points
+    pl = pools("P300")
+    infos = [dict(i) for i in pl["infos"]]
+    synthetic.write_lidar_files(infos, str(tmp_path), n_points=1200, nsweeps=3)
+    infos_file = str(tmp_path / "infos.pkl")
+    pickle.dump(infos, open(infos_file, "wb"), protocol=2)
+    buf = str(tmp_path / "buffer.json")
+    json.dump({"0": []}, open(buf, "w"))
+    res = {}
+    for budget in (40, 40):
+        random.seed(3407)
+        sel = build_selector(dict(type="BevSpatialSelector", budget=budget, buffer_file=buf, infos_origin=infos_file,
+                                  data_root=str(tmp_path), nsweeps=3, batch_frames=128))
+        sel.select_samples(local_rank=0)
+        sel.dump_file()
+        res.update(sel.get_selected_samples())
+    # oracle pipeline on the same files
+    frames = [load_multisweep_points(i, str(tmp_path), 3) for i in infos]
+    off = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    lv = B.density_levels(B.bev_counts(np.concatenate(frames), off))
+    d2 = B.sq_distance_matrix(lv, lv).astype(np.float64)
+    n_boxes = np.array([i["gt_names"].shape[0] for i in infos])
+    random.seed(3407)
+    first = random.choice(range(len(infos)))
+    r1 = R.greedy_select(lambda i: d2[i], len(infos), n_boxes, [], first, "40", forbid_sampled=True)
+    r2 = R.greedy_select(lambda i: d2[i], len(infos), n_boxes, r1, -1, "80", forbid_sampled=True)
+    assert res == {"40": r1, "80": r1 + r2}
+    assert json.load(open(buf)) == {"0": [], "40": r1, "80": r1 + r2}
