@@ -223,12 +223,12 @@ class Handle:
         frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
         assert points.ndim == 2 and points.shape[1] == 5 and frame_off[-1] == len(points)
         self.bev_batch, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
-        _check(load().adsel_bev_set_points(self._h, _ptr(points), _ptr(frame_off), self.bev_frames))
+        _check(load().adsel_bev_set_points(self._h, _ptr(points), _ptr(frame_off), self.bev_batch))
 
     def bev_generate(self, frame_off, n_sweeps=10, seed=20221107):
         frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
         self.bev_batch, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
-        _check(load().adsel_bev_generate(self._h, self.bev_frames, _ptr(frame_off), n_sweeps, seed))
+        _check(load().adsel_bev_generate(self._h, self.bev_batch, _ptr(frame_off), n_sweeps, seed))
 
     def bev_get_points(self):
         pts = np.empty((self.bev_points, 5), dtype=np.float32)
