@@ -22,6 +22,23 @@ int end_stage(adsel_handle *h, int stage) {
 }
 
 int build_knn_graph(adsel_handle *h, int32_t k);
+int build_knn_graph_sharded(adsel_handle *h, int32_t k);
+void update_shard(adsel_handle *h);
+int knn_prepare(adsel_handle *h, int32_t k, bool own_tables);
+int greedy_prepare(adsel_handle *h, const adsel_select_params *p, int32_t n_sampled, int32_t out_cap);
+void comm_destroy(adsel_handle *h);
+int greedy_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
+                                int32_t first_index, int32_t out_cap);
+int greedy_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
+
+static int refresh_nnz(adsel_handle *h) {
+    if (h->nnz >= 0) return ADSEL_OK;
+    int32_t nnz32 = 0;
+    ADSEL_CUDA(cudaMemcpyAsync(&nnz32, h->row_ptr.p + h->n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    h->nnz = nnz32;
+    return ADSEL_OK;
+}
 int geodesic_rows(adsel_handle *h, const int32_t *sources, int32_t m, double radius, double *out_host);
 int geodesic_max_finite(adsel_handle *h, double *out);
 int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
@@ -78,12 +95,13 @@ int adsel_destroy(adsel_handle *h) {
     if (!h) return ADSEL_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    comm_destroy(h);
     h->loc.release(); h->group_id.release(); h->n_boxes.release(); h->group_ptr.release(); h->group_members.release();
     h->knn_idx.release(); h->knn_dist.release(); h->row_ptr.release(); h->col.release(); h->deg_own.release();
     h->deg_rev.release(); h->w.release();
     h->sc_dist.release(); h->sc_stamp.release(); h->sc_q0.release(); h->sc_q1.release(); h->sc_touched.release();
     h->list_off.release(); h->list_len.release(); h->list_idx.release(); h->list_val.release(); h->cursor.release();
-    h->fps.release(); h->blk_val.release(); h->blk_idx.release(); h->is_selected.release(); h->tlut.release();
+    h->fps.release(); h->frame_rec.release(); h->is_selected.release(); h->tlut.release();
     h->d_sampled.release(); h->d_out.release(); h->d_result.release();
     h->pd_d2.release(); h->pd_norm.release(); h->pd_fps.release(); h->pd_boxes.release();
     h->bev_pts.release(); h->bev_off.release(); h->bev_counts.release(); h->bev_norm2.release(); h->bev_levels.release();
@@ -143,8 +161,13 @@ int adsel_set_pool(adsel_handle *h, int32_t n, const double *loc_xy, const int32
         std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
         for (int i = 0; i < n; ++i) members[fill[group_id[i]]++] = i;
     }
+    h->max_group = 0;
+    for (int g = 0; g < n_groups; ++g) h->max_group = ptr[g + 1] - ptr[g] > h->max_group ? ptr[g + 1] - ptr[g] : h->max_group;
+    h->groups_contiguous = true;   // consecutive runs: frames sorted by group are already in index order
+    for (int i = 0; i < n; ++i) h->groups_contiguous = h->groups_contiguous && members[i] == i;
     h->n = n;
     h->n_groups = n_groups;
+    update_shard(h);
     h->graph_ready = false;
     h->lists_mode = -1;
     ADSEL_TRY(h->loc.reserve(n));
@@ -171,14 +194,16 @@ int adsel_get_knn(adsel_handle *h, int32_t *knn_idx, double *knn_dist) {
     ADSEL_REQUIRE(h && h->graph_ready && knn_idx && knn_dist, "adsel_get_knn: graph not built / null argument");
     ADSEL_CUDA(cudaSetDevice(h->device));
     const size_t cells = (size_t)h->n * (h->k + 1);
-    ADSEL_CUDA(cudaMemcpy(knn_idx, h->knn_idx.p, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost));
-    ADSEL_CUDA(cudaMemcpy(knn_dist, h->knn_dist.p, sizeof(double) * cells, cudaMemcpyDeviceToHost));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    ADSEL_CUDA(cudaMemcpy(knn_idx, h->knn_idx_p, sizeof(int32_t) * cells, cudaMemcpyDeviceToHost));
+    ADSEL_CUDA(cudaMemcpy(knn_dist, h->knn_dist_p, sizeof(double) * cells, cudaMemcpyDeviceToHost));
     return ADSEL_OK;
 }
 
 int adsel_get_csr(adsel_handle *h, int32_t *row_ptr, int32_t *col, double *w, int64_t *nnz) {
     ADSEL_REQUIRE(h && h->graph_ready && nnz, "adsel_get_csr: graph not built / null argument");
     ADSEL_CUDA(cudaSetDevice(h->device));
+    ADSEL_TRY(refresh_nnz(h));
     *nnz = h->nnz;
     if (row_ptr) ADSEL_CUDA(cudaMemcpy(row_ptr, h->row_ptr.p, sizeof(int32_t) * (h->n + 1), cudaMemcpyDeviceToHost));
     if (col) ADSEL_CUDA(cudaMemcpy(col, h->col.p, sizeof(int32_t) * h->nnz, cudaMemcpyDeviceToHost));
@@ -205,6 +230,42 @@ int adsel_select(adsel_handle *h, const adsel_select_params *p, const int32_t *s
     return greedy_select(h, p, sampled, n_sampled, first_index, out_idx, out_cap, out_m, out_cost);
 }
 
+int adsel_build_knn_graph_sharded(adsel_handle *h, int32_t k) {
+    ADSEL_REQUIRE(h, "adsel_build_knn_graph_sharded: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return build_knn_graph_sharded(h, k);
+}
+
+int adsel_shard_prepare(adsel_handle *h, int32_t k, const adsel_select_params *p, int32_t n_sampled, int32_t out_cap) {
+    ADSEL_REQUIRE(h && p && h->n > 0 && out_cap > 0, "adsel_shard_prepare: set the pool first / null argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    if (p->spatial == ADSEL_SPATIAL_GEODESIC) ADSEL_TRY(knn_prepare(h, k, false));
+    ADSEL_TRY(greedy_prepare(h, p, n_sampled, out_cap));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    return ADSEL_OK;
+}
+
+int adsel_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
+                               int32_t first_index, int32_t out_cap) {
+    ADSEL_REQUIRE(h, "adsel_select_sharded_begin: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return greedy_select_sharded_begin(h, p, sampled, n_sampled, first_index, out_cap);
+}
+
+int adsel_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {
+    ADSEL_REQUIRE(h, "adsel_select_sharded_end: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    if (h->knn_pending_timing) {   // the graph build enqueued before this selection has completed by now
+        h->knn_pending_timing = false;
+        ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        ADSEL_CUDA(cudaEventElapsedTime(&ms, h->knn_ev[0], h->knn_ev[1]));
+        h->stage_ms[0] = ms;
+        h->stage_ms[1] = 0.f;
+    }
+    return greedy_select_sharded_end(h, out_idx, out_cap, out_m, out_cost);
+}
+
 int adsel_get_fps(adsel_handle *h, double *fps) {
     ADSEL_REQUIRE(h && fps && h->fps.p, "adsel_get_fps: no selection has run");
     ADSEL_CUDA(cudaSetDevice(h->device));
@@ -220,6 +281,10 @@ int adsel_get_stage_ms(adsel_handle *h, float *ms8) {
 
 int adsel_get_counters(adsel_handle *h, int64_t *c4) {
     ADSEL_REQUIRE(h && c4, "adsel_get_counters: null argument");
+    if (h->graph_ready) {
+        ADSEL_CUDA(cudaSetDevice(h->device));
+        ADSEL_TRY(refresh_nnz(h));
+    }
     c4[0] = h->launches;
     c4[1] = h->last_steps;
     c4[2] = h->list_total;

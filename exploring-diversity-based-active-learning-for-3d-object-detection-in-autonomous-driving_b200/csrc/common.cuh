@@ -64,6 +64,23 @@ struct DevBuf {
 
 }  // namespace adsel
 
+namespace adsel {
+// Everything the greedy kernel needs about the frame it just selected, fetched in one round trip.
+struct __align__(16) FrameRec {
+    long long list_off;   // neighbour list of this frame (entries inside this rank's column slice)
+    int list_len;
+    int e0, e1;           // its temporal group as a range of group_members
+    int n_boxes;
+    double box_cost;      // n_boxes * cost_b, rounded once (the reference's per-frame product)
+};
+
+// Parameters the precombined neighbour-list values depend on (lists are rebuilt when any changes).
+struct ListsKey {
+    int norm_mode = -1, temporal = 0, aggregate = 0, lo = 0, hi = 0, pad = 0;
+    double max_spatial = 0.0, max_temporal = 0.0, lambda_t = 0.0;
+};
+}  // namespace adsel
+
 struct adsel_handle {
     int device = 0;
     int num_sms = 0;
@@ -78,7 +95,7 @@ struct adsel_handle {
     adsel::DevBuf<double2> loc;
     adsel::DevBuf<int32_t> group_id, n_boxes;
     adsel::DevBuf<int32_t> group_ptr, group_members;   // CSR of frames by group (ascending index)
-    int32_t n_groups = 0;
+    int32_t n_groups = 0, max_group = 0;                  // number of groups, size of the largest
 
     // kNN + CSR graph
     int32_t k = 0;
@@ -101,8 +118,9 @@ struct adsel_handle {
     adsel::DevBuf<double> list_val;
     adsel::DevBuf<unsigned long long> cursor;   // [0] entries reserved, [1] max finite bits
     int64_t list_total = 0;
-    int lists_mode = -1;                         // normalize mode the lists were built for
-    double lists_max_spatial = 0.0;
+    long long list_capacity = 0;
+    int lists_mode = -1;                         // normalize mode the lists were built for (-1: none)
+    adsel::ListsKey lists_key;
 
     // BEV descriptors
     int32_t bev_frames = 0, bev_cells = 0, bev_batch = 0;   // pool frames, cells per frame, frames of the resident point batch
@@ -118,12 +136,33 @@ struct adsel_handle {
 
     // greedy state
     adsel::DevBuf<unsigned long long> fps;       // ordered-u64 view of non-negative doubles
-    adsel::DevBuf<unsigned long long> blk_val;
-    adsel::DevBuf<int32_t> blk_idx;
+    adsel::DevBuf<adsel::FrameRec> frame_rec;    // per-frame record read once per greedy step
     adsel::DevBuf<unsigned char> is_selected;
     adsel::DevBuf<double> tlut;
     adsel::DevBuf<int32_t> d_sampled, d_out;
-    adsel::DevBuf<double> d_result;              // [0] cost, [1] status, [2] m, [3] steps
+    adsel::DevBuf<double> d_result;              // [0] cost, [1] status, [2] m, [3] steps, [4] offending frame
+    bool groups_contiguous = false;              // every group is one contiguous index range (consecutive runs)
+
+    // pool sharding across ranks (comm.cu): this rank owns frames [shard_lo, shard_hi)
+    int32_t rank = 0, world = 1;
+    int32_t shard_lo = 0, shard_hi = 0;
+    unsigned char *arena = nullptr;              // peer-visible allocation: mailbox | kNN tables | descriptors
+    size_t arena_bytes = 0;
+    int32_t arena_n = 0, arena_k1 = 0, arena_dim = 0;
+    bool knn_pending_timing = false;             // ev[0..1] bracket an enqueued sharded graph build
+    unsigned char *peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool peer_ipc[8] = {false, false, false, false, false, false, false, false};   // opened with cudaIpcOpenMemHandle
+    bool comm_ready = false;
+    unsigned comm_seq = 0;                       // tag of the last completed exchange
+    unsigned long long comm_barrier_seq = 0;
+    double comm_timeout_s = 20.0;
+    int32_t *knn_idx_p = nullptr;                // kNN table in use: own buffers or the arena's (sharded build)
+    double *knn_dist_p = nullptr;
+    // pending sharded selection (begin/end split so several ranks can be driven from one host thread)
+    bool pending = false;
+    int32_t pending_cap = 0;
+    cudaEvent_t pending_ev[2] = {nullptr, nullptr};
+    cudaEvent_t knn_ev[2] = {nullptr, nullptr};
 };
 
 namespace adsel {

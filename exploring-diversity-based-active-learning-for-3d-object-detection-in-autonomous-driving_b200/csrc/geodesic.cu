@@ -135,12 +135,24 @@ geodesic_rows_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restr
     if (max_finite_bits && threadIdx.x == 0) atomicMax(max_finite_bits, blk_max);
 }
 
-// Neighbour lists: for every source the vertices with d < radius and their NORMALISED spatial
-// value (spatial_temporal_selector.py:138-144 applied to the row).  Lists are appended to one
-// pool through a global cursor; `count_only` sizes the pool on a first pass.
+// Neighbour lists: for every source the vertices with d < radius that fall in this rank's column slice
+// [lo, hi), each with the FINAL row value distance_map[src][v]: the normalised spatial term
+// (spatial_temporal_selector.py:138-144) already aggregated with the temporal term of the pair
+// (:131-133,148-155), so that a greedy step needs no further lookups.  Lists are appended to one pool
+// through a global cursor; entries beyond `capacity` are counted but not written (the greedy kernel
+// sees cursor > capacity and reports it; the host grows the pool and reruns).
+struct ListArgs {
+    int n, lo, hi;
+    double radius;
+    int norm_mode, temporal, aggregate;
+    double divisor, lambda_t, t_far;
+    const int32_t *group_id;
+    const double *tlut;
+};
+
 __global__ void __launch_bounds__(SSSP_THREADS)
 geodesic_lists_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const double *__restrict__ w,
-                      int n, double radius, int norm_mode, double divisor,
+                      const ListArgs la,
                       unsigned long long *sc_dist, int32_t *sc_stamp, int32_t *sc_q0, int32_t *sc_q1, int32_t *sc_touched,
                       unsigned long long *__restrict__ cursor, long long capacity,
                       int64_t *__restrict__ list_off, int32_t *__restrict__ list_len,
@@ -149,6 +161,8 @@ geodesic_lists_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__rest
     __shared__ int n_keep, n_written;
     __shared__ unsigned long long base_off;
     if (threadIdx.x == 0) sh.tag = 0;
+    const int n = la.n;
+    const double radius = la.radius;
     const SsspScratch sc = scratch_of(sc_dist, sc_stamp, sc_q0, sc_q1, sc_touched, (size_t)n);
     __syncthreads();
     for (int src = blockIdx.x; src < n; src += gridDim.x) {
@@ -161,27 +175,34 @@ geodesic_lists_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__rest
         __syncthreads();
         int mine = 0;
         for (int t = threadIdx.x; t < nt; t += SSSP_THREADS) {
-            const double d = __longlong_as_double((long long)__ldcg(&sc.dist[sc.touched[t]]));
-            mine += d < radius ? 1 : 0;
+            const int v = sc.touched[t];
+            const double d = __longlong_as_double((long long)__ldcg(&sc.dist[v]));
+            mine += (d < radius && v >= la.lo && v < la.hi) ? 1 : 0;
         }
         if (mine) atomicAdd(&n_keep, mine);
         __syncthreads();
         if (threadIdx.x == 0) base_off = atomicAdd(cursor, (unsigned long long)n_keep);
         __syncthreads();
         const bool fits = (long long)(base_off + n_keep) <= capacity;
+        const int gsrc = la.temporal ? la.group_id[src] : 0;
         for (int t = threadIdx.x; t < nt; t += SSSP_THREADS) {
             const int v = sc.touched[t];
             const double d = __longlong_as_double((long long)__ldcg(&sc.dist[v]));
-            if (d < radius && fits) {
+            if (d < radius && v >= la.lo && v < la.hi && fits) {
                 const int pos = atomicAdd(&n_written, 1);
+                double val = normalize_value(d, la.norm_mode, la.divisor);
+                if (la.temporal) {
+                    const double tv = la.group_id[v] == gsrc ? la.tlut[abs(v - src)] : la.t_far;
+                    val = aggregate_value(val, tv, la.aggregate, la.lambda_t);
+                }
                 list_idx[base_off + pos] = v;
-                list_val[base_off + pos] = normalize_value(d, norm_mode, divisor);
+                list_val[base_off + pos] = val;
             }
             sc.dist[v] = INF_BITS;
         }
         if (threadIdx.x == 0) {
             list_off[src] = (int64_t)base_off;
-            list_len[src] = n_keep;
+            list_len[src] = fits ? n_keep : 0;
         }
         __syncthreads();
     }
@@ -254,45 +275,78 @@ int geodesic_max_finite(adsel_handle *h, double *out) {
     return ADSEL_OK;
 }
 
-// Builds (or reuses) the neighbour lists for `norm_mode`; radius is 38 for exp, inf otherwise.
-int build_lists(adsel_handle *h, int norm_mode, double max_spatial) {
-    ADSEL_REQUIRE(h->graph_ready, "adsel_select: call adsel_build_knn_graph first");
-    if (h->lists_mode == norm_mode && (norm_mode != ADSEL_NORM_LINEAR || h->lists_max_spatial == max_spatial)) return ADSEL_OK;
-    const double inf = host_inf();
-    const double radius = norm_mode == ADSEL_NORM_EXP ? 38.0 : inf;
+// Allocations of the list build (scratch, offsets, entry pool); never shrinks.
+int lists_prepare(adsel_handle *h) {
     const int n = h->n;
     ADSEL_TRY(ensure_scratch(h));
     ADSEL_TRY(h->cursor.reserve(2));
     ADSEL_TRY(h->list_off.reserve(n));
     ADSEL_TRY(h->list_len.reserve(n));
-    ADSEL_TRY(begin_stage(h));
-    long long capacity = (long long)h->list_idx.cap;
-    if (capacity < (long long)n * 64) {
-        capacity = (long long)n * 64;
+    if (h->list_capacity < (long long)n * 64) {
+        const long long capacity = (long long)n * 64;
         ADSEL_TRY(h->list_idx.reserve(capacity));
         ADSEL_TRY(h->list_val.reserve(capacity));
+        h->list_capacity = capacity;
     }
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        ADSEL_TRY(clear_stamps(h));
-        ADSEL_CUDA(cudaMemsetAsync(h->cursor.p, 0, 2 * sizeof(unsigned long long), h->stream));
-        geodesic_lists_kernel<<<min(h->sssp_ctas, n), SSSP_THREADS, 0, h->stream>>>(
-            h->row_ptr.p, h->col.p, h->w.p, n, radius, norm_mode, max_spatial, h->sc_dist.p, h->sc_stamp.p, h->sc_q0.p,
-            h->sc_q1.p, h->sc_touched.p, h->cursor.p, capacity, h->list_off.p, h->list_len.p, h->list_idx.p, h->list_val.p);
-        h->launches += 1;
-        ADSEL_CUDA(cudaGetLastError());
-        unsigned long long total = 0;
-        ADSEL_CUDA(cudaMemcpyAsync(&total, h->cursor.p, sizeof(total), cudaMemcpyDeviceToHost, h->stream));
-        ADSEL_CUDA(cudaStreamSynchronize(h->stream));
-        h->list_total = (int64_t)total;
-        if ((long long)total <= capacity) break;
-        ADSEL_REQUIRE(attempt == 0, "adsel_select: neighbour-list pool overflow after resize");
-        capacity = (long long)total;
-        ADSEL_TRY(h->list_idx.reserve(capacity));
-        ADSEL_TRY(h->list_val.reserve(capacity));
-    }
-    ADSEL_TRY(end_stage(h, 2));
-    h->lists_mode = norm_mode;
-    h->lists_max_spatial = max_spatial;
+    return ADSEL_OK;
+}
+
+int grow_lists(adsel_handle *h, long long needed) {
+    ADSEL_REQUIRE(needed > h->list_capacity, "adsel_select: neighbour-list pool overflow after resize");
+    const long long capacity = needed + needed / 16;
+    ADSEL_TRY(h->list_idx.reserve(capacity));
+    ADSEL_TRY(h->list_val.reserve(capacity));
+    h->list_capacity = capacity;
+    h->lists_mode = -1;
+    return ADSEL_OK;
+}
+
+// Enqueues the neighbour-list build for these selection parameters unless the resident lists were
+// built for the same ones; radius is 38 for exp, inf otherwise.  h->tlut must already be enqueued.
+int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, int lo, int hi) {
+    ADSEL_REQUIRE(h->graph_ready, "adsel_select: call adsel_build_knn_graph first");
+    ListsKey key;
+    key.norm_mode = p->normalize;
+    key.temporal = p->temporal ? 1 : 0;
+    key.aggregate = key.temporal ? p->aggregate : 0;
+    key.lo = lo;
+    key.hi = hi;
+    key.max_spatial = p->normalize == ADSEL_NORM_LINEAR ? p->max_spatial : 0.0;
+    key.max_temporal = (key.temporal && p->normalize == ADSEL_NORM_LINEAR) ? p->max_temporal : 0.0;
+    key.lambda_t = (key.temporal && p->aggregate == ADSEL_AGG_SUM) ? p->lambda_t : 0.0;
+    if (h->lists_mode >= 0 && memcmp(&key, &h->lists_key, sizeof(key)) == 0) return ADSEL_OK;
+    const int n = h->n;
+    ADSEL_TRY(lists_prepare(h));
+    ListArgs la;
+    la.n = n;
+    la.lo = lo;
+    la.hi = hi;
+    la.radius = p->normalize == ADSEL_NORM_EXP ? 38.0 : host_inf();
+    la.norm_mode = p->normalize;
+    la.temporal = key.temporal;
+    la.aggregate = p->aggregate;
+    la.divisor = p->max_spatial;
+    la.lambda_t = p->lambda_t;
+    la.t_far = t_far;
+    la.group_id = h->group_id.p;
+    la.tlut = h->tlut.p;
+    ADSEL_TRY(clear_stamps(h));
+    ADSEL_CUDA(cudaMemsetAsync(h->cursor.p, 0, 2 * sizeof(unsigned long long), h->stream));
+    geodesic_lists_kernel<<<min(h->sssp_ctas, n), SSSP_THREADS, 0, h->stream>>>(
+        h->row_ptr.p, h->col.p, h->w.p, la, h->sc_dist.p, h->sc_stamp.p, h->sc_q0.p, h->sc_q1.p, h->sc_touched.p,
+        h->cursor.p, h->list_capacity, h->list_off.p, h->list_len.p, h->list_idx.p, h->list_val.p);
+    h->launches += 1;
+    ADSEL_CUDA(cudaGetLastError());
+    h->lists_mode = p->normalize;
+    h->lists_key = key;
+    return ADSEL_OK;
+}
+
+int geodesic_preload() {
+    cudaFuncAttributes attr;
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, geodesic_lists_kernel));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, geodesic_rows_kernel));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, fill_u64_kernel));
     return ADSEL_OK;
 }
 

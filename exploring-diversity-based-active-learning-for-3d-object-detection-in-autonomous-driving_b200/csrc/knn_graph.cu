@@ -18,13 +18,21 @@ constexpr int KNN_TILE = 1024;   // candidates staged per shared-memory tile (16
 // Each thread keeps its K1 = k+1 best (d2, idx) sorted ascending in registers.
 // SPLIT > 1: SPLIT consecutive threads share one query and scan interleaved candidate tiles; their
 // partial lists are merged through shared memory (used when n is too small to fill the GPU).
+// Destination tables of the kNN rows: one per rank.  In the sharded build every rank computes the rows
+// of its own slice [q_lo, q_hi) and stores them straight into every rank's table (peer memory over
+// NVLink): the all-gather of the kNN table is fused into the kernel's epilogue.
+struct KnnOut {
+    int world;
+    int32_t *idx[8];
+    double *dist[8];
+};
+
 template <int K1>
 __global__ void __launch_bounds__(KNN_THREADS)
-knn_bruteforce_kernel(const double2 *__restrict__ loc, int n, int32_t *__restrict__ out_idx,
-                      double *__restrict__ out_dist) {
+knn_bruteforce_kernel(const double2 *__restrict__ loc, int n, int q_lo, int q_hi, const KnnOut out) {
     __shared__ double2 tile[KNN_TILE];
-    const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
-    const double2 me = loc[q < n ? q : n - 1];
+    const int q = q_lo + blockIdx.x * KNN_THREADS + threadIdx.x;
+    const double2 me = loc[q < q_hi ? q : q_hi - 1];
     double best_d[K1];
     int best_i[K1];
 #pragma unroll
@@ -60,22 +68,27 @@ knn_bruteforce_kernel(const double2 *__restrict__ loc, int n, int32_t *__restric
             }
         }
     }
-    if (q < n) {
+    if (q < q_hi) {
 #pragma unroll
-        for (int s = 0; s < K1; ++s) {
-            out_idx[(size_t)q * K1 + s] = best_i[s];
-            out_dist[(size_t)q * K1 + s] = __dsqrt_rn(best_d[s]);
+        for (int s = 0; s < K1; ++s) best_d[s] = __dsqrt_rn(best_d[s]);
+        for (int wdst = 0; wdst < out.world; ++wdst) {
+            int32_t *oi = out.idx[wdst] + (size_t)q * K1;
+            double *od = out.dist[wdst] + (size_t)q * K1;
+#pragma unroll
+            for (int s = 0; s < K1; ++s) {
+                oi[s] = best_i[s];
+                od[s] = best_d[s];
+            }
         }
     }
 }
 
 // Generic k (K1 up to 64) with the running list in local memory; same ordering contract.
 __global__ void __launch_bounds__(KNN_THREADS)
-knn_bruteforce_generic_kernel(const double2 *__restrict__ loc, int n, int k1, int32_t *__restrict__ out_idx,
-                              double *__restrict__ out_dist) {
+knn_bruteforce_generic_kernel(const double2 *__restrict__ loc, int n, int q_lo, int q_hi, int k1, const KnnOut out) {
     __shared__ double2 tile[KNN_TILE];
-    const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
-    const double2 me = loc[q < n ? q : n - 1];
+    const int q = q_lo + blockIdx.x * KNN_THREADS + threadIdx.x;
+    const double2 me = loc[q < q_hi ? q : q_hi - 1];
     double best_d[64];
     int best_i[64];
     for (int s = 0; s < k1; ++s) {
@@ -103,10 +116,12 @@ knn_bruteforce_generic_kernel(const double2 *__restrict__ loc, int n, int k1, in
             }
         }
     }
-    if (q < n) {
-        for (int s = 0; s < k1; ++s) {
-            out_idx[(size_t)q * k1 + s] = best_i[s];
-            out_dist[(size_t)q * k1 + s] = __dsqrt_rn(best_d[s]);
+    if (q < q_hi) {
+        for (int wdst = 0; wdst < out.world; ++wdst) {
+            for (int s = 0; s < k1; ++s) {
+                out.idx[wdst][(size_t)q * k1 + s] = best_i[s];
+                out.dist[wdst][(size_t)q * k1 + s] = __dsqrt_rn(best_d[s]);
+            }
         }
     }
 }
@@ -197,58 +212,125 @@ __global__ void fill_edges_kernel(const int32_t *__restrict__ knn_idx, const dou
 }
 
 template <int K1>
-static void launch_knn(adsel_handle *h) {
-    const int grid = (h->n + KNN_THREADS - 1) / KNN_THREADS;
-    knn_bruteforce_kernel<K1><<<grid, KNN_THREADS, 0, h->stream>>>(h->loc.p, h->n, h->knn_idx.p, h->knn_dist.p);
+static void launch_knn(adsel_handle *h, int q_lo, int q_hi, const KnnOut &out) {
+    const int grid = (q_hi - q_lo + KNN_THREADS - 1) / KNN_THREADS;
+    knn_bruteforce_kernel<K1><<<grid, KNN_THREADS, 0, h->stream>>>(h->loc.p, h->n, q_lo, q_hi, out);
+}
+
+static void enqueue_knn(adsel_handle *h, int k1, int q_lo, int q_hi, const KnnOut &out) {
+    if (q_hi <= q_lo) return;
+    switch (k1) {
+        case 9: launch_knn<9>(h, q_lo, q_hi, out); break;
+        case 5: launch_knn<5>(h, q_lo, q_hi, out); break;
+        case 17: launch_knn<17>(h, q_lo, q_hi, out); break;
+        default: {
+            const int grid = (q_hi - q_lo + KNN_THREADS - 1) / KNN_THREADS;
+            knn_bruteforce_generic_kernel<<<grid, KNN_THREADS, 0, h->stream>>>(h->loc.p, h->n, q_lo, q_hi, k1, out);
+        }
+    }
+    h->launches += 1;
+}
+
+// count -> scan -> fill on the kNN table in use.  col/w are sized for the worst case (every table entry an
+// edge in both directions) so that no host read-back sits between the kernels.
+static int enqueue_csr(adsel_handle *h) {
+    const int n = h->n, k1 = h->k + 1;
+    ADSEL_CUDA(cudaMemsetAsync(h->deg_own.p, 0, sizeof(int32_t) * n, h->stream));
+    ADSEL_CUDA(cudaMemsetAsync(h->deg_rev.p, 0, sizeof(int32_t) * 2 * n, h->stream));
+    const int threads = 256, blocks = (int)(((size_t)n * k1 + threads - 1) / threads);
+    count_edges_kernel<<<blocks, threads, 0, h->stream>>>(h->knn_idx_p, h->knn_dist_p, n, k1, h->deg_own.p, h->deg_rev.p);
+    scan_degrees_kernel<<<1, 1024, 0, h->stream>>>(h->deg_own.p, h->deg_rev.p, n, h->row_ptr.p);
+    fill_edges_kernel<<<blocks, threads, 0, h->stream>>>(h->knn_idx_p, h->knn_dist_p, n, k1, h->row_ptr.p, h->deg_own.p,
+                                                         h->deg_rev.p + n, h->col.p, h->w.p);
+    h->launches += 3;
+    ADSEL_CUDA(cudaGetLastError());
+    h->nnz = -1;   // read back lazily (adsel_get_csr / adsel_get_counters)
+    return ADSEL_OK;
+}
+
+int knn_prepare(adsel_handle *h, int32_t k, bool own_tables) {
+    ADSEL_REQUIRE(h->n > 0, "adsel_build_knn_graph: call adsel_set_pool first");
+    ADSEL_REQUIRE(k >= 1 && k + 1 <= 64 && k + 1 <= h->n, "adsel_build_knn_graph: need 1 <= k < min(n, 64)");
+    const int n = h->n, k1 = k + 1;
+    if (own_tables) {
+        ADSEL_TRY(h->knn_idx.reserve((size_t)n * k1));
+        ADSEL_TRY(h->knn_dist.reserve((size_t)n * k1));
+    }
+    ADSEL_TRY(h->row_ptr.reserve(n + 1));
+    ADSEL_TRY(h->deg_own.reserve(n));
+    ADSEL_TRY(h->deg_rev.reserve(2 * (size_t)n));   // [0,n) reverse counts, [n,2n) fill cursors
+    ADSEL_TRY(h->col.reserve(2 * (size_t)n * k1));
+    ADSEL_TRY(h->w.reserve(2 * (size_t)n * k1));
+    return ADSEL_OK;
 }
 
 int build_knn_graph(adsel_handle *h, int32_t k) {
-    ADSEL_REQUIRE(h->n > 0, "adsel_build_knn_graph: call adsel_set_pool first");
-    ADSEL_REQUIRE(k >= 1 && k + 1 <= 64 && k + 1 <= h->n, "adsel_build_knn_graph: need 1 <= k < min(n, 64)");
+    ADSEL_TRY(knn_prepare(h, k, true));
     const int n = h->n, k1 = k + 1;
     h->k = k;
     h->graph_ready = false;
     h->lists_mode = -1;
-    ADSEL_TRY(h->knn_idx.reserve((size_t)n * k1));
-    ADSEL_TRY(h->knn_dist.reserve((size_t)n * k1));
-    ADSEL_TRY(h->row_ptr.reserve(n + 1));
-    ADSEL_TRY(h->deg_own.reserve(n));
-    ADSEL_TRY(h->deg_rev.reserve(2 * (size_t)n));   // [0,n) reverse counts, [n,2n) fill cursors
-
+    h->knn_idx_p = h->knn_idx.p;
+    h->knn_dist_p = h->knn_dist.p;
+    KnnOut out;
+    memset(&out, 0, sizeof(out));
+    out.world = 1;
+    out.idx[0] = h->knn_idx_p;
+    out.dist[0] = h->knn_dist_p;
     ADSEL_TRY(begin_stage(h));
-    switch (k1) {
-        case 9: launch_knn<9>(h); break;
-        case 5: launch_knn<5>(h); break;
-        case 17: launch_knn<17>(h); break;
-        default: {
-            const int grid = (n + KNN_THREADS - 1) / KNN_THREADS;
-            knn_bruteforce_generic_kernel<<<grid, KNN_THREADS, 0, h->stream>>>(h->loc.p, n, k1, h->knn_idx.p, h->knn_dist.p);
-        }
-    }
-    h->launches += 1;
+    enqueue_knn(h, k1, 0, n, out);
     ADSEL_CUDA(cudaGetLastError());
     ADSEL_TRY(end_stage(h, 0));
-
     ADSEL_TRY(begin_stage(h));
-    ADSEL_CUDA(cudaMemsetAsync(h->deg_own.p, 0, sizeof(int32_t) * n, h->stream));
-    ADSEL_CUDA(cudaMemsetAsync(h->deg_rev.p, 0, sizeof(int32_t) * 2 * n, h->stream));
-    const int threads = 256, blocks = (int)(((size_t)n * k1 + threads - 1) / threads);
-    count_edges_kernel<<<blocks, threads, 0, h->stream>>>(h->knn_idx.p, h->knn_dist.p, n, k1, h->deg_own.p, h->deg_rev.p);
-    scan_degrees_kernel<<<1, 1024, 0, h->stream>>>(h->deg_own.p, h->deg_rev.p, n, h->row_ptr.p);
-    h->launches += 2;
-    ADSEL_CUDA(cudaGetLastError());
-    int32_t nnz32 = 0;
-    ADSEL_CUDA(cudaMemcpyAsync(&nnz32, h->row_ptr.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
-    h->nnz = nnz32;
-    ADSEL_TRY(h->col.reserve((size_t)nnz32 + 1));
-    ADSEL_TRY(h->w.reserve((size_t)nnz32 + 1));
-    fill_edges_kernel<<<blocks, threads, 0, h->stream>>>(h->knn_idx.p, h->knn_dist.p, n, k1, h->row_ptr.p, h->deg_own.p,
-                                                         h->deg_rev.p + n, h->col.p, h->w.p);
-    h->launches += 1;
-    ADSEL_CUDA(cudaGetLastError());
+    ADSEL_TRY(enqueue_csr(h));
     ADSEL_TRY(end_stage(h, 1));
     h->graph_ready = true;
+    return ADSEL_OK;
+}
+
+int32_t *arena_knn_idx(adsel_handle *h, int w);
+double *arena_knn_dist(adsel_handle *h, int w);
+int comm_barrier(adsel_handle *h);
+
+// Sharded build (enqueue only): this rank's kNN rows -> every rank's table, device barrier, CSR.
+int build_knn_graph_sharded(adsel_handle *h, int32_t k) {
+    ADSEL_REQUIRE(h->comm_ready, "adsel_build_knn_graph_sharded: call adsel_comm_init / adsel_comm_attach first");
+    ADSEL_REQUIRE(h->arena_n == h->n && h->arena_k1 == k + 1, "adsel_build_knn_graph_sharded: arena was sized for another n / k");
+    ADSEL_TRY(knn_prepare(h, k, false));
+    const int k1 = k + 1;
+    h->k = k;
+    h->graph_ready = false;
+    h->lists_mode = -1;
+    h->knn_idx_p = arena_knn_idx(h, h->rank);
+    h->knn_dist_p = arena_knn_dist(h, h->rank);
+    KnnOut out;
+    memset(&out, 0, sizeof(out));
+    out.world = h->world;
+    for (int w = 0; w < h->world; ++w) {
+        out.idx[w] = arena_knn_idx(h, w);
+        out.dist[w] = arena_knn_dist(h, w);
+    }
+    ADSEL_CUDA(cudaEventRecord(h->knn_ev[0], h->stream));
+    enqueue_knn(h, k1, h->shard_lo, h->shard_hi, out);
+    ADSEL_CUDA(cudaGetLastError());
+    ADSEL_TRY(comm_barrier(h));      // every rank's rows have landed in this rank's table
+    ADSEL_TRY(enqueue_csr(h));
+    ADSEL_TRY(comm_barrier(h));      // nobody overwrites a table (next build) while a peer still reads its copy
+    ADSEL_CUDA(cudaEventRecord(h->knn_ev[1], h->stream));
+    h->knn_pending_timing = true;
+    h->graph_ready = true;
+    return ADSEL_OK;
+}
+
+int knn_preload() {
+    cudaFuncAttributes attr;
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, knn_bruteforce_kernel<9>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, knn_bruteforce_kernel<5>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, knn_bruteforce_kernel<17>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, knn_bruteforce_generic_kernel));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, count_edges_kernel));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, scan_degrees_kernel));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, fill_edges_kernel));
     return ADSEL_OK;
 }
 

@@ -560,4 +560,11 @@ int dense_select(adsel_handle *h, const adsel_select_params *p, const int32_t *n
     return ADSEL_OK;
 }
 
+int dense_preload() {
+    cudaFuncAttributes attr;
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, pairdist_tcgen05_kernel));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, levels_norm_kernel));
+    return ADSEL_OK;
+}
+
 }  // namespace adsel

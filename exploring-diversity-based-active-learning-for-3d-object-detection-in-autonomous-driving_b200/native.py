@@ -10,7 +10,8 @@ import numpy as np
 
 from . import build as _build
 
-OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_RESELECTED = 0, -1, -2, -3, -4
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_RESELECTED, ERR_COMM, ERR_PEER_ABORT = 0, -1, -2, -3, -4, -5, -6
+IPC_HANDLE_BYTES = 64
 SPATIAL = {"none": 0, "geodesic": 1, "euclid": 2}
 NORMALIZE = {"raw": 0, "exp": 1, "linear": 2}
 AGGREGATE = {"sum": 0, "min": 1, "max": 2}
@@ -21,6 +22,10 @@ class NativeError(RuntimeError):
         super().__init__(f"adsel_b200 native call failed (status {status}): {message}")
         self.status = status
         self.message = message
+
+
+class RetrySharded(NativeError):
+    """A rank's neighbour-list pool was too small (it has been grown): every rank repeats begin/end."""
 
 
 class BevParams(ctypes.Structure):
@@ -65,6 +70,19 @@ _SIGNATURES = {
     "adsel_pairdist_get_rows": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P]),
     "adsel_select_dense": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, _P, ctypes.c_int32, ctypes.c_int32, _P,
                                           ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
+    "adsel_comm_init": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),
+    "adsel_comm_attach": (ctypes.c_int, [_P, _P]),
+    "adsel_comm_attach_local": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
+    "adsel_comm_set_timeout": (ctypes.c_int, [_P, ctypes.c_double]),
+    "adsel_comm_barrier": (ctypes.c_int, [_P]),
+    "adsel_comm_check": (ctypes.c_int, [_P]),
+    "adsel_shard_range": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
+    "adsel_shard_prepare": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.POINTER(SelectParams), ctypes.c_int32, ctypes.c_int32]),
+    "adsel_build_knn_graph_sharded": (ctypes.c_int, [_P, ctypes.c_int32]),
+    "adsel_select_sharded_begin": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.c_int32]),
+    "adsel_select_sharded_end": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                                ctypes.POINTER(ctypes.c_double)]),
     "adsel_bev_set_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32]),
     "adsel_bev_generate": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_uint64]),
     "adsel_bev_get_points": (ctypes.c_int, [_P, _P]),
@@ -196,6 +214,79 @@ class Handle:
         if status == ERR_RESELECTED:
             # the reference's AssertionError (spatial_temporal_selector.py:182), same message
             raise AssertionError(load().adsel_last_error().decode())
+        _check(status)
+        return out[: m.value].tolist(), cost.value
+
+    # -- pool sharded over several ranks ---------------------------------------
+    def comm_init(self, rank, world, n, k=8, dim=0) -> bytes:
+        """Allocate the peer-visible arena; returns this rank's 64-byte CUDA IPC handle."""
+        out = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+        _check(load().adsel_comm_init(self._h, int(rank), int(world), int(n), int(k), int(dim), out))
+        self.rank, self.world = int(rank), int(world)
+        return out.raw
+
+    def comm_attach(self, ipc_handles):
+        """``ipc_handles``: the world's handles in rank order (other processes on the same box)."""
+        blob = b"".join(ipc_handles)
+        assert len(blob) == IPC_HANDLE_BYTES * self.world
+        _check(load().adsel_comm_attach(self._h, ctypes.c_char_p(blob)))
+
+    def comm_attach_local(self, handles):
+        """``handles``: the world's ``Handle`` objects of THIS process in rank order."""
+        arr = (_P * len(handles))(*[h._h for h in handles])
+        _check(load().adsel_comm_attach_local(self._h, arr))
+
+    def comm_set_timeout(self, seconds):
+        _check(load().adsel_comm_set_timeout(self._h, float(seconds)))
+
+    def comm_barrier(self):
+        _check(load().adsel_comm_barrier(self._h))
+
+    def comm_check(self):
+        _check(load().adsel_comm_check(self._h))
+
+    def shard_range(self):
+        lo, hi = ctypes.c_int32(0), ctypes.c_int32(0)
+        _check(load().adsel_shard_range(self._h, ctypes.byref(lo), ctypes.byref(hi)))
+        return lo.value, hi.value
+
+    def build_knn_graph_sharded(self, k: int = 8):
+        self.k = k
+        _check(load().adsel_build_knn_graph_sharded(self._h, k))
+
+    @staticmethod
+    def _select_params(spatial, temporal, normalize, aggregate, lambda_t, max_spatial, max_temporal, cost_b, cost_f,
+                       cost_start, budget, forbid_sampled):
+        return SelectParams(SPATIAL[spatial], int(bool(temporal)), NORMALIZE[normalize], AGGREGATE[aggregate],
+                            float(lambda_t), float(max_spatial), float(max_temporal), float(cost_b), float(cost_f),
+                            float(cost_start), float(budget), int(bool(forbid_sampled)), 0)
+
+    def shard_prepare(self, k=8, n_sampled=0, out_cap=None, **kw):
+        p = self._select_params(kw.get("spatial", "geodesic"), kw.get("temporal", True), kw.get("normalize", "exp"),
+                                kw.get("aggregate", "sum"), 1.0, 0.0, 0.0, 0.04, 0.12, 0.0, 0.0, False)
+        _check(load().adsel_shard_prepare(self._h, int(k), ctypes.byref(p), int(n_sampled),
+                                          self.n if out_cap is None else int(out_cap)))
+
+    def select_sharded_begin(self, *, spatial, temporal, normalize, aggregate="sum", lambda_t=1.0, max_spatial=0.0,
+                             max_temporal=0.0, cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=0.0,
+                             forbid_sampled=False, sampled=(), first_index=-1, out_cap=None):
+        p = self._select_params(spatial, temporal, normalize, aggregate, lambda_t, max_spatial, max_temporal, cost_b,
+                                cost_f, cost_start, budget, forbid_sampled)
+        sampled = np.ascontiguousarray(sampled, dtype=np.int32)
+        self._out_cap = self.n if out_cap is None else int(out_cap)
+        _check(load().adsel_select_sharded_begin(self._h, ctypes.byref(p), _ptr(sampled) if len(sampled) else None,
+                                                 len(sampled), int(first_index), self._out_cap))
+
+    def select_sharded_end(self):
+        """Returns ``(selected, cost)``; raises ``RetrySharded`` when every rank must call begin/end again."""
+        out = np.empty(self._out_cap, dtype=np.int32)
+        m, cost = ctypes.c_int32(0), ctypes.c_double(0.0)
+        status = load().adsel_select_sharded_end(self._h, _ptr(out), self._out_cap, ctypes.byref(m), ctypes.byref(cost))
+        if status == ERR_RESELECTED:
+            raise AssertionError(load().adsel_last_error().decode())
+        message = load().adsel_last_error().decode() if status != OK else ""
+        if status == ERR_PEER_ABORT or (status == ERR_CAPACITY and "neighbour-list" in message):
+            raise RetrySharded(status, message)
         _check(status)
         return out[: m.value].tolist(), cost.value
 

@@ -5,7 +5,7 @@ from typing import Optional
 
 import numpy as np
 
-from .. import native, pool
+from .. import pool, sharded
 from ..fileio import load
 from .base_selector import BaseSelector
 from .registry import SELECTORS
@@ -31,7 +31,7 @@ class EuSpatialSelector(BaseSelector):
         extent = float(np.hypot(*(locations.max(0) - locations.min(0))))
         if not extent < 1e6:
             raise NotImplementedError("ego locations span >= 1e6 m: exceeds the reference's cross-city margin")
-        handle = native.Handle(self._device_index(kwargs))
+        handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's shard
         try:
             handle.set_pool(locations, city, pool.box_counts(infos))
             self._run_greedy(handle, spatial="euclid", temporal=False, normalize="raw", forbid_sampled=True)

@@ -2,7 +2,7 @@
 import logging
 from typing import Optional
 
-from .. import native, pool
+from .. import pool, sharded
 from ..fileio import load
 from .base_selector import BaseSelector
 from .registry import SELECTORS
@@ -30,7 +30,7 @@ class SpatialSelector(BaseSelector):
             if nm not in known:
                 raise KeyError(nm)
         run_id, _ = pool.consecutive_runs(names)
-        handle = native.Handle(self._device_index(kwargs))
+        handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's shard
         try:
             handle.set_pool(pool.ego_locations(infos), run_id, pool.box_counts(infos))
             handle.build_knn_graph(self.k)

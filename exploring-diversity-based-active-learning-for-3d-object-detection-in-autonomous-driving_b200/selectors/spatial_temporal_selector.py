@@ -7,7 +7,7 @@ sm_100a library through ``native.Handle``.
 import logging
 from typing import Optional
 
-from .. import native, pool
+from .. import pool, sharded
 from ..fileio import load
 from .base_selector import BaseSelector
 from .registry import SELECTORS
@@ -46,7 +46,7 @@ class SpatialTemporalSelector(BaseSelector):
                 raise KeyError(nm)
         locations = pool.ego_locations(infos)             # :83-91
         run_id, max_td = pool.consecutive_runs(names)     # :114-129
-        handle = native.Handle(self._device_index(kwargs))
+        handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's shard
         try:
             handle.set_pool(locations, run_id, pool.box_counts(infos))
             handle.build_knn_graph(self.k)                # :93-101 (+ scipy's dense->CSR rules)

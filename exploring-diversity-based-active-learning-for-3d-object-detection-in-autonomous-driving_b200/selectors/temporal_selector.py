@@ -5,7 +5,7 @@ from typing import Optional
 
 import numpy as np
 
-from .. import native, pool
+from .. import pool, sharded
 from .base_selector import BaseSelector
 from .registry import SELECTORS
 
@@ -21,7 +21,7 @@ class TemporalSelector(BaseSelector):
     def select_samples(self, **kwargs) -> None:
         infos = self.infos_origin
         groups = pool.name_groups(pool.logfile_names(infos))     # :50-55
-        handle = native.Handle(self._device_index(kwargs))
+        handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's shard
         try:
             handle.set_pool(np.zeros((len(infos), 2)), groups, pool.box_counts(infos))   # no ego pose in this selector
             self._run_greedy(handle, spatial="none", temporal=True, normalize="raw", forbid_sampled=True)

@@ -1,0 +1,224 @@
+"""Pool sharded over the GPUs of one NVSwitch box.
+
+The reference has no multi-GPU selection: under ``torch.distributed.launch`` every rank recomputes the
+whole selection and rank 0 writes (det3d/selectors/base_selector.py:57, tools/active_select.py:94-101).
+Here every rank owns a contiguous slice of the pool's columns.  All data-path communication happens
+inside the CUDA kernels over peer-mapped memory (kNN rows stored into every rank's table, one
+``(value, index)`` mailbox exchange per greedy step); ``torch.distributed`` is used only to hand the
+64-byte CUDA IPC handles around once.
+
+Two drivers with the interface of ``native.Handle`` (``set_pool``, ``build_knn_graph``,
+``geodesic_max_finite``, ``select``, ``stage_ms``, ``counters``, ``close``):
+
+* ``DistWorld``  -- one process per GPU (``torchrun``); what the selectors use when
+  ``torch.distributed`` is initialised with more than one rank.
+* ``LocalWorld`` -- all ranks driven by ONE host thread, on one device or several; used by the tests
+  (the exchange protocol runs unchanged between CTAs of one GPU) and for single-process multi-GPU.
+"""
+import os
+
+import numpy as np
+
+from . import native
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Frames ``[lo, hi)`` owned by ``rank``: contiguous, 256-aligned slices (mirrors csrc/comm.cu:update_shard)."""
+    if world <= 1:
+        return 0, n
+    per = -(-n // world)
+    per = -(-per // 256) * 256
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def pick_global_best(records):
+    """The exchange's reduction rule on the host: ``records`` = ``[(value_key, index), ...]`` per rank ->
+    the record with the largest key, lowest index among equal keys (np.argmax's first maximum)."""
+    best = None
+    for key, idx in records:
+        if best is None or key > best[0] or (key == best[0] and idx < best[1]):
+            best = (key, idx)
+    return best
+
+
+class _WorldBase:
+    MAX_RETRIES = 4
+
+    def __init__(self):
+        self.n = 0
+        self.k = 0
+        self._pool = None
+        self._arena_shape = None
+
+    def set_pool(self, loc_xy, group_id, n_boxes):
+        self._pool = (np.ascontiguousarray(loc_xy, dtype=np.float64), np.ascontiguousarray(group_id, dtype=np.int32),
+                      np.ascontiguousarray(n_boxes, dtype=np.int32))
+        self.n = len(self._pool[0])
+        self._pool_dirty = True
+
+
+class LocalWorld(_WorldBase):
+    """``world`` ranks of this process; ``devices[r]`` is rank r's CUDA device (default: all on device 0)."""
+
+    def __init__(self, world: int, devices=None, timeout: float = 20.0):
+        super().__init__()
+        self.world = int(world)
+        devices = [0] * self.world if devices is None else list(devices)
+        assert len(devices) == self.world
+        self.handles = [native.Handle(d) for d in devices]
+        self.timeout = timeout
+
+    def close(self):
+        for h in self.handles:
+            h.close()
+        self.handles = []
+
+    def _ensure(self, k: int, dim: int = 0):
+        shape = (self.n, int(k), int(dim))
+        if self._arena_shape != shape:
+            for r, h in enumerate(self.handles):
+                h.comm_init(r, self.world, self.n, k, dim)
+                h.comm_set_timeout(self.timeout)
+            for h in self.handles:
+                h.comm_attach_local(self.handles)
+            self._arena_shape = shape
+            self._pool_dirty = True
+        if self._pool_dirty:
+            for h in self.handles:
+                h.set_pool(*self._pool)
+            self._pool_dirty = False
+
+    def shard_ranges(self):
+        return [h.shard_range() for h in self.handles]
+
+    def build_knn_graph(self, k: int = 8):
+        self.k = k
+        self._ensure(k)
+        for h in self.handles:       # allocations first: none may happen while a rank's kernel waits for its peers
+            h.shard_prepare(k=k)
+        for h in self.handles:
+            h.build_knn_graph_sharded(k)
+        for h in self.handles:
+            h.comm_check()
+
+    def geodesic_max_finite(self) -> float:
+        vals = [h.geodesic_max_finite() for h in self.handles]
+        assert all(v == vals[0] for v in vals)
+        return vals[0]
+
+    def select(self, **kw):
+        self._ensure(self.k)
+        sampled = kw.get("sampled", ())
+        prep = {key: kw[key] for key in ("spatial", "temporal", "normalize", "aggregate") if key in kw}
+        for _ in range(self.MAX_RETRIES):
+            for h in self.handles:
+                h.shard_prepare(k=max(self.k, 1), n_sampled=len(sampled), out_cap=kw.get("out_cap"), **prep)
+            for h in self.handles:
+                h.select_sharded_begin(**kw)
+            results, retry, error = [], False, None
+            for h in self.handles:   # every rank is collected even if one raises (their kernels are all in flight)
+                try:
+                    results.append(h.select_sharded_end())
+                except native.RetrySharded:
+                    retry = True
+                except (AssertionError, native.NativeError) as e:
+                    error = error or e
+            if error is not None and not retry:
+                raise error
+            if retry:
+                continue
+            assert all(r == results[0] for r in results), "ranks disagree on the selection"
+            return results[0]
+        raise native.NativeError(native.ERR_CAPACITY, "sharded selection kept overflowing its neighbour-list pools")
+
+    def get_fps(self):
+        """The min-distance vector assembled from every rank's slice."""
+        out = np.empty(self.n, dtype=np.float64)
+        for h in self.handles:
+            lo, hi = h.shard_range()
+            out[lo:hi] = h.get_fps()[lo:hi]
+        return out
+
+    def stage_ms(self):
+        return self.handles[0].stage_ms()
+
+    def counters(self):
+        c = self.handles[0].counters()
+        c["launches"] = sum(h.counters()["launches"] for h in self.handles)
+        return c
+
+
+class DistWorld(_WorldBase):
+    """This process's rank of a ``torch.distributed`` world whose ranks all sit on one NVSwitch box."""
+
+    def __init__(self, device: int, group=None, timeout: float = 20.0):
+        super().__init__()
+        import torch.distributed as dist
+        assert dist.is_available() and dist.is_initialized(), "DistWorld needs an initialised torch.distributed"
+        self._dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("the sharded path spans one 8-GPU NVSwitch box (world <= 8); set ADSEL_SHARD=0 for replicas")
+        self.handle = native.Handle(device)
+        self.device = device
+        self.timeout = timeout
+
+    def close(self):
+        if self.handle is not None:
+            self.handle.close()
+            self.handle = None
+
+    def _ensure(self, k: int, dim: int = 0):
+        shape = (self.n, int(k), int(dim))
+        if self._arena_shape != shape:
+            ipc = self.handle.comm_init(self.rank, self.world, self.n, k, dim)
+            self.handle.comm_set_timeout(self.timeout)
+            gathered = [None] * self.world
+            self._dist.all_gather_object(gathered, ipc, group=self.group)   # 64 bytes per rank, once per pool shape
+            self.handle.comm_attach(gathered)
+            self._arena_shape = shape
+            self._pool_dirty = True
+        if self._pool_dirty:
+            self.handle.set_pool(*self._pool)
+            self._pool_dirty = False
+
+    def shard_range(self):
+        return self.handle.shard_range()
+
+    def build_knn_graph(self, k: int = 8):
+        self.k = k
+        self._ensure(k)
+        self.handle.build_knn_graph_sharded(k)
+
+    def geodesic_max_finite(self) -> float:
+        return self.handle.geodesic_max_finite()
+
+    def select(self, **kw):
+        self._ensure(self.k)
+        for _ in range(self.MAX_RETRIES):
+            self.handle.select_sharded_begin(**kw)
+            try:
+                return self.handle.select_sharded_end()
+            except native.RetrySharded:      # raised on EVERY rank by the same call: the loop stays collective
+                continue
+        raise native.NativeError(native.ERR_CAPACITY, "sharded selection kept overflowing its neighbour-list pools")
+
+    def get_fps(self):
+        return self.handle.get_fps()
+
+    def stage_ms(self):
+        return self.handle.stage_ms()
+
+    def counters(self):
+        return self.handle.counters()
+
+
+def make_engine(device: int):
+    """``native.Handle`` for a single process, ``DistWorld`` when torch.distributed runs more than one rank
+    (``ADSEL_SHARD=0`` keeps the reference's behaviour: every rank selects on its own replica)."""
+    from .dist import get_dist_info
+    _, world = get_dist_info()
+    if world > 1 and os.environ.get("ADSEL_SHARD", "1") != "0":
+        return DistWorld(device)
+    return native.Handle(device)

@@ -27,8 +27,11 @@ enum adsel_status {
     ADSEL_ERR_INVALID = -1,    /* bad argument / call order */
     ADSEL_ERR_CUDA = -2,       /* CUDA runtime failure (message has the cudaError string) */
     ADSEL_ERR_CAPACITY = -3,   /* an output buffer supplied by the caller is too small */
-    ADSEL_ERR_RESELECTED = -4  /* greedy argmax landed on an already selected frame:
+    ADSEL_ERR_RESELECTED = -4, /* greedy argmax landed on an already selected frame:
                                   the reference's AssertionError (spatial_temporal_selector.py:182) */
+    ADSEL_ERR_COMM = -5,       /* sharded path: timed out waiting for a peer rank (mailbox / barrier) */
+    ADSEL_ERR_PEER_ABORT = -6  /* sharded path: a peer rank aborted the selection; every rank returns an error
+                                  from the same call, so a caller may retry collectively */
 };
 
 /* spatial term of a row of the distance map */
@@ -114,6 +117,40 @@ int adsel_get_stage_ms(adsel_handle *h, float *ms8);
 /* counters of the last select: [0] kernels launched since adsel_create, [1] greedy steps,
  * [2] total neighbour-list entries, [3] csr nnz */
 int adsel_get_counters(adsel_handle *h, int64_t *c4);
+
+/* ---- pool sharded over the GPUs of one NVSwitch box -------------------------------
+ * The reference issues no collective here: under torch.distributed.launch every rank recomputes the
+ * whole selection and rank 0 writes (base_selector.py:57, tools/active_select.py:94-101).  In this
+ * library one handle per rank owns a contiguous, 256-aligned slice of the pool's columns; the kNN rows
+ * are computed per slice and stored straight into every rank's table over NVLink, and every greedy
+ * step ends with ONE exchange of the ranks' local (value, index) maxima, done inside the persistent
+ * greedy kernel through peer-memory mailboxes (np.argmax's first-maximum rule holds across shards).
+ *
+ * Call order on every rank: adsel_create, adsel_comm_init (-> 64-byte CUDA IPC handle), exchange the
+ * handles by any means (torch.distributed all_gather in this repo), adsel_comm_attach, adsel_set_pool,
+ * adsel_build_knn_graph_sharded, adsel_select_sharded_begin, adsel_select_sharded_end.  The *_sharded
+ * calls only enqueue work (no host synchronisation, no allocation after a first call of the same
+ * shape), so one host thread may also drive several handles (adsel_comm_attach_local: ranks that live in
+ * one process, on one or several devices).  All ranks must make the same sequence of sharded calls. */
+/* n, k, dim size the peer-visible arena (kNN tables [n,k+1], descriptors [n,dim]); identical on all ranks. */
+int adsel_comm_init(adsel_handle *h, int32_t rank, int32_t world, int32_t n, int32_t k, int32_t dim,
+                    void *ipc_handle_out /* 64 bytes, may be NULL */);
+int adsel_comm_attach(adsel_handle *h, const void *ipc_handles /* world x 64 bytes, rank order */);
+int adsel_comm_attach_local(adsel_handle *h, adsel_handle *const *handles /* world handles, rank order */);
+int adsel_comm_set_timeout(adsel_handle *h, double seconds);   /* device-side wait limit (default 20 s) */
+int adsel_comm_barrier(adsel_handle *h);                       /* enqueue a device-side barrier over all ranks */
+int adsel_comm_check(adsel_handle *h);                         /* synchronise; ADSEL_ERR_COMM if a barrier timed out */
+int adsel_shard_range(adsel_handle *h, int32_t *lo, int32_t *hi);   /* this rank's frames [lo, hi) */
+/* optional: performs every allocation of the following build/select calls now, so that they only enqueue
+ * (needed when one host thread drives several ranks: cudaFree may wait for a rank's spinning kernel) */
+int adsel_shard_prepare(adsel_handle *h, int32_t k, const adsel_select_params *p, int32_t n_sampled, int32_t out_cap);
+int adsel_build_knn_graph_sharded(adsel_handle *h, int32_t k);
+/* as adsel_select, split in two: `begin` enqueues lists + greedy loop, `end` waits and returns the result
+ * (identical on every rank).  ADSEL_ERR_CAPACITY / ADSEL_ERR_PEER_ABORT from `end` on all ranks means a
+ * rank's neighbour-list pool was too small; it has been grown -- call begin/end again on every rank. */
+int adsel_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled,
+                               int32_t n_sampled, int32_t first_index, int32_t out_cap);
+int adsel_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
 
 /* ---- BEV density descriptor from LiDAR points (north_star kernel 1; no reference function -- the
  *      binning semantics are those of det3d/ops/point_cloud/bev_ops.py:27-53, see csrc/bev.cu) -------

@@ -1,0 +1,184 @@
+"""GPU: the pool-sharded path -- kNN rows written into every rank's table, column-sharded
+neighbour lists and one mailbox exchange per greedy step -- must select exactly what the single-GPU path
+and the reference select.  ``LocalWorld`` drives all ranks from this process; with one visible GPU the
+ranks are CTAs of the same device (the exchange protocol is the same code), with several GPUs the last
+test also spreads them over devices (peer access instead of CUDA IPC)."""
+import random
+
+import numpy as np
+import pytest
+
+import restatement as R
+from adsel_b200 import native, pool, sharded
+from conftest import KIND, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _arrays(infos):
+    loc = pool.ego_locations(infos)
+    run_id, max_td = pool.consecutive_runs(pool.logfile_names(infos))
+    return loc, run_id, max_td, pool.box_counts(infos)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_sharded_knn_table_and_csr_equal_single_gpu(pools, world):
+    loc, run_id, _, n_boxes = _arrays(pools("P2K")["infos"])
+    w = sharded.LocalWorld(world, timeout=10.0)
+    try:
+        w.set_pool(loc, run_id, n_boxes)
+        w.build_knn_graph(8)
+        ref_d, ref_i = R.knn_query(loc, 8)
+        ranges = w.shard_ranges()
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(loc)
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert ranges == [sharded.shard_bounds(len(loc), world, r) for r in range(world)]
+        for h in w.handles:                       # every rank holds the complete table, written by all ranks
+            dist, idx = h.get_knn()
+            assert np.array_equal(dist.view(np.uint64), ref_d.view(np.uint64))
+            assert np.array_equal(idx, ref_i)
+            row_ptr, col, wgt = h.get_csr()
+            ref = R.knn_graph_csr(loc, 8)
+            assert np.array_equal(row_ptr, ref.indptr)
+    finally:
+        w.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_selection_identical_to_single_gpu_and_oracle(pools, world):
+    infos = pools("P2K")["infos"]
+    loc, run_id, max_td, n_boxes = _arrays(infos)
+    single = native.Handle(0)
+    single.set_pool(loc, run_id, n_boxes)
+    single.build_knn_graph(8)
+    kw = dict(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0, budget=300, first_index=17)
+    want, want_cost = single.select(**kw)
+    want_fps = single.get_fps()
+    single.close()
+    prov = R.RowProvider("spatial_temporal", infos)
+    assert want == R.greedy_select(prov.row, len(infos), n_boxes, [], 17, "300")
+    w = sharded.LocalWorld(world, timeout=10.0)
+    try:
+        w.set_pool(loc, run_id, n_boxes)
+        w.build_knn_graph(8)
+        got, cost = w.select(**kw)
+        assert got == want and cost == want_cost
+        assert np.array_equal(w.get_fps().view(np.uint64), want_fps.view(np.uint64))
+        # a second round resumes from the first (sampled rows applied on every rank's slice)
+        got2, _ = w.select(**{**kw, "budget": 500, "sampled": got, "first_index": -1, "cost_start": cost})
+        single = native.Handle(0)
+        single.set_pool(loc, run_id, n_boxes)
+        single.build_knn_graph(8)
+        ref2, _ = single.select(**{**kw, "budget": 500, "sampled": want, "first_index": -1, "cost_start": want_cost})
+        single.close()
+        assert got2 == ref2 and len(got2) > 0
+    finally:
+        w.close()
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_goldens_all_variants(pools, world):
+    """Every normalize x aggregate variant and the one-term siblings of the reference, sharded."""
+    golden = load_golden("P300_all.json")
+    pl = pools("P300")
+    infos, logs = pl["infos"], pl["logs"]
+    names = pool.logfile_names(infos)
+    loc = pool.ego_locations(infos)
+    n_boxes = pool.box_counts(infos)
+    run_id, max_td = pool.consecutive_runs(names)
+    checked = 0
+    for cid, case in golden["cases"].items():
+        if len(case["rounds"]) != 1 or not all(isinstance(v, list) for v in case["selected_index"].values()):
+            continue
+        kind = KIND[case["selector"]]
+        kwargs = dict(case["kwargs"])
+        cost_b, cost_f = kwargs.pop("cost_b", 0.04), kwargs.pop("cost_f", 0.12)
+        w = sharded.LocalWorld(world, timeout=10.0)
+        try:
+            if kind == "spatial_temporal":
+                w.set_pool(loc, run_id, n_boxes)
+                w.build_knn_graph(kwargs.get("k", 8))
+                normalize = kwargs.get("normalize", "exp")
+                max_sd = w.geodesic_max_finite() if normalize == "linear" else 0.0
+                sel_kw = dict(spatial="geodesic", temporal=True, normalize=normalize, aggregate=kwargs.get("aggregate", "sum"),
+                              lambda_t=kwargs.get("lambda_t", 1), max_spatial=max_sd, max_temporal=max_td)
+            elif kind == "spatial":
+                w.set_pool(loc, run_id, n_boxes)
+                w.build_knn_graph(kwargs.get("k", 8))
+                sel_kw = dict(spatial="geodesic", temporal=False, normalize="raw", forbid_sampled=True)
+            elif kind == "temporal":
+                w.set_pool(loc, pool.name_groups(names), n_boxes)
+                sel_kw = dict(spatial="none", temporal=True, normalize="raw", forbid_sampled=True)
+            else:
+                w.set_pool(loc, pool.city_groups(names, logs), n_boxes)
+                sel_kw = dict(spatial="euclid", temporal=False, normalize="raw", forbid_sampled=True)
+            budget = case["rounds"][0]
+            random.seed(3407)
+            first = random.choice(range(len(infos)))
+            got, _ = w.select(cost_b=cost_b, cost_f=cost_f, cost_start=0, budget=budget, first_index=first, **sel_kw)
+            assert got == case["selected_index"][str(budget)], f"{cid} world={world}"
+            checked += 1
+        finally:
+            w.close()
+    assert checked >= 8
+
+
+def test_sharded_p28k_budget_4800_identical_to_reference(pools):
+    golden = load_golden("P28K_st.json")["cases"]["st_exp_sum_4800"]["selected_index"]["4800"]
+    infos = pools("P28K")["infos"]
+    loc, run_id, max_td, n_boxes = _arrays(infos)
+    random.seed(3407)
+    first = random.choice(range(len(infos)))
+    w = sharded.LocalWorld(8, timeout=20.0)
+    try:
+        w.set_pool(loc, run_id, n_boxes)
+        w.build_knn_graph(8)
+        got, _ = w.select(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0, budget=4800,
+                          first_index=first)
+        assert got == golden
+    finally:
+        w.close()
+
+
+def test_sharded_list_pool_overflow_is_retried_collectively(pools):
+    """A rank whose neighbour-list pool is too small aborts every rank in the same exchange; the pool is
+    grown and the second attempt gives the normal result."""
+    infos = pools("P2K")["infos"]
+    loc, run_id, max_td, n_boxes = _arrays(infos)
+    # 60 near-coincident frames: every one of them has all the others within the 38 m radius
+    loc = loc.copy()
+    loc[:] = loc[0] + np.random.default_rng(0).uniform(0.0, 30.0, size=loc.shape)
+    single = native.Handle(0)
+    single.set_pool(loc, run_id, n_boxes)
+    single.build_knn_graph(8)
+    kw = dict(spatial="geodesic", temporal=True, normalize="exp", budget=40, first_index=3)
+    want, _ = single.select(**kw)          # ~n*n list entries > the default pool of 64 n: grown inside
+    assert single.counters()["list_entries"] > 64 * len(loc)
+    single.close()
+    w = sharded.LocalWorld(2, timeout=10.0)
+    try:
+        w.set_pool(loc, run_id, n_boxes)
+        w.build_knn_graph(8)
+        got, _ = w.select(**kw)
+        assert got == want
+    finally:
+        w.close()
+
+
+def test_sharded_over_two_devices_when_available(pools):
+    if native.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    infos = pools("P8K")["infos"]
+    loc, run_id, max_td, n_boxes = _arrays(infos)
+    golden = load_golden("P8K_all.json")["cases"]["st_exp_sum"]
+    budget = golden["rounds"][0]
+    random.seed(3407)
+    first = random.choice(range(len(infos)))
+    w = sharded.LocalWorld(2, devices=[0, 1], timeout=20.0)
+    try:
+        w.set_pool(loc, run_id, n_boxes)
+        w.build_knn_graph(8)
+        got, _ = w.select(spatial="geodesic", temporal=True, normalize="exp", budget=budget, first_index=first)
+        assert got == golden["selected_index"][str(budget)]
+    finally:
+        w.close()
