@@ -11,9 +11,11 @@ One "step" = one whole selection: kNN graph -> geodesic neighbour lists -> greed
   value : device-timed (CUDA events on the launching stream), pool arrays already resident in HBM.
   e2e   : the user-facing call ``SpatialTemporalSelector.select_samples()`` on host-resident infos
           (host string/pose extraction, H2D copies, kernels, D2H of the selected indices), wall clock.
-  N > 1 : one process per GPU, each running the same selection on its own replica of the pool
-          ("weak": per-GPU work fixed; the greedy loop is a sequential dependency chain and the
-          precompute is ~1 ms, so the path does not shard usefully at this size -- DESIGN.md §7).
+  N > 1 : one process per GPU, the pool SHARDED by column over the N ranks (sharded.DistWorld: kNN rows
+          stored into every rank's table over NVLink, one peer-memory mailbox exchange per greedy step,
+          DESIGN.md §7).  "weak": the pool grows with N (N x 28,130 frames, the same generator with N x
+          the scenes -- BASELINE.json config 5 is the 10x pool), budget 4800 fixed; value = pool frames /
+          max-over-ranks time.  extras.strong_p28k reports the fixed 28,130-frame pool on the same N ranks.
 
 ``--impl reference`` times the CPU implementation of the same workload on the host cores: the
 unmodified reference when /root/reference is present (this container), else the oracle port.
@@ -85,10 +87,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_pool(tmp):
+def pool_spec(world):
     import adsel_b200  # noqa: F401
     from adsel_b200 import synthetic
-    spec = getattr(synthetic, POOL)
+    if world <= 1:
+        return getattr(synthetic, POOL)
+    base = getattr(synthetic, POOL)
+    return synthetic.PoolSpec(f"{POOL}x{world}", base.n_scenes * world, base.n_long * world, base.long_len, base.short_len,
+                              base.scenes_per_log, base.seed)
+
+
+def workload_name(world):
+    return WORKLOAD if world <= 1 else WORKLOAD.replace(POOL, f"{POOL}x{world}(sharded over {world} GPUs)")
+
+
+def make_pool(tmp, world=1):
+    from adsel_b200 import synthetic
+    spec = pool_spec(world)
     paths = synthetic.write_pool(spec, tmp)
     return spec, paths
 
@@ -140,10 +155,11 @@ def run_reference_arm(args):
     from reference_loader import reference_available
     import adsel_b200  # noqa: F401
     from adsel_b200 import fileio
+    world = _env_int("WORLD_SIZE", 1)
     with tempfile.TemporaryDirectory() as tmp:
-        spec, paths = make_pool(tmp)
+        spec, paths = make_pool(tmp, world)
         infos, logs = fileio.load(paths["infos"]), fileio.load(paths["logs"])
-        use_ref = reference_available() and not args.port
+        use_ref = reference_available() and not args.port and world == 1   # the dense reference needs 4 x N^2 x 8 B
         kind = "reference" if use_ref else "port"
 
         def once():
@@ -166,7 +182,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm_done, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pool_frames": spec.n_frames, "budget": BUDGET},
+        "config": {"workload": workload_name(world), "pool_frames": spec.n_frames, "budget": BUDGET},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": kind,
                          "sample": f"full workload, {steps} timed selection(s); single-threaded numpy/scipy; "
                                    f"host has {os.cpu_count()} cores"},
@@ -260,7 +276,7 @@ def run_b200_arm(args):
         return float(t.item())
 
     with tempfile.TemporaryDirectory() as tmp:
-        spec, paths = make_pool(tmp)
+        spec, paths = make_pool(tmp, world)
         infos, logs = fileio.load(paths["infos"]), fileio.load(paths["logs"])
         n = spec.n_frames
         first = first_index(n)
@@ -270,7 +286,13 @@ def run_b200_arm(args):
         loc = pool.ego_locations(infos)
         run_id, max_td = pool.consecutive_runs(names)
         n_boxes = pool.box_counts(infos)
-        h = native.Handle(local_rank)
+        if world > 1:
+            from adsel_b200 import sharded
+            h = sharded.DistWorld(local_rank)          # this rank's shard of the pool
+            timer = h.handle
+        else:
+            h = native.Handle(local_rank)
+            timer = h
         h.set_pool(loc, run_id, n_boxes)              # inputs resident in HBM before the timed region
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -292,12 +314,13 @@ def run_b200_arm(args):
         for _ in range(args.steps):
             flush.add_(1)
             torch.cuda.synchronize()
-            h.timer_start()
+            if world > 1:
+                dist.barrier()                          # all ranks enter the timed selection together
+            timer.timer_start()
             h.build_knn_graph(8)
-            st1 = h.stage_ms()
             sel, cost = h.select(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0,
                                  cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=BUDGET, first_index=first)
-            dev_ms += h.timer_stop()
+            dev_ms += timer.timer_stop()
             st = h.stage_ms()
             for k in ("knn", "csr", "geodesic_lists", "greedy"):
                 stage_acc[k] = stage_acc.get(k, 0.0) + st[k]
@@ -335,7 +358,7 @@ def run_b200_arm(args):
         # ---- parity spot-check against the committed golden (reference output) ------------------
         golden_ok = None
         gpath = os.path.join(ROOT, "tests", "golden", "P28K_st.json")
-        if os.path.exists(gpath):
+        if os.path.exists(gpath) and world == 1:
             golden = json.load(open(gpath))["cases"]["st_exp_sum_4800"]["selected_index"][str(BUDGET)]
             golden_ok = bool(golden == sel)
 
@@ -346,6 +369,32 @@ def run_b200_arm(args):
             cpu = {"value": n / sec, "unit": "frames/s", "cores": 1, "kind": "port",
                    "sample": f"full workload once ({sec:.1f} s): streaming oracle port of the selector, single-threaded "
                              f"numpy/scipy on a {os.cpu_count()}-core host; selected list identical: {cpu_sel == sel}"}
+        # ---- strong scaling on the fixed 28,130-frame pool, same N ranks (N > 1) ------------------
+        strong = None
+        if world > 1:
+            from adsel_b200 import synthetic
+            infos28, _ = synthetic.generate_pool(getattr(synthetic, POOL))
+            run28, _ = pool.consecutive_runs(pool.logfile_names(infos28))
+            h.set_pool(pool.ego_locations(infos28), run28, pool.box_counts(infos28))
+            first28 = first_index(len(infos28))
+            ms28 = []
+            for it in range(args.warmup + args.steps):
+                flush.add_(1)
+                torch.cuda.synchronize()
+                dist.barrier()
+                timer.timer_start()
+                h.build_knn_graph(8)
+                sel28, _ = h.select(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0,
+                                    cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=BUDGET, first_index=first28)
+                t = timer.timer_stop()
+                if it >= args.warmup:
+                    ms28.append(t)
+            ms28 = max_over_ranks(sum(ms28) / len(ms28))
+            golden28 = json.load(open(gpath))["cases"]["st_exp_sum_4800"]["selected_index"][str(BUDGET)] \
+                if os.path.exists(gpath) else None
+            strong = {"workload": WORKLOAD + f" sharded over {world} GPUs", "pool_frames": len(infos28), "ms_per_step": ms28,
+                      "frames_per_s": len(infos28) / (ms28 * 1e-3), "greedy_steps": h.counters()["steps"],
+                      "identical_to_reference_golden": (golden28 == sel28) if golden28 is not None else None}
         h.close()
 
         # ---- BEV-descriptor configuration: HBM-bound histogram and tensor-core distance tiles ----
@@ -357,6 +406,8 @@ def run_b200_arm(args):
                      "bf16_source": ("measured burst (MEASURED_PEAKS.json bf16_tflops): kernel timed alone"
                                      if pk else "fallback (B200_PROFILING.md)")}
             extras = bev_extras(native, local_rank, n, n_boxes, first, peaks)
+        if strong is not None:
+            extras = {"strong_p28k": strong}
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -385,16 +436,17 @@ def run_b200_arm(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": world * n / (ms_per_step * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "metric": METRIC, "value": n / (ms_per_step * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pool_frames": n, "budget": BUDGET, "selected_frames": len(sel),
+            "config": {"workload": workload_name(world), "pool_frames": n, "budget": BUDGET, "selected_frames": len(sel),
                        "greedy_steps": steps_per_sel, "l2": "flushed between timed iterations (256 MiB write)",
-                       "parallelism": "1 process per GPU, independent pool replicas" if world > 1 else "single GPU",
+                       "parallelism": (f"1 process per GPU, pool sharded by column over {world} ranks, kNN rows and the "
+                                       "per-step (value,index) exchange over peer memory (NVLink)") if world > 1 else "single GPU",
                        "identical_to_reference_golden": golden_ok},
             "stages_ms": stages, "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": world * n / e2e_sec, "unit": "frames/s", "ms_per_step": e2e_sec * 1e3,
+            "e2e": {"value": n / e2e_sec, "unit": "frames/s", "ms_per_step": e2e_sec * 1e3,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clock_info,
             "extras": extras,

@@ -92,12 +92,17 @@ int comm_preload() {
     return ADSEL_OK;
 }
 
-static void comm_release(adsel_handle *h) {
+static void comm_detach(adsel_handle *h) {
     for (int w = 0; w < COMM_MAX_WORLD; ++w) {
         if (h->peer_arena[w] && h->peer_ipc[w]) cudaIpcCloseMemHandle(h->peer_arena[w]);
         h->peer_arena[w] = nullptr;
         h->peer_ipc[w] = false;
     }
+    h->comm_ready = false;
+}
+
+static void comm_release(adsel_handle *h) {
+    comm_detach(h);
     if (h->arena) cudaFree(h->arena);
     h->arena = nullptr;
     h->arena_bytes = 0;
@@ -184,6 +189,16 @@ int adsel_comm_attach(adsel_handle *h, const void *ipc_handles) {
         h->peer_ipc[w] = true;
     }
     h->comm_ready = true;
+    return ADSEL_OK;
+}
+
+int adsel_comm_detach(adsel_handle *h) {
+    ADSEL_REQUIRE(h, "adsel_comm_detach: null handle");
+    ADSEL_REQUIRE(!h->pending, "adsel_comm_detach: a sharded selection is pending");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    comm_detach(h);
+    if (h->arena) h->peer_arena[h->rank] = h->arena;
     return ADSEL_OK;
 }
 

@@ -758,6 +758,7 @@ int greedy_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap
     ADSEL_CUDA(cudaStreamSynchronize(h->stream));
     float ms = 0.f;
     ADSEL_CUDA(cudaEventElapsedTime(&ms, h->pending_ev[0], h->pending_ev[1]));
+    h->stage_ms[2] = 0.f;
     h->stage_ms[3] = ms;   // lists + greedy + exchanges of this rank
     const int status = (int)result[1];
     // every rank ran the same number of exchanges unless the launch failed; after a failure the tags are

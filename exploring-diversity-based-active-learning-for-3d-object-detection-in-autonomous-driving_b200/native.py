@@ -72,6 +72,7 @@ _SIGNATURES = {
                                           ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
     "adsel_comm_init": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),
     "adsel_comm_attach": (ctypes.c_int, [_P, _P]),
+    "adsel_comm_detach": (ctypes.c_int, [_P]),
     "adsel_comm_attach_local": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     "adsel_comm_set_timeout": (ctypes.c_int, [_P, ctypes.c_double]),
     "adsel_comm_barrier": (ctypes.c_int, [_P]),
@@ -230,6 +231,10 @@ class Handle:
         blob = b"".join(ipc_handles)
         assert len(blob) == IPC_HANDLE_BYTES * self.world
         _check(load().adsel_comm_attach(self._h, ctypes.c_char_p(blob)))
+
+    def comm_detach(self):
+        """Unmap every peer's arena (before any rank frees or re-sizes its own)."""
+        _check(load().adsel_comm_detach(self._h))
 
     def comm_attach_local(self, handles):
         """``handles``: the world's ``Handle`` objects of THIS process in rank order."""

@@ -172,6 +172,9 @@ class DistWorld(_WorldBase):
     def _ensure(self, k: int, dim: int = 0):
         shape = (self.n, int(k), int(dim))
         if self._arena_shape != shape:
+            if self._arena_shape is not None:       # nobody may still map an arena that is about to be freed
+                self.handle.comm_detach()
+                self._dist.barrier(group=self.group)
             ipc = self.handle.comm_init(self.rank, self.world, self.n, k, dim)
             self.handle.comm_set_timeout(self.timeout)
             gathered = [None] * self.world
@@ -214,11 +217,43 @@ class DistWorld(_WorldBase):
         return self.handle.counters()
 
 
+_ENGINES = {}
+
+
+class _Lease:
+    """An engine borrowed from the per-process cache: ``close()`` returns it instead of destroying it, so that
+    repeated selections (active-learning rounds in one process, the bench) reuse the CUDA context's buffers,
+    the peer mappings and the loaded kernels rather than paying cudaMalloc / cudaFree / IPC setup every call."""
+
+    def __init__(self, key, engine):
+        self._key, self._engine = key, engine
+
+    def __getattr__(self, name):
+        return getattr(self._engine, name)
+
+    def close(self):
+        pass
+
+
 def make_engine(device: int):
     """``native.Handle`` for a single process, ``DistWorld`` when torch.distributed runs more than one rank
-    (``ADSEL_SHARD=0`` keeps the reference's behaviour: every rank selects on its own replica)."""
+    (``ADSEL_SHARD=0`` keeps the reference's behaviour: every rank selects on its own replica).
+    Engines are cached per (kind, device); ``release_engines()`` destroys them."""
     from .dist import get_dist_info
     _, world = get_dist_info()
-    if world > 1 and os.environ.get("ADSEL_SHARD", "1") != "0":
-        return DistWorld(device)
-    return native.Handle(device)
+    sharded_mode = world > 1 and os.environ.get("ADSEL_SHARD", "1") != "0"
+    key = ("dist" if sharded_mode else "single", int(device), world)
+    if key not in _ENGINES:
+        _ENGINES[key] = DistWorld(device) if sharded_mode else native.Handle(device)
+    return _Lease(key, _ENGINES[key])
+
+
+def release_engines():
+    for engine in _ENGINES.values():
+        engine.close()
+    _ENGINES.clear()
+
+
+import atexit  # noqa: E402
+
+atexit.register(release_engines)

@@ -136,6 +136,7 @@ int adsel_get_counters(adsel_handle *h, int64_t *c4);
 int adsel_comm_init(adsel_handle *h, int32_t rank, int32_t world, int32_t n, int32_t k, int32_t dim,
                     void *ipc_handle_out /* 64 bytes, may be NULL */);
 int adsel_comm_attach(adsel_handle *h, const void *ipc_handles /* world x 64 bytes, rank order */);
+int adsel_comm_detach(adsel_handle *h);   /* unmap the peers' arenas; every rank does this before any rank re-sizes or frees */
 int adsel_comm_attach_local(adsel_handle *h, adsel_handle *const *handles /* world handles, rank order */);
 int adsel_comm_set_timeout(adsel_handle *h, double seconds);   /* device-side wait limit (default 20 s) */
 int adsel_comm_barrier(adsel_handle *h);                       /* enqueue a device-side barrier over all ranks */

@@ -1,0 +1,102 @@
+"""CPU, world_size 2 over gloo: the host side of the pool-sharded path (sharded.DistWorld, the selectors'
+engine switch, rank-0-only dump).  The CUDA library is replaced by tests/fake_native.py (oracle rows +
+all_gather exchange); the device-side exchange itself is covered by tests/test_gpu_sharded.py."""
+import json
+import os
+import random
+import sys
+import traceback
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from adsel_b200 import sharded
+from conftest import ROOT, load_golden
+
+
+def test_shard_bounds_cover_the_pool_in_aligned_contiguous_slices():
+    for n in (1, 255, 256, 257, 2099, 28130, 281300):
+        for world in (1, 2, 3, 4, 8):
+            bounds = [sharded.shard_bounds(n, world, r) for r in range(world)]
+            assert bounds[0][0] == 0 and bounds[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+            assert all(lo % 256 == 0 or lo == n for lo, _ in bounds)
+            assert all(hi >= lo for lo, hi in bounds)
+
+
+def test_pick_global_best_is_first_maximum_across_ranks():
+    assert sharded.pick_global_best([(1.0, 7), (2.0, 300), (2.0, 12), (0.5, 1)]) == (2.0, 12)
+    assert sharded.pick_global_best([(2.0, 300), (2.0, 301)]) == (2.0, 300)
+    assert sharded.pick_global_best([(0.0, 2 ** 31 - 1), (0.0, 5)]) == (0.0, 5)      # empty slice loses to a real entry
+
+
+def _worker(rank, world, init_file, pool_dir, out_dir):
+    try:
+        for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        import adsel_b200  # noqa: F401
+        from adsel_b200 import native, pool
+        from adsel_b200.selectors import build_selector
+        import fake_native
+        dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+        native.Handle = fake_native.FakeShardHandle                     # no GPU in this test
+        infos_path, logs_path = os.path.join(pool_dir, "infos_train_10sweeps_withvelo.pkl"), os.path.join(pool_dir, "log.json")
+        result = {}
+
+        # 1. the drop-in selector API under torch.distributed: ranks cooperate, rank 0 writes
+        buffer_file = os.path.join(out_dir, "buffer.json")
+        if rank == 0:
+            json.dump({"0": []}, open(buffer_file, "w"))
+        dist.barrier()
+        for budget in (50, 50):
+            random.seed(3407)
+            sel = build_selector(dict(type="SpatialTemporalSelector", budget=budget, buffer_file=buffer_file,
+                                      infos_origin=infos_path, logs_file=logs_path,
+                                      distance_store_file=os.path.join(out_dir, "unused.npy")))
+            sel.select_samples(local_rank=rank)
+            sel.dump_file()
+            dist.barrier()
+            result.update(sel.get_selected_samples())
+        engine = sharded.make_engine(rank)
+        result["engine"] = type(engine._engine).__name__
+        result["handle_calls"] = [c if isinstance(c, str) else c[0] for c in fake_native.FakeShardHandle.instances[0].calls]
+
+        # 2. DistWorld directly, one-term sibling (temporal groups by logfile name), tie-heavy integer rows
+        from adsel_b200 import fileio
+        infos = fileio.load(infos_path)
+        w = sharded.DistWorld(rank)
+        w.set_pool(np.zeros((len(infos), 2)), pool.name_groups(pool.logfile_names(infos)), pool.box_counts(infos))
+        random.seed(3407)
+        first = random.choice(range(len(infos)))
+        result["temporal"], _ = w.select(spatial="none", temporal=True, normalize="raw", forbid_sampled=True, cost_b=0.04,
+                                         cost_f=0.12, cost_start=0, budget=100, first_index=first)
+        result["range"] = list(w.shard_range())
+        json.dump(result, open(os.path.join(out_dir, f"rank{rank}.json"), "w"))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:                                                  # surface the traceback in the parent
+        open(os.path.join(out_dir, f"rank{rank}.err"), "w").write(traceback.format_exc())
+        raise
+
+
+def test_two_ranks_select_like_the_reference_and_only_rank0_writes(pools, tmp_path):
+    pl = pools("P300")
+    golden = load_golden("P300_all.json")["cases"]
+    out_dir = str(tmp_path)
+    init_file = os.path.join(out_dir, "rendezvous")
+    mp.spawn(_worker, args=(2, init_file, pl["dir"], out_dir), nprocs=2, join=True)
+    errs = [f for f in os.listdir(out_dir) if f.endswith(".err")]
+    assert not errs, open(os.path.join(out_dir, errs[0])).read()
+    r0, r1 = (json.load(open(os.path.join(out_dir, f"rank{r}.json"))) for r in (0, 1))
+    want = golden["st_exp_sum_rounds"]["selected_index"]
+    for r in (r0, r1):
+        assert r["50"] == want["50"] and r["100"] == want["100"]            # identical on every rank
+        assert r["temporal"] == golden["temporal"]["selected_index"]["100"]
+        assert r["engine"] == "DistWorld"
+        assert r["handle_calls"].count("comm_init") == 1                      # engine (arena, peer mappings) reused across rounds
+    assert r0["range"] == [0, 256] and r1["range"] == [256, 300]
+    assert json.load(open(os.path.join(out_dir, "buffer.json"))) == {"0": [], "50": want["50"], "100": want["100"]}
+    assert os.path.exists(pl["paths"]["infos"].replace(".pkl", "_100.pkl"))
