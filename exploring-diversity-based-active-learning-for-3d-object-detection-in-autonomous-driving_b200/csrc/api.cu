@@ -50,6 +50,11 @@ int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics,
 
 int pairdist_build(adsel_handle *h);
 int pairdist_set_descriptors(adsel_handle *h, const uint16_t *levels_host, int32_t n, int32_t dim);
+int pairdist_build_sharded(adsel_handle *h);
+int dense_prepare(adsel_handle *h, int32_t n_sampled, int32_t out_cap);
+int dense_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
+                               int32_t n_sampled, int32_t first_index, int32_t out_cap);
+int dense_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
 int dense_select(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
                  int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
 
@@ -324,8 +329,8 @@ int adsel_bev_get_descriptors(adsel_handle *h, int32_t *counts, uint16_t *levels
     const size_t tot = (size_t)h->bev_frames * h->bev_cells;
     if (cells) *cells = h->bev_cells;
     if (counts) ADSEL_CUDA(cudaMemcpy(counts, h->bev_counts.p, sizeof(int32_t) * tot, cudaMemcpyDeviceToHost));
-    if (levels) ADSEL_CUDA(cudaMemcpy(levels, h->bev_levels.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost));
-    if (norm2) ADSEL_CUDA(cudaMemcpy(norm2, h->bev_norm2.p, sizeof(int32_t) * h->bev_frames, cudaMemcpyDeviceToHost));
+    if (levels) ADSEL_CUDA(cudaMemcpy(levels, h->desc_levels, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost));
+    if (norm2) ADSEL_CUDA(cudaMemcpy(norm2, h->desc_norm2, sizeof(int32_t) * h->bev_frames, cudaMemcpyDeviceToHost));
     return ADSEL_OK;
 }
 
@@ -345,8 +350,11 @@ int adsel_pairdist_get_rows(adsel_handle *h, int32_t row0, int32_t rows, int32_t
     ADSEL_REQUIRE(h && out && h->pd_n > 0, "adsel_pairdist_get_rows: call adsel_pairdist_build first");
     ADSEL_REQUIRE(row0 >= 0 && rows > 0 && row0 + rows <= h->pd_n, "adsel_pairdist_get_rows: rows out of range");
     ADSEL_CUDA(cudaSetDevice(h->device));
-    ADSEL_CUDA(cudaMemcpy2D(out, sizeof(int32_t) * h->pd_n, h->pd_d2.p + (size_t)row0 * h->pd_ld, sizeof(int32_t) * h->pd_ld,
-                            sizeof(int32_t) * h->pd_n, rows, cudaMemcpyDeviceToHost));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    // out is [rows, pd_cols]: the columns this handle holds (all of them unless the matrix is a column shard)
+    if (h->pd_cols > 0)
+        ADSEL_CUDA(cudaMemcpy2D(out, sizeof(int32_t) * h->pd_cols, h->pd_d2.p + (size_t)row0 * h->pd_ld, sizeof(int32_t) * h->pd_ld,
+                                sizeof(int32_t) * h->pd_cols, rows, cudaMemcpyDeviceToHost));
     return ADSEL_OK;
 }
 
@@ -356,6 +364,31 @@ int adsel_select_dense(adsel_handle *h, const adsel_select_params *p, const int3
     ADSEL_REQUIRE(h, "adsel_select_dense: null handle");
     ADSEL_CUDA(cudaSetDevice(h->device));
     return dense_select(h, p, n_boxes, sampled, n_sampled, first_index, out_idx, out_cap, out_m, out_cost);
+}
+
+int adsel_pairdist_build_sharded(adsel_handle *h) {
+    ADSEL_REQUIRE(h, "adsel_pairdist_build_sharded: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return pairdist_build_sharded(h);
+}
+
+int adsel_select_dense_prepare(adsel_handle *h, int32_t n_sampled, int32_t out_cap) {
+    ADSEL_REQUIRE(h && out_cap > 0, "adsel_select_dense_prepare: bad argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return dense_prepare(h, n_sampled, out_cap);
+}
+
+int adsel_select_dense_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes, const int32_t *sampled,
+                                     int32_t n_sampled, int32_t first_index, int32_t out_cap) {
+    ADSEL_REQUIRE(h, "adsel_select_dense_sharded_begin: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return dense_select_sharded_begin(h, p, n_boxes, sampled, n_sampled, first_index, out_cap);
+}
+
+int adsel_select_dense_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {
+    ADSEL_REQUIRE(h, "adsel_select_dense_sharded_end: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return dense_select_sharded_end(h, out_idx, out_cap, out_m, out_cost);
 }
 
 int adsel_exp_f64(adsel_handle *h, const double *x, int64_t n, double *out) {

@@ -64,10 +64,19 @@ __device__ __forceinline__ void hist_add(int *hist, int cell) {
     }
 }
 
+// Destinations of the descriptors: one per rank.  In the sharded build every rank histograms the frames of
+// its own slice and stores levels / norms straight into every rank's arena (peer memory over NVLink): the
+// all-gather of the descriptor matrix is fused into the histogram kernel's epilogue.
+struct BevOut {
+    int world;
+    __nv_bfloat16 *levels[8];   // each already offset to this batch's first frame
+    int32_t *norm2[8];
+};
+
 template <bool AGGREGATE>
 __global__ void __launch_bounds__(BEV_THREADS, 2)
 bev_histogram_kernel(const float *__restrict__ pts, const int64_t *__restrict__ frame_off, int n_frames, BevGrid g,
-                     int32_t *__restrict__ counts, __nv_bfloat16 *__restrict__ levels, int32_t *__restrict__ norm2) {
+                     int32_t *__restrict__ counts, const BevOut out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = g.nx * g.ny;
     int *hist = reinterpret_cast<int *>(smem_raw);
@@ -120,14 +129,15 @@ bev_histogram_kernel(const float *__restrict__ pts, const int64_t *__restrict__ 
             const int cnt = hist[c];
             const int level = min(31, 32 - __clz(cnt));     // bit length: 0,1,2,2,3,3,3,3,4,...
             counts[(size_t)f * cells + c] = cnt;
-            levels[(size_t)f * cells + c] = __int2bfloat16_rn(level);
+            const __nv_bfloat16 lv = __int2bfloat16_rn(level);
+            for (int w = 0; w < out.world; ++w) out.levels[w][(size_t)f * cells + c] = lv;
             local += level * level;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
         if (lane == 0) atomicAdd(&s_norm, local);
         __syncthreads();
-        if (threadIdx.x == 0) norm2[f] = s_norm;
+        if (threadIdx.x < out.world) out.norm2[threadIdx.x][f] = s_norm;
         __syncthreads();
     }
 }
@@ -169,6 +179,9 @@ __global__ void bev_generate_kernel(float *__restrict__ pts, const int64_t *__re
         }
     }
 }
+
+uint16_t *arena_levels(adsel_handle *h, int w);
+int32_t *arena_norm2(adsel_handle *h, int w);
 
 static int bev_grid_from_params(const adsel_bev_params *p, BevGrid *g) {
     for (int a = 0; a < 3; ++a) {
@@ -229,23 +242,44 @@ int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics,
     BevGrid g;
     ADSEL_TRY(bev_grid_from_params(p, &g));
     const int cells = g.nx * g.ny;
-    ADSEL_REQUIRE(frame_base == 0 || (h->bev_cells == cells && h->bev_frames == total_frames),
+    // sharded: the arena was sized for exactly this descriptor matrix and every peer is attached
+    const bool sharded = h->comm_ready && h->world > 1 && h->arena_n == total_frames && h->arena_dim == cells;
+    // a rank's first batch of a sharded pool starts at its slice, not at frame 0
+    ADSEL_REQUIRE(frame_base == 0 || sharded || (h->bev_cells == cells && h->bev_frames == total_frames),
                   "adsel_bev_build: grid / pool size changed between batches");
     h->bev_cells = cells;
     h->bev_frames = total_frames;
-    if (frame_base == 0) {
+    if (frame_base == 0 || h->bev_counts.cap < (size_t)total_frames * cells) {
         ADSEL_TRY(h->bev_counts.reserve((size_t)total_frames * cells));
-        ADSEL_TRY(h->bev_levels.reserve((size_t)total_frames * cells));
-        ADSEL_TRY(h->bev_norm2.reserve(total_frames));
+        if (!sharded) {
+            ADSEL_TRY(h->bev_levels.reserve((size_t)total_frames * cells));
+            ADSEL_TRY(h->bev_norm2.reserve(total_frames));
+        }
+    }
+    BevOut out;
+    memset(&out, 0, sizeof(out));
+    const size_t o = (size_t)frame_base * cells;
+    if (sharded) {
+        out.world = h->world;
+        for (int w = 0; w < h->world; ++w) {
+            out.levels[w] = reinterpret_cast<__nv_bfloat16 *>(arena_levels(h, w)) + o;
+            out.norm2[w] = arena_norm2(h, w) + frame_base;
+        }
+        h->desc_levels = arena_levels(h, h->rank);
+        h->desc_norm2 = arena_norm2(h, h->rank);
+    } else {
+        out.world = 1;
+        out.levels[0] = reinterpret_cast<__nv_bfloat16 *>(h->bev_levels.p) + o;
+        out.norm2[0] = h->bev_norm2.p + frame_base;
+        h->desc_levels = h->bev_levels.p;
+        h->desc_norm2 = h->bev_norm2.p;
     }
     const size_t smem = (size_t)((cells + 3) & ~3) * sizeof(int) + (size_t)BEV_WARPS * CHUNK_VEC4 * sizeof(float4);
     auto kern = aggregate_atomics ? bev_histogram_kernel<true> : bev_histogram_kernel<false>;
     ADSEL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = min(h->bev_batch, 2 * h->num_sms);
-    const size_t o = (size_t)frame_base * cells;
     ADSEL_TRY(begin_stage(h));
-    kern<<<grid, BEV_THREADS, smem, h->stream>>>(h->bev_pts.p, h->bev_off.p, h->bev_batch, g, h->bev_counts.p + o,
-                                                  reinterpret_cast<__nv_bfloat16 *>(h->bev_levels.p) + o, h->bev_norm2.p + frame_base);
+    kern<<<grid, BEV_THREADS, smem, h->stream>>>(h->bev_pts.p, h->bev_off.p, h->bev_batch, g, h->bev_counts.p + o, out);
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     ADSEL_TRY(end_stage(h, 5));

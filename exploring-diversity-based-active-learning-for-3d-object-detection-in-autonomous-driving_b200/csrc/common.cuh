@@ -129,9 +129,11 @@ struct adsel_handle {
     adsel::DevBuf<int64_t> bev_off;
     adsel::DevBuf<int32_t> bev_counts, bev_norm2;
     adsel::DevBuf<uint16_t> bev_levels;          // bf16 bits
+    uint16_t *desc_levels = nullptr;             // descriptors in use: own buffers, or the arena's copy (sharded)
+    int32_t *desc_norm2 = nullptr;
 
     // pairwise squared distances of the descriptors (dense path)
-    int32_t pd_n = 0, pd_ld = 0;
+    int32_t pd_n = 0, pd_ld = 0, pd_col0 = 0, pd_cols = 0;   // pool frames, row pitch, first / number of local columns
     adsel::DevBuf<int32_t> pd_d2, pd_norm, pd_fps, pd_boxes;
 
     // greedy state
@@ -149,6 +151,7 @@ struct adsel_handle {
     unsigned char *arena = nullptr;              // peer-visible allocation: mailbox | kNN tables | descriptors
     size_t arena_bytes = 0;
     int32_t arena_n = 0, arena_k1 = 0, arena_dim = 0;
+    bool pd_pending_timing = false;              // knn_ev[0..1] bracket an enqueued sharded distance build
     bool knn_pending_timing = false;             // ev[0..1] bracket an enqueued sharded graph build
     unsigned char *peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool peer_ipc[8] = {false, false, false, false, false, false, false, false};   // opened with cudaIpcOpenMemHandle

@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include "comm.cuh"
 #include "common.cuh"
 
 namespace adsel {
@@ -112,7 +113,7 @@ __device__ __forceinline__ PdTile pd_tile(int t, int blocks_m, int blocks_n) {
 
 __global__ void __launch_bounds__(PD_THREADS, 1)
 pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ norm2,
-                        int32_t *__restrict__ out, int ld, int blocks_m, int blocks_n, int k_blocks) {
+                        int32_t *__restrict__ out, int ld, int blocks_m, int blocks_n, int k_blocks, int col0) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t *stage_mem = base;                                             // PD_STAGES x (A | B)
@@ -157,8 +158,8 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
                     uint8_t *a = stage_mem + (size_t)stage * PD_STAGE_BYTES, *b = a + PD_A_BYTES;
                     mbar_expect_tx(&full[stage], PD_STAGE_BYTES);
                     tma_load_2d(a, &tmap, &full[stage], kb * PD_BLOCK_K, tl.m_blk * PD_BLOCK_M);
-                    tma_load_2d(b, &tmap, &full[stage], kb * PD_BLOCK_K, tl.n_blk * PD_BLOCK_N);
-                    tma_load_2d(b + PD_A_BYTES, &tmap, &full[stage], kb * PD_BLOCK_K, tl.n_blk * PD_BLOCK_N + 128);
+                    tma_load_2d(b, &tmap, &full[stage], kb * PD_BLOCK_K, col0 + tl.n_blk * PD_BLOCK_N);
+                    tma_load_2d(b + PD_A_BYTES, &tmap, &full[stage], kb * PD_BLOCK_K, col0 + tl.n_blk * PD_BLOCK_N + 128);
                     if (++stage == PD_STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -212,8 +213,8 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
             const PdTile tl = pd_tile(t, blocks_m, blocks_n);
             const int m0 = tl.m_blk * PD_BLOCK_M, n0 = tl.n_blk * PD_BLOCK_N;
             int *nn = norm_n + acc * PD_BLOCK_N;
-            nn[et] = norm2[n0 + et];
-            nn[et + 128] = norm2[n0 + et + 128];
+            nn[et] = norm2[col0 + n0 + et];
+            nn[et + 128] = norm2[col0 + n0 + et + 128];
             const int ni = norm2[m0 + row_in_tile];
             asm volatile("bar.sync 1, 128;" ::: "memory");     // norm_n visible to the 4 epilogue warps
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -249,6 +250,9 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
     }
 }
 
+uint16_t *arena_levels(adsel_handle *h, int w);
+int32_t *arena_norm2(adsel_handle *h, int w);
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -264,22 +268,28 @@ static int get_encode_fn(EncodeTiledFn *fn) {
     return ADSEL_OK;
 }
 
-// d2 [n_pad, ld] int32 from levels bf16 [n, dim] and norm2 int32 [n] (both device buffers of the handle).
-int pairdist_build(adsel_handle *h) {
-    ADSEL_REQUIRE(h->bev_cells > 0 && h->bev_frames > 0, "adsel_pairdist_build: call adsel_bev_build (or adsel_pairdist_set_descriptors) first");
+// d2 [rows_pad, ld] int32 for the columns [col0, col0 + cols) of the pool, from levels bf16 [n, dim] and
+// norm2 int32 [n] (h->desc_levels / h->desc_norm2: own buffers, or the arena's gathered copy when sharded).
+static int pairdist_enqueue(adsel_handle *h, int col0, int cols) {
+    ADSEL_REQUIRE(h->bev_cells > 0 && h->bev_frames > 0 && h->desc_levels,
+                  "adsel_pairdist_build: call adsel_bev_build (or adsel_pairdist_set_descriptors) first");
     const int n = h->bev_frames, dim = h->bev_cells;
     ADSEL_REQUIRE(dim % 8 == 0, "adsel_pairdist_build: descriptor length must be a multiple of 8 (16-byte TMA rows)");
     ADSEL_REQUIRE((long long)dim * 31 * 31 < (1ll << 24), "adsel_pairdist_build: descriptor too long for exact fp32 accumulation");
-    const int blocks_m = (n + PD_BLOCK_M - 1) / PD_BLOCK_M, blocks_n = (n + PD_BLOCK_N - 1) / PD_BLOCK_N;
+    const int blocks_m = (n + PD_BLOCK_M - 1) / PD_BLOCK_M, blocks_n = (cols + PD_BLOCK_N - 1) / PD_BLOCK_N;
     const int k_blocks = (dim + PD_BLOCK_K - 1) / PD_BLOCK_K;
     const int ld = blocks_n * PD_BLOCK_N, rows = blocks_m * PD_BLOCK_M;
     h->pd_n = n;
     h->pd_ld = ld;
+    h->pd_col0 = col0;
+    h->pd_cols = cols;
+    if (blocks_n == 0) return ADSEL_OK;   // this rank owns no column (more ranks than 256-frame slices)
     ADSEL_TRY(h->pd_d2.reserve((size_t)rows * ld));
     // padded norms (zeros beyond n) so the epilogue needs no bounds checks
-    ADSEL_TRY(h->pd_norm.reserve((size_t)max(rows, ld)));
-    ADSEL_CUDA(cudaMemsetAsync(h->pd_norm.p, 0, sizeof(int32_t) * (size_t)max(rows, ld), h->stream));
-    ADSEL_CUDA(cudaMemcpyAsync(h->pd_norm.p, h->bev_norm2.p, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, h->stream));
+    const size_t norm_len = (size_t)max(rows, col0 + ld);
+    ADSEL_TRY(h->pd_norm.reserve(norm_len));
+    ADSEL_CUDA(cudaMemsetAsync(h->pd_norm.p, 0, sizeof(int32_t) * norm_len, h->stream));
+    ADSEL_CUDA(cudaMemcpyAsync(h->pd_norm.p, h->desc_norm2, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, h->stream));
 
     EncodeTiledFn encode = nullptr;
     ADSEL_TRY(get_encode_fn(&encode));
@@ -288,17 +298,56 @@ int pairdist_build(adsel_handle *h) {
     const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
     const cuuint32_t box[2] = {PD_BLOCK_K, 128};
     const cuuint32_t estride[2] = {1, 1};
-    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->bev_levels.p, gdim, gstride, box, estride,
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->desc_levels, gdim, gstride, box, estride,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ADSEL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
     ADSEL_CUDA(cudaFuncSetAttribute(pairdist_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM));
     const int grid = min(h->num_sms, blocks_m * blocks_n);
-    ADSEL_TRY(begin_stage(h));
-    pairdist_tcgen05_kernel<<<grid, PD_THREADS, PD_SMEM, h->stream>>>(tmap, h->pd_norm.p, h->pd_d2.p, ld, blocks_m, blocks_n, k_blocks);
+    pairdist_tcgen05_kernel<<<grid, PD_THREADS, PD_SMEM, h->stream>>>(tmap, h->pd_norm.p, h->pd_d2.p, ld, blocks_m, blocks_n,
+                                                                      k_blocks, col0);
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
+    return ADSEL_OK;
+}
+
+int pairdist_build(adsel_handle *h) {
+    ADSEL_TRY(begin_stage(h));
+    ADSEL_TRY(pairdist_enqueue(h, 0, h->bev_frames));
     ADSEL_TRY(end_stage(h, 6));
+    return ADSEL_OK;
+}
+
+int comm_barrier(adsel_handle *h);
+
+// Sharded (enqueue only): wait until every rank's descriptors have landed in this rank's arena, compute the
+// distance tiles of this rank's column slice, then a second barrier so that no rank starts overwriting the
+// gathered descriptors (a next build) while a peer still reads its copy.
+int pairdist_build_sharded(adsel_handle *h) {
+    ADSEL_REQUIRE(h->comm_ready, "adsel_pairdist_build_sharded: call adsel_comm_init / adsel_comm_attach first");
+    ADSEL_REQUIRE(h->bev_frames == h->arena_n && h->bev_cells == h->arena_dim && h->desc_levels,
+                  "adsel_pairdist_build_sharded: descriptors were not built into the arena (arena sized for another pool?)");
+    int lo = 0, hi = h->bev_frames;
+    if (h->world > 1) {
+        long long per = ((long long)h->bev_frames + h->world - 1) / h->world;
+        per = (per + 255) / 256 * 256;
+        lo = (int)min((long long)h->bev_frames, (long long)h->rank * per);
+        hi = (int)min((long long)h->bev_frames, (long long)lo + per);
+    }
+    {   // allocate before the first barrier is enqueued (see greedy_prepare)
+        const int blocks_m = (h->bev_frames + PD_BLOCK_M - 1) / PD_BLOCK_M, blocks_n = (hi - lo + PD_BLOCK_N - 1) / PD_BLOCK_N;
+        const int ld = blocks_n * PD_BLOCK_N, rows = blocks_m * PD_BLOCK_M;
+        if (blocks_n > 0) {
+            ADSEL_TRY(h->pd_d2.reserve((size_t)rows * ld));
+            ADSEL_TRY(h->pd_norm.reserve((size_t)max(rows, lo + ld)));
+        }
+    }
+    ADSEL_CUDA(cudaEventRecord(h->knn_ev[0], h->stream));
+    ADSEL_TRY(comm_barrier(h));
+    ADSEL_TRY(pairdist_enqueue(h, lo, hi - lo));
+    ADSEL_TRY(comm_barrier(h));
+    ADSEL_CUDA(cudaEventRecord(h->knn_ev[1], h->stream));
+    h->pd_pending_timing = true;
     return ADSEL_OK;
 }
 
@@ -323,10 +372,17 @@ int pairdist_set_descriptors(adsel_handle *h, const uint16_t *levels_host, int32
     ADSEL_REQUIRE(levels_host && n > 0 && dim > 0, "adsel_pairdist_set_descriptors: null/empty argument");
     h->bev_frames = n;
     h->bev_cells = dim;
-    ADSEL_TRY(h->bev_levels.reserve((size_t)n * dim));
-    ADSEL_TRY(h->bev_norm2.reserve(n));
-    ADSEL_CUDA(cudaMemcpyAsync(h->bev_levels.p, levels_host, sizeof(uint16_t) * (size_t)n * dim, cudaMemcpyHostToDevice, h->stream));
-    levels_norm_kernel<<<n, 256, 0, h->stream>>>(h->bev_levels.p, n, dim, h->bev_norm2.p);
+    if (h->comm_ready && h->world > 1 && h->arena_n == n && h->arena_dim == dim) {   // every rank uploads the full matrix itself
+        h->desc_levels = arena_levels(h, h->rank);
+        h->desc_norm2 = arena_norm2(h, h->rank);
+    } else {
+        ADSEL_TRY(h->bev_levels.reserve((size_t)n * dim));
+        ADSEL_TRY(h->bev_norm2.reserve(n));
+        h->desc_levels = h->bev_levels.p;
+        h->desc_norm2 = h->bev_norm2.p;
+    }
+    ADSEL_CUDA(cudaMemcpyAsync(h->desc_levels, levels_host, sizeof(uint16_t) * (size_t)n * dim, cudaMemcpyHostToDevice, h->stream));
+    levels_norm_kernel<<<n, 256, 0, h->stream>>>(h->desc_levels, n, dim, h->desc_norm2);
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     ADSEL_CUDA(cudaStreamSynchronize(h->stream));
@@ -337,7 +393,8 @@ int pairdist_set_descriptors(adsel_handle *h, const uint16_t *levels_host, int32
 constexpr int DG_THREADS = 1024;
 
 struct DenseArgs {
-    int n, ld;
+    int n, ld;        // n: columns owned by this rank (the whole pool when not sharded); ld: row pitch of d2
+    int col0;         // pool index of local column 0
     const int32_t *d2, *n_boxes, *sampled;
     int32_t *fps, *out;
     unsigned char *is_selected;
@@ -354,14 +411,18 @@ __device__ __forceinline__ BestI better_i(BestI a, BestI b) { return (b.v > a.v 
 // fps lives in registers (ITEMS columns per thread, column j = threadIdx.x + 1024*i), so a step is one
 // fully unrolled wave of independent streaming row loads (one memory latency) plus the arg-reduce.
 // ITEMS == 0: generic variant with fps in global memory for pools beyond 32,768 columns per GPU.
-template <int ITEMS>
-__global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const DenseArgs a) {
+// SHARDED: the rank holds the columns [col0, col0 + n) of every row; the step's local maximum is exchanged
+// with the other ranks through the peer-memory mailboxes (comm.cuh) and every rank does the same bookkeeping.
+template <int ITEMS, bool SHARDED>
+__global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const DenseArgs a, const CommView comm) {
     __shared__ BestI warp_res[DG_THREADS / 32];
     __shared__ int s_cur, s_stop, s_m;
     __shared__ double s_cost;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr int NREG = ITEMS > 0 ? ITEMS : 1;
     int fps_reg[NREG];
+    ExchangeLane xlane;
+    if (SHARDED) xlane = make_exchange_lane(comm);
     if (threadIdx.x == 0) {
         s_stop = 0;
         s_m = 0;
@@ -414,7 +475,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
                 fps_reg[i] = min(fps_reg[i], r[i]);
                 if (j < a.n && fps_reg[i] > x.v) {      // ascending j per thread: strict '>' keeps the first maximum
                     x.v = fps_reg[i];
-                    x.i = j;
+                    x.i = a.col0 + j;
                 }
             }
         } else {
@@ -426,7 +487,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
                 }
                 if (v > x.v) {
                     x.v = v;
-                    x.i = j;
+                    x.i = a.col0 + j;
                 }
             }
         }
@@ -444,9 +505,20 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
                 BestI z{__shfl_xor_sync(0xffffffffu, y.v, o), __shfl_xor_sync(0xffffffffu, y.i, o)};
                 y = better_i(y, z);
             }
+            int comm_status = 0;
+            if (SHARDED) {   // squared distances are >= 0: the int value is its own ordered key; -1 marks an empty slice
+                const ExchangeResult r = exchange_best(comm, xlane, comm.seq_base + 1u + (unsigned)steps,
+                                                       (unsigned long long)(unsigned)(y.v + 1), (unsigned)y.i);
+                y.v = (int)r.key - 1;
+                y.i = r.index;
+                comm_status = r.status;
+            }
             if (lane == 0) {
                 const int nxt = y.i;
-                if (seeding) {
+                if (comm_status != 0) {
+                    a.result[1] = (double)(comm_status == 2 ? ADSEL_ERR_COMM : ADSEL_ERR_PEER_ABORT);
+                    s_stop = 2;
+                } else if (seeding) {
                     a.out[0] = nxt;
                     s_m = 1;
                     a.is_selected[nxt] = 1;
@@ -476,6 +548,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
         }
         __syncthreads();
         ++steps;
+        if (s_stop == 2) break;
         if (seeding) {
             seeding = false;
             continue;
@@ -496,24 +569,46 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
     }
 }
 
-int dense_select(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
-                 int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {
+static int dense_validate(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
+                          int32_t n_sampled, int32_t first_index, int32_t out_cap) {
     ADSEL_REQUIRE(h->pd_n > 0, "adsel_select_dense: call adsel_pairdist_build first");
-    ADSEL_REQUIRE(p && n_boxes_host && out_idx && out_m && out_cap > 0, "adsel_select_dense: null argument");
+    ADSEL_REQUIRE(p && n_boxes_host && out_cap > 0, "adsel_select_dense: null argument");
     const int n = h->pd_n;
     ADSEL_REQUIRE(n_sampled >= 0 && (n_sampled == 0 || sampled), "adsel_select_dense: bad sampled list");
     ADSEL_REQUIRE(n_sampled > 0 || (first_index >= 0 && first_index < n), "adsel_select_dense: first_index out of range");
     for (int i = 0; i < n_sampled; ++i) ADSEL_REQUIRE(sampled[i] >= 0 && sampled[i] < n, "adsel_select_dense: sampled index out of range");
-    ADSEL_TRY(h->pd_fps.reserve(n));
-    ADSEL_TRY(h->pd_boxes.reserve(n));
-    ADSEL_TRY(h->is_selected.reserve(n));
+    return ADSEL_OK;
+}
+
+int dense_prepare(adsel_handle *h, int32_t n_sampled, int32_t out_cap) {
+    ADSEL_REQUIRE(h->pd_n > 0, "adsel_select_dense: call adsel_pairdist_build first");
+    ADSEL_TRY(h->pd_fps.reserve(h->pd_cols > 0 ? h->pd_cols : 1));
+    ADSEL_TRY(h->pd_boxes.reserve(h->pd_n));
+    ADSEL_TRY(h->is_selected.reserve(h->pd_n));
     ADSEL_TRY(h->d_sampled.reserve(n_sampled > 0 ? n_sampled : 1));
     ADSEL_TRY(h->d_out.reserve(out_cap));
     ADSEL_TRY(h->d_result.reserve(8));
+    return ADSEL_OK;
+}
+
+int comm_view(adsel_handle *h, CommView *view);
+
+template <bool SHARDED>
+static void launch_dense(adsel_handle *h, const DenseArgs &a, const CommView &view) {
+    if (a.n <= 8 * DG_THREADS) dense_greedy_kernel<8, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
+    else if (a.n <= 16 * DG_THREADS) dense_greedy_kernel<16, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
+    else if (a.n <= 32 * DG_THREADS) dense_greedy_kernel<32, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
+    else dense_greedy_kernel<0, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
+}
+
+static int dense_enqueue(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
+                         int32_t n_sampled, int32_t first_index, int32_t out_cap, bool sharded) {
+    const int n = h->pd_n;
     DenseArgs a;
     memset(&a, 0, sizeof(a));
-    a.n = n;
+    a.n = h->pd_cols;
     a.ld = h->pd_ld;
+    a.col0 = h->pd_col0;
     a.d2 = h->pd_d2.p;
     a.n_boxes = h->pd_boxes.p;
     a.sampled = h->d_sampled.p;
@@ -529,21 +624,24 @@ int dense_select(adsel_handle *h, const adsel_select_params *p, const int32_t *n
     a.first_index = first_index;
     a.out_cap = out_cap;
     a.result = h->d_result.p;
-    ADSEL_TRY(begin_stage(h));
     ADSEL_CUDA(cudaMemcpyAsync(h->pd_boxes.p, n_boxes_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
     if (n_sampled > 0)
         ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyHostToDevice, h->stream));
     ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, n, h->stream));
     ADSEL_CUDA(cudaMemsetAsync(h->d_result.p, 0, sizeof(double) * 8, h->stream));
-    if (n <= 8 * DG_THREADS) dense_greedy_kernel<8><<<1, DG_THREADS, 0, h->stream>>>(a);
-    else if (n <= 16 * DG_THREADS) dense_greedy_kernel<16><<<1, DG_THREADS, 0, h->stream>>>(a);
-    else if (n <= 32 * DG_THREADS) dense_greedy_kernel<32><<<1, DG_THREADS, 0, h->stream>>>(a);
-    else dense_greedy_kernel<0><<<1, DG_THREADS, 0, h->stream>>>(a);
+    CommView view;
+    if (sharded) {
+        ADSEL_TRY(comm_view(h, &view));
+        launch_dense<true>(h, a, view);
+    } else {
+        launch_dense<false>(h, a, view);
+    }
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
-    double result[8];
-    ADSEL_CUDA(cudaMemcpyAsync(result, h->d_result.p, sizeof(result), cudaMemcpyDeviceToHost, h->stream));
-    ADSEL_TRY(end_stage(h, 7));
+    return ADSEL_OK;
+}
+
+static int dense_finish(adsel_handle *h, const double *result, int32_t *out_idx, int32_t *out_m, double *out_cost, const char *who) {
     const int m = (int)result[2], status = (int)result[1];
     h->last_steps = (int64_t)result[3];
     if (m > 0) ADSEL_CUDA(cudaMemcpy(out_idx, h->d_out.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
@@ -554,16 +652,77 @@ int dense_select(adsel_handle *h, const adsel_select_params *p, const int32_t *n
         return ADSEL_ERR_RESELECTED;
     }
     if (status == ADSEL_ERR_CAPACITY) {
-        set_error("adsel_select_dense: out_idx capacity exhausted");
+        set_error(std::string(who) + ": out_idx capacity exhausted");
         return ADSEL_ERR_CAPACITY;
     }
+    if (status == ADSEL_ERR_COMM) {
+        set_error(std::string(who) + ": timed out waiting for a peer rank's mailbox record");
+        return ADSEL_ERR_COMM;
+    }
+    if (status != 0) {
+        set_error(std::string(who) + ": device-side failure " + std::to_string(status));
+        return status;
+    }
     return ADSEL_OK;
+}
+
+int dense_select(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
+                 int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {
+    ADSEL_TRY(dense_validate(h, p, n_boxes_host, sampled, n_sampled, first_index, out_cap));
+    ADSEL_REQUIRE(out_idx && out_m, "adsel_select_dense: null argument");
+    ADSEL_REQUIRE(h->pd_col0 == 0 && h->pd_cols == h->pd_n, "adsel_select_dense: the distance matrix is a column shard (use the sharded call)");
+    ADSEL_TRY(dense_prepare(h, n_sampled, out_cap));
+    ADSEL_TRY(begin_stage(h));
+    ADSEL_TRY(dense_enqueue(h, p, n_boxes_host, sampled, n_sampled, first_index, out_cap, false));
+    double result[8];
+    ADSEL_CUDA(cudaMemcpyAsync(result, h->d_result.p, sizeof(result), cudaMemcpyDeviceToHost, h->stream));
+    ADSEL_TRY(end_stage(h, 7));
+    return dense_finish(h, result, out_idx, out_m, out_cost, "adsel_select_dense");
+}
+
+int dense_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
+                               int32_t n_sampled, int32_t first_index, int32_t out_cap) {
+    ADSEL_TRY(dense_validate(h, p, n_boxes_host, sampled, n_sampled, first_index, out_cap));
+    ADSEL_REQUIRE(h->comm_ready, "adsel_select_dense_sharded_begin: call adsel_comm_init / adsel_comm_attach first");
+    ADSEL_REQUIRE(!h->pending, "adsel_select_dense_sharded_begin: a sharded selection is already pending");
+    ADSEL_TRY(dense_prepare(h, n_sampled, out_cap));
+    ADSEL_CUDA(cudaEventRecord(h->pending_ev[0], h->stream));
+    ADSEL_TRY(dense_enqueue(h, p, n_boxes_host, sampled, n_sampled, first_index, out_cap, true));
+    ADSEL_CUDA(cudaEventRecord(h->pending_ev[1], h->stream));
+    h->pending = true;
+    h->pending_cap = out_cap;
+    return ADSEL_OK;
+}
+
+int dense_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {
+    ADSEL_REQUIRE(h->pending, "adsel_select_dense_sharded_end: no pending sharded selection");
+    ADSEL_REQUIRE(out_idx && out_m && out_cap >= h->pending_cap, "adsel_select_dense_sharded_end: bad output buffer");
+    h->pending = false;
+    double result[8];
+    ADSEL_CUDA(cudaMemcpyAsync(result, h->d_result.p, sizeof(result), cudaMemcpyDeviceToHost, h->stream));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    if (h->pd_pending_timing) {
+        h->pd_pending_timing = false;
+        ADSEL_CUDA(cudaEventElapsedTime(&ms, h->knn_ev[0], h->knn_ev[1]));
+        h->stage_ms[6] = ms;   // barrier + this rank's distance tiles + barrier
+    }
+    ADSEL_CUDA(cudaEventElapsedTime(&ms, h->pending_ev[0], h->pending_ev[1]));
+    h->stage_ms[7] = ms;
+    const int status = (int)result[1];
+    if (status == 0 || status == ADSEL_ERR_RESELECTED || status == ADSEL_ERR_CAPACITY) h->comm_seq += (unsigned)result[3];
+    else h->comm_seq = ((h->comm_seq >> 24) + 1u) << 24;
+    return dense_finish(h, result, out_idx, out_m, out_cost, "adsel_select_dense_sharded");
 }
 
 int dense_preload() {
     cudaFuncAttributes attr;
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, pairdist_tcgen05_kernel));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, levels_norm_kernel));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, dense_greedy_kernel<8, true>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, dense_greedy_kernel<16, true>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, dense_greedy_kernel<32, true>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, dense_greedy_kernel<0, true>));
     return ADSEL_OK;
 }
 

@@ -84,6 +84,12 @@ _SIGNATURES = {
                                                   ctypes.c_int32]),
     "adsel_select_sharded_end": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                                 ctypes.POINTER(ctypes.c_double)]),
+    "adsel_pairdist_build_sharded": (ctypes.c_int, [_P]),
+    "adsel_select_dense_prepare": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32]),
+    "adsel_select_dense_sharded_begin": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, _P, ctypes.c_int32,
+                                                        ctypes.c_int32, ctypes.c_int32]),
+    "adsel_select_dense_sharded_end": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                                      ctypes.POINTER(ctypes.c_double)]),
     "adsel_bev_set_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32]),
     "adsel_bev_generate": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_uint64]),
     "adsel_bev_get_points": (ctypes.c_int, [_P, _P]),
@@ -133,6 +139,16 @@ def _ptr(a):
     return a.ctypes.data_as(_P) if a is not None else None
 
 
+def shard_bounds_256(n, world, rank):
+    """Frames ``[lo, hi)`` of ``rank``: contiguous 256-aligned slices (csrc/comm.cu:update_shard)."""
+    if world <= 1:
+        return 0, n
+    per = -(-n // world)
+    per = -(-per // 256) * 256
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
 def device_count() -> int:
     c = ctypes.c_int(0)
     _check(load().adsel_device_count(ctypes.byref(c)))
@@ -146,6 +162,7 @@ class Handle:
         self._h = _P()
         self.n = 0
         self.k = 0
+        self.rank, self.world = 0, 1
         _check(load().adsel_create(device, ctypes.byref(self._h)))
 
     def close(self):
@@ -358,9 +375,38 @@ class Handle:
 
     def pairdist_build(self):
         _check(load().adsel_pairdist_build(self._h))
+        self.pd_cols = self.pd_n
+
+    def pairdist_build_sharded(self):
+        _check(load().adsel_pairdist_build_sharded(self._h))
+        lo, hi = shard_bounds_256(self.pd_n, self.world, self.rank)
+        self.pd_cols = hi - lo
+
+    def select_dense_prepare(self, n_sampled=0, out_cap=None):
+        _check(load().adsel_select_dense_prepare(self._h, int(n_sampled), self.pd_n if out_cap is None else int(out_cap)))
+
+    def select_dense_sharded_begin(self, n_boxes, *, cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=0.0,
+                                   forbid_sampled=True, sampled=(), first_index=-1, out_cap=None):
+        p = SelectParams(0, 0, 0, 0, 0.0, 0.0, 0.0, float(cost_b), float(cost_f), float(cost_start), float(budget),
+                         int(bool(forbid_sampled)), 0)
+        n_boxes = np.ascontiguousarray(n_boxes, dtype=np.int32)
+        sampled = np.ascontiguousarray(sampled, dtype=np.int32)
+        self._out_cap = len(n_boxes) if out_cap is None else int(out_cap)
+        _check(load().adsel_select_dense_sharded_begin(self._h, ctypes.byref(p), _ptr(n_boxes),
+                                                       _ptr(sampled) if len(sampled) else None, len(sampled),
+                                                       int(first_index), self._out_cap))
+
+    def select_dense_sharded_end(self):
+        out = np.empty(self._out_cap, dtype=np.int32)
+        m, cost = ctypes.c_int32(0), ctypes.c_double(0.0)
+        status = load().adsel_select_dense_sharded_end(self._h, _ptr(out), self._out_cap, ctypes.byref(m), ctypes.byref(cost))
+        if status == ERR_RESELECTED:
+            raise AssertionError(load().adsel_last_error().decode())
+        _check(status)
+        return out[: m.value].tolist(), cost.value
 
     def pairdist_get_rows(self, row0, rows):
-        out = np.empty((rows, self.pd_n), dtype=np.int32)
+        out = np.empty((rows, getattr(self, "pd_cols", None) or self.pd_n), dtype=np.int32)
         _check(load().adsel_pairdist_get_rows(self._h, int(row0), int(rows), _ptr(out)))
         return out
 
@@ -380,6 +426,26 @@ class Handle:
             raise AssertionError(load().adsel_last_error().decode())
         _check(status)
         return out[: m.value].tolist(), cost.value
+
+    # -- one interface for the dense (BEV) path on a single GPU and on a sharded world -------------------
+    @staticmethod
+    def bev_cells(point_range=NUSC_RANGE, voxel=(0.8, 0.8, 8.0)) -> int:
+        """ny*nx of the BEV grid: round((hi-lo)/voxel) in float32 (bev_ops.py:27-30)."""
+        r, v = np.asarray(point_range, dtype=np.float32), np.asarray(voxel, dtype=np.float32)
+        nx, ny = int(np.rint((r[3] - r[0]) / v[0])), int(np.rint((r[4] - r[1]) / v[1]))
+        return nx * ny
+
+    def dense_build(self, n, batch_frames, load_batch, point_range=NUSC_RANGE, voxel=(0.8, 0.8, 8.0)):
+        """Descriptors of all ``n`` frames (``load_batch(handle, lo, hi)`` puts the points of frames [lo, hi) on
+        the handle), then the pairwise distance matrix."""
+        for lo in range(0, n, batch_frames):
+            hi = min(n, lo + batch_frames)
+            load_batch(self, lo, hi)
+            self.bev_build(point_range, voxel, frame_base=lo, total_frames=n)
+        self.pairdist_build()
+
+    def dense_select(self, n_boxes, **kw):
+        return self.select_dense(n_boxes, **kw)
 
     def stream_ptr(self) -> int:
         s = _P()

@@ -18,7 +18,7 @@ from typing import Callable, Optional
 
 import numpy as np
 
-from .. import native, pool
+from .. import pool, sharded
 from .base_selector import BaseSelector
 from .registry import SELECTORS
 
@@ -75,18 +75,18 @@ class BevSpatialSelector(BaseSelector):
     def select_samples(self, **kwargs) -> None:
         import random
         n = len(self.infos_origin)
-        handle = native.Handle(self._device_index(kwargs))
+        handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's slice of the frames
+
+        def load_batch(h, lo, hi):                                 # stream the pool through HBM
+            frames = [self._points(i) for i in range(lo, hi)]
+            off = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.int64)
+            h.bev_set_points(np.concatenate(frames, axis=0), off)
+
         try:
-            for lo in range(0, n, self.batch_frames):                      # stream the pool through HBM
-                hi = min(n, lo + self.batch_frames)
-                frames = [self._points(i) for i in range(lo, hi)]
-                off = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.int64)
-                handle.bev_set_points(np.concatenate(frames, axis=0), off)
-                handle.bev_build(self.point_range, self.voxel_size, frame_base=lo, total_frames=n)
-            handle.pairdist_build()
+            handle.dense_build(n, self.batch_frames, load_batch, self.point_range, self.voxel_size)
             sampled = list(self.buffer[self.get_max_key()])
             first_index = random.choice(range(n)) if len(sampled) == 0 else -1   # spatial_selector.py:111
-            selected, cost = handle.select_dense(pool.box_counts(self.infos_origin), cost_b=self.cost_b,
+            selected, cost = handle.dense_select(pool.box_counts(self.infos_origin), cost_b=self.cost_b,
                                                  cost_f=self.cost_f, cost_start=self.get_cost_amount(),
                                                  budget=int(self.current_budget), forbid_sampled=True,
                                                  sampled=sampled, first_index=first_index)

@@ -24,12 +24,7 @@ from . import native
 
 def shard_bounds(n: int, world: int, rank: int):
     """Frames ``[lo, hi)`` owned by ``rank``: contiguous, 256-aligned slices (mirrors csrc/comm.cu:update_shard)."""
-    if world <= 1:
-        return 0, n
-    per = -(-n // world)
-    per = -(-per // 256) * 256
-    lo = min(n, rank * per)
-    return lo, min(n, lo + per)
+    return native.shard_bounds_256(n, world, rank)
 
 
 def pick_global_best(records):
@@ -49,6 +44,7 @@ class _WorldBase:
         self.n = 0
         self.k = 0
         self._pool = None
+        self._pool_dirty = False
         self._arena_shape = None
 
     def set_pool(self, loc_xy, group_id, n_boxes):
@@ -84,10 +80,55 @@ class LocalWorld(_WorldBase):
                 h.comm_attach_local(self.handles)
             self._arena_shape = shape
             self._pool_dirty = True
-        if self._pool_dirty:
+        if self._pool_dirty and self._pool is not None:
             for h in self.handles:
                 h.set_pool(*self._pool)
             self._pool_dirty = False
+
+    # -- dense (BEV descriptor) path ---------------------------------------------------------------
+    def dense_build(self, n, batch_frames, load_batch, point_range=native.Handle.NUSC_RANGE, voxel=(0.8, 0.8, 8.0)):
+        """Every rank histograms the frames of its own slice (``load_batch(handle, lo, hi)``) and stores the
+        descriptors into every rank's arena; then each rank computes the distance tiles of its column slice."""
+        self.n = n
+        self._ensure(self.k, dim=native.Handle.bev_cells(point_range, voxel))
+        for r, h in enumerate(self.handles):
+            lo, hi = shard_bounds(n, self.world, r)
+            for b in range(lo, hi, batch_frames):
+                e = min(hi, b + batch_frames)
+                load_batch(h, b, e)
+                h.bev_build(point_range, voxel, frame_base=b, total_frames=n)
+        for h in self.handles:
+            h.pd_n = n
+            h.pairdist_build_sharded()
+        for h in self.handles:
+            h.comm_check()
+
+    def dense_set_descriptors(self, levels_bf16_bits):
+        """Caller-supplied descriptors (tests): every rank uploads the full matrix into its own arena."""
+        self.n = levels_bf16_bits.shape[0]
+        self._ensure(self.k, dim=levels_bf16_bits.shape[1])
+        for h in self.handles:
+            h.pairdist_set_descriptors(levels_bf16_bits)
+        for h in self.handles:
+            h.pairdist_build_sharded()
+        for h in self.handles:
+            h.comm_check()
+
+    def dense_select(self, n_boxes, **kw):
+        for h in self.handles:
+            h.select_dense_prepare(len(kw.get("sampled", ())), kw.get("out_cap"))
+        for h in self.handles:
+            h.select_dense_sharded_begin(n_boxes, **kw)
+        results, error = [], None
+        for h in self.handles:
+            try:
+                results.append(h.select_dense_sharded_end())
+            except (AssertionError, native.NativeError) as e:
+                error = error or e
+        if error is not None:
+            raise error
+        assert all(r == results[0] for r in results), "ranks disagree on the selection"
+        return results[0]
 
     def shard_ranges(self):
         return [h.shard_range() for h in self.handles]
@@ -182,9 +223,27 @@ class DistWorld(_WorldBase):
             self.handle.comm_attach(gathered)
             self._arena_shape = shape
             self._pool_dirty = True
-        if self._pool_dirty:
+        if self._pool_dirty and self._pool is not None:
             self.handle.set_pool(*self._pool)
             self._pool_dirty = False
+
+    # -- dense (BEV descriptor) path ---------------------------------------------------------------
+    def dense_build(self, n, batch_frames, load_batch, point_range=native.Handle.NUSC_RANGE, voxel=(0.8, 0.8, 8.0)):
+        """This rank histograms the frames of its own slice and stores their descriptors into every rank's
+        arena (fused all-gather over NVLink); then the distance tiles of its column slice."""
+        self.n = n
+        self._ensure(self.k, dim=native.Handle.bev_cells(point_range, voxel))
+        lo, hi = shard_bounds(n, self.world, self.rank)
+        for b in range(lo, hi, batch_frames):
+            e = min(hi, b + batch_frames)
+            load_batch(self.handle, b, e)
+            self.handle.bev_build(point_range, voxel, frame_base=b, total_frames=n)
+        self.handle.pd_n = n
+        self.handle.pairdist_build_sharded()
+
+    def dense_select(self, n_boxes, **kw):
+        self.handle.select_dense_sharded_begin(n_boxes, **kw)
+        return self.handle.select_dense_sharded_end()
 
     def shard_range(self):
         return self.handle.shard_range()

@@ -192,6 +192,18 @@ int adsel_select_dense(adsel_handle *h, const adsel_select_params *p, const int3
                        int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m,
                        double *out_cost);
 
+/* ---- the BEV / dense path sharded over ranks (after adsel_comm_init with dim = cells, n = pool frames) ----
+ * adsel_bev_build then stores each frame's descriptor into EVERY rank's arena (the all-gather is fused into
+ * the histogram kernel's epilogue); every rank builds the frames of its own slice [adsel_shard_range), at
+ * frame_base = their pool index.  adsel_pairdist_build_sharded (enqueue only): device barrier, the distance
+ * tiles of this rank's 256-aligned column slice d2[:, lo:hi), device barrier.  adsel_pairdist_get_rows then
+ * returns [rows, hi-lo].  The dense greedy loop runs on the column slice with one mailbox exchange per step. */
+int adsel_pairdist_build_sharded(adsel_handle *h);
+int adsel_select_dense_prepare(adsel_handle *h, int32_t n_sampled, int32_t out_cap);   /* allocations only */
+int adsel_select_dense_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes,
+                                     const int32_t *sampled, int32_t n_sampled, int32_t first_index, int32_t out_cap);
+int adsel_select_dense_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
+
 /* ---- element-wise helpers (tests) ----------------------------------------------------------- */
 /* out[i] = exp(x[i]) with the arithmetic of numpy's AVX512_SKX float64 exp (np.exp in
  * spatial_temporal_selector.py:142-143); host buffers, computed on the device. */

@@ -182,3 +182,69 @@ def test_sharded_over_two_devices_when_available(pools):
         assert got == golden["selected_index"][str(budget)]
     finally:
         w.close()
+
+
+# ---- dense (BEV descriptor) path sharded -------------------------------------------------------------
+import bev_oracle as B  # noqa: E402
+
+
+@pytest.mark.parametrize("world,n,dim", [(2, 700, 1024), (3, 1000, 256), (8, 300, 64)])
+def test_sharded_distance_columns_and_dense_selection(world, n, dim):
+    rng = np.random.default_rng(n + dim)
+    lv = rng.integers(0, 32, size=(n, dim))
+    lv[rng.random((n, dim)) < 0.85] = 0
+    lv[100:140] = lv[99]                      # exact ties across (and inside) column shards
+    n_boxes = rng.integers(0, 60, size=n).astype(np.int32)
+    d2 = B.sq_distance_matrix(lv, lv)
+    ref = R.greedy_select(lambda i: d2[i].astype(np.float64), n, n_boxes, [], 5, "150", forbid_sampled=True)
+    w = sharded.LocalWorld(world, timeout=10.0)
+    try:
+        w.dense_set_descriptors(B.bf16_bits(lv))
+        for r, h in enumerate(w.handles):     # each rank holds exactly its 256-aligned column slice
+            lo, hi = sharded.shard_bounds(n, world, r)
+            if hi > lo:
+                assert np.array_equal(h.pairdist_get_rows(0, n).astype(np.int64), d2[:, lo:hi])
+        got, cost = w.dense_select(n_boxes, budget=150, first_index=5)
+        assert got == ref
+        ref2 = R.greedy_select(lambda i: d2[i].astype(np.float64), n, n_boxes, ref, -1, "300", forbid_sampled=True)
+        got2, _ = w.dense_select(n_boxes, budget=300, sampled=ref, cost_start=R.cost_of_sampled(n_boxes, ref, 0.04, 0.12))
+        assert got2 == ref2
+        with pytest.raises(AssertionError):   # pool exhausted -> the reference's assertion, on every rank
+            w.dense_select(n_boxes, budget=10 ** 9, first_index=5)
+    finally:
+        w.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_bev_pipeline_descriptors_gathered_by_the_histogram_kernel(world):
+    """points -> histogram on the owner rank -> descriptors stored into every rank's arena -> column-sharded
+    distances -> sharded greedy, against the oracle end to end."""
+    n = 600
+    sizes = 8_000 + (np.arange(n) * 131) % 3001
+    single = native.Handle(0)
+    off_all = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    single.bev_generate(off_all, n_sweeps=4, seed=3)
+    pts = single.bev_get_points()
+    single.close()
+    ref_counts = B.bev_counts(pts, off_all)
+    lv = B.density_levels(ref_counts)
+    d2 = B.sq_distance_matrix(lv, lv)
+
+    def load_batch(h, lo, hi):
+        h.bev_set_points(pts[off_all[lo]:off_all[hi]], off_all[lo:hi + 1] - off_all[lo])
+
+    n_boxes = (np.arange(n) * 7 % 40).astype(np.int32)
+    ref = R.greedy_select(lambda i: d2[i].astype(np.float64), n, n_boxes, [], 11, "60", forbid_sampled=True)
+    w = sharded.LocalWorld(world, timeout=10.0)
+    try:
+        w.dense_build(n, 100, load_batch)
+        for r, h in enumerate(w.handles):
+            _, levels, norm2 = h.bev_get_descriptors(counts=False)
+            assert np.array_equal(levels, B.bf16_bits(lv))        # the full matrix, written by all ranks
+            assert np.array_equal(norm2.astype(np.int64), (lv.astype(np.int64) ** 2).sum(1))
+            lo, hi = sharded.shard_bounds(n, world, r)
+            assert np.array_equal(h.pairdist_get_rows(0, n).astype(np.int64), d2[:, lo:hi])
+        got, _ = w.dense_select(n_boxes, budget=60, first_index=11)
+        assert got == ref
+    finally:
+        w.close()
