@@ -209,7 +209,7 @@ def bev_extras(native, device, n_frames, n_boxes, first, peaks, reps=3, batch=20
             for lo in range(0, n_frames, batch):
                 hi = min(n_frames, lo + batch)
                 off = np.concatenate([[0], np.cumsum(sizes[lo:hi])]).astype(np.int64)
-                h.bev_generate(off, n_sweeps=10, seed=20221107 + lo)  # synthetic LiDAR generated in HBM (untimed)
+                h.bev_generate(off, n_sweeps=10, seed=20221107, first_frame=lo)  # synthetic LiDAR generated in HBM (untimed)
                 h.bev_build(frame_base=lo, total_frames=n_frames)
                 hist_ms[rep] += h.stage_ms()["bev_histogram"]
         ms = sum(hist_ms[1:]) / reps
@@ -239,10 +239,67 @@ def bev_extras(native, device, n_frames, n_boxes, first, peaks, reps=3, batch=20
         out["bev_selection_budget1200"] = {
             "workload": "BevSpatialSelector/budget1200/%d frames x ~300k points" % n_frames, "selected_frames": len(sel),
             "greedy_ms": ms_g, "us_per_step": ms_g * 1e3 / max(len(sel), 1), "ms_total": total,
-            "frames_per_s": n_frames / (total * 1e-3)}
+            "frames_per_s": n_frames / (total * 1e-3),
+            "selected_crc32": __import__("zlib").crc32(np.asarray(sel, dtype=np.int32).tobytes())}
     finally:
         h.close()
     return out
+
+
+def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_ranks, barrier, reps=2, batch=1024,
+                       pts_per_frame=300_000):
+    """BASELINE.json config 3 shape on N ranks: every rank histograms its own slice of the 28,130 frames x ~300k
+    points (descriptors stored into every rank's arena by the kernel epilogue), computes the tcgen05 distance
+    tiles of its column slice and runs the dense greedy loop (budget 1200) with one exchange per step."""
+    import numpy as np
+    w = world_engine
+    h = w.handle
+    sizes = pts_per_frame + (np.arange(n_frames, dtype=np.int64) * 977) % 4001 - 2000
+    lo, hi = w.handle.shard_range() if w._arena_shape else (0, 0)
+    hist_ms, pd_ms, g_ms, sel = [], [], [], None
+
+    def load_batch(handle, a, b):
+        off = np.concatenate([[0], np.cumsum(sizes[a:b])]).astype(np.int64)
+        handle.bev_generate(off, n_sweeps=10, seed=20221107, first_frame=a)   # synthetic LiDAR generated in HBM (untimed)
+        load_batch.ms += 0.0
+
+    load_batch.ms = 0.0
+    orig_bev_build = h.bev_build
+
+    def timed_bev_build(*a, **k):
+        orig_bev_build(*a, **k)
+        timed_bev_build.ms += h.stage_ms()["bev_histogram"]
+
+    timed_bev_build.ms = 0.0
+    h.bev_build = timed_bev_build
+    try:
+        for rep in range(reps + 1):                                   # rep 0 = warm-up
+            timed_bev_build.ms = 0.0
+            barrier()
+            w.dense_build(n_frames, batch, load_batch)
+            sel, _ = w.dense_select(n_boxes, budget=1200, first_index=first)
+            st = h.stage_ms()
+            if rep > 0:
+                hist_ms.append(timed_bev_build.ms)
+                pd_ms.append(st["pairdist"])
+                g_ms.append(st["dense_greedy"])
+    finally:
+        h.bev_build = orig_bev_build
+    lo, hi = h.shard_range()
+    my_pts = int(sizes[lo:hi].sum())
+    ms_h = max_over_ranks(sum(hist_ms) / len(hist_ms))
+    ms_p = max_over_ranks(sum(pd_ms) / len(pd_ms))
+    ms_g = max_over_ranks(sum(g_ms) / len(g_ms))
+    gbs_rank = (20.0 * my_pts + (hi - lo) * (16384 * (4 + 2 * w.world) + 4)) / (sum(hist_ms) / len(hist_ms) * 1e-3) / 1e9
+    tf_rank = 2.0 * n_frames * (hi - lo) * 16384 / (sum(pd_ms) / len(pd_ms) * 1e-3) / 1e12
+    total = ms_h + ms_p + ms_g
+    return {"bev_sharded_budget1200": {
+        "workload": "BevSpatialSelector/budget1200/%d frames x ~300k points sharded over %d GPUs" % (n_frames, w.world),
+        "selected_frames": len(sel), "histogram_ms": ms_h, "pairdist_ms_incl_2_barriers": ms_p, "greedy_ms": ms_g,
+        "us_per_step": ms_g * 1e3 / max(len(sel), 1), "ms_total": total, "frames_per_s": n_frames / (total * 1e-3),
+        "rank0_histogram_GBps": gbs_rank, "rank0_histogram_frac_of_hbm_peak": gbs_rank / peaks["hbm"],
+        "rank0_tiles_TFLOPs": tf_rank, "rank0_tiles_frac_of_bf16_peak": tf_rank / peaks["bf16"],
+        "selected_crc32": __import__("zlib").crc32(np.asarray(sel, dtype=np.int32).tobytes())}}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -395,6 +452,11 @@ def run_b200_arm(args):
             strong = {"workload": WORKLOAD + f" sharded over {world} GPUs", "pool_frames": len(infos28), "ms_per_step": ms28,
                       "frames_per_s": len(infos28) / (ms28 * 1e-3), "greedy_steps": h.counters()["steps"],
                       "identical_to_reference_golden": (golden28 == sel28) if golden28 is not None else None}
+            if not args.no_bev:
+                pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+                    os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+                peaks = {"hbm": float(pk.get("hbm_gbs", 6650.0)), "bf16": float(pk.get("bf16_tflops", 1590.0))}
+                bev_sh = bev_extras_sharded(h, len(infos28), pool.box_counts(infos28), first28, peaks, max_over_ranks, barrier)
         h.close()
 
         # ---- BEV-descriptor configuration: HBM-bound histogram and tensor-core distance tiles ----
@@ -408,6 +470,8 @@ def run_b200_arm(args):
             extras = bev_extras(native, local_rank, n, n_boxes, first, peaks)
         if strong is not None:
             extras = {"strong_p28k": strong}
+            if not args.no_bev:
+                extras.update(bev_sh)
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -152,9 +152,10 @@ __device__ __forceinline__ float u01(uint32_t h) { return (float)(h >> 8) * (1.0
 // nuScenes-like sweep: 32 beams fired per azimuth step, points stored in firing order; ranges
 // concentrated near the sensor; a fraction of returns leaves the [-51.2,51.2]^2 x [-5,3] box.
 __global__ void bev_generate_kernel(float *__restrict__ pts, const int64_t *__restrict__ frame_off, int n_frames,
-                                    int n_sweeps, uint32_t seed) {
-    for (int f = blockIdx.y; f < n_frames; f += gridDim.y) {
-        const int64_t p0 = frame_off[f], np = frame_off[f + 1] - p0;
+                                    int n_sweeps, uint32_t seed, uint32_t first_frame) {
+    for (int fb = blockIdx.y; fb < n_frames; fb += gridDim.y) {
+        const uint32_t f = first_frame + (uint32_t)fb;   // pool-wide frame id: the points do not depend on the batching
+        const int64_t p0 = frame_off[fb], np = frame_off[fb + 1] - p0;
         const int64_t per_sweep = (np + n_sweeps - 1) / n_sweeps;
         for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < np; i += (int64_t)gridDim.x * blockDim.x) {
             const int sweep = (int)(i / per_sweep);
@@ -214,7 +215,9 @@ int bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_off_hos
     ADSEL_REQUIRE(n_sweeps > 0, "adsel_bev_generate: n_sweeps must be positive");
     ADSEL_TRY(bev_layout(h, n_frames, frame_off_host));
     dim3 grid(64, (unsigned)min(n_frames, 4096));
-    bev_generate_kernel<<<grid, 256, 0, h->stream>>>(h->bev_pts.p, h->bev_off.p, n_frames, n_sweeps, (uint32_t)(seed ^ (seed >> 32)));
+    // seed: low 32 bits = generator seed, high 32 bits = pool index of the batch's first frame
+    bev_generate_kernel<<<grid, 256, 0, h->stream>>>(h->bev_pts.p, h->bev_off.p, n_frames, n_sweeps, (uint32_t)seed,
+                                                     (uint32_t)(seed >> 32));
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     ADSEL_CUDA(cudaStreamSynchronize(h->stream));

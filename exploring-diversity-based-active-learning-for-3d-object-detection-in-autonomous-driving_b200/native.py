@@ -338,10 +338,12 @@ class Handle:
         self.bev_batch, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
         _check(load().adsel_bev_set_points(self._h, _ptr(points), _ptr(frame_off), self.bev_batch))
 
-    def bev_generate(self, frame_off, n_sweeps=10, seed=20221107):
+    def bev_generate(self, frame_off, n_sweeps=10, seed=20221107, first_frame=0):
+        """Synthetic LiDAR for the batch whose first frame has pool index ``first_frame``."""
         frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
         self.bev_batch, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
-        _check(load().adsel_bev_generate(self._h, self.bev_batch, _ptr(frame_off), n_sweeps, seed))
+        _check(load().adsel_bev_generate(self._h, self.bev_batch, _ptr(frame_off), n_sweeps,
+                                         (int(seed) & 0xffffffff) | (int(first_frame) << 32)))
 
     def bev_get_points(self):
         pts = np.empty((self.bev_points, 5), dtype=np.float32)

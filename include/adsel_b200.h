@@ -163,7 +163,9 @@ typedef struct adsel_bev_params {
     int32_t reserved;
 } adsel_bev_params;
 int adsel_bev_set_points(adsel_handle *h, const float *points, const int64_t *frame_off, int32_t n_frames);
-/* synthetic multi-sweep LiDAR generated directly in HBM (counter-based hash keyed by frame/sweep) */
+/* synthetic multi-sweep LiDAR generated directly in HBM (counter-based hash keyed by frame/sweep);
+ * seed: low 32 bits = generator seed, high 32 bits = pool index of the batch's first frame, so that a frame's
+ * points do not depend on how the pool is cut into batches or shards */
 int adsel_bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_off, int32_t n_sweeps, uint64_t seed);
 int adsel_bev_get_points(adsel_handle *h, float *points);
 /* histogram + density level + squared norm for every frame of the resident point batch;
