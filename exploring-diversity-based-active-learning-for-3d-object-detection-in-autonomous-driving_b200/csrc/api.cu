@@ -102,7 +102,7 @@ int adsel_destroy(adsel_handle *h) {
     cudaStreamSynchronize(h->stream);
     comm_destroy(h);
     h->loc.release(); h->group_id.release(); h->n_boxes.release(); h->group_ptr.release(); h->group_members.release();
-    h->knn_idx.release(); h->knn_dist.release(); h->row_ptr.release(); h->col.release(); h->deg_own.release();
+    h->knn_idx.release(); h->knn_dist.release(); h->grid_cell.release(); h->grid_idx.release(); h->grid_start.release(); h->grid_loc.release(); h->row_ptr.release(); h->col.release(); h->deg_own.release();
     h->deg_rev.release(); h->w.release();
     h->sc_dist.release(); h->sc_stamp.release(); h->sc_q0.release(); h->sc_q1.release(); h->sc_touched.release();
     h->list_off.release(); h->list_len.release(); h->list_idx.release(); h->list_val.release(); h->cursor.release();
@@ -165,6 +165,16 @@ int adsel_set_pool(adsel_handle *h, int32_t n, const double *loc_xy, const int32
     {
         std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
         for (int i = 0; i < n; ++i) members[fill[group_id[i]]++] = i;
+    }
+    h->bbox[0] = h->bbox[2] = loc_xy[0];
+    h->bbox[1] = h->bbox[3] = loc_xy[1];
+    for (int i = 0; i < n; ++i) {
+        const double x = loc_xy[2 * i], y = loc_xy[2 * i + 1];
+        ADSEL_REQUIRE(x == x && y == y, "adsel_set_pool: NaN ego location");
+        h->bbox[0] = x < h->bbox[0] ? x : h->bbox[0];
+        h->bbox[1] = y < h->bbox[1] ? y : h->bbox[1];
+        h->bbox[2] = x > h->bbox[2] ? x : h->bbox[2];
+        h->bbox[3] = y > h->bbox[3] ? y : h->bbox[3];
     }
     h->max_group = 0;
     for (int g = 0; g < n_groups; ++g) h->max_group = ptr[g + 1] - ptr[g] > h->max_group ? ptr[g + 1] - ptr[g] : h->max_group;

@@ -105,6 +105,9 @@ struct adsel_handle {
     adsel::DevBuf<double> w;
     int64_t nnz = 0;
     bool graph_ready = false;
+    double bbox[4] = {0, 0, 0, 0};               // xmin, ymin, xmax, ymax of the ego locations
+    adsel::DevBuf<int32_t> grid_cell, grid_idx, grid_start;   // uniform grid of the kNN search
+    adsel::DevBuf<double2> grid_loc;
 
     // SSSP scratch (per resident CTA)
     int32_t sssp_ctas = 0;

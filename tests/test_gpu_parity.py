@@ -205,3 +205,26 @@ def test_cli_two_invocations_match_reference(pools, tmp_path):
     for b in golden["rounds"]:
         assert cli.main(["--config", str(cfg), "--budget", str(b)]) == 0
     assert json.load(open(buf)) == {"0": [], **golden["selected_index"]}
+
+
+def test_grid_knn_equals_bruteforce_on_tie_heavy_and_degenerate_inputs(handle, monkeypatch):
+    """The uniform-grid search and the brute-force scan are both exact with the same (d2, index) order:
+    integer lattices (masses of exact distance ties), duplicated points, a single cluster far from a few
+    outliers (almost everything in one cell) and collinear points must give identical tables."""
+    rng = np.random.default_rng(12)
+    lattice = np.stack(np.meshgrid(np.arange(48.0), np.arange(40.0)), -1).reshape(-1, 2)
+    dup = np.repeat(rng.uniform(0, 50, size=(400, 2)), 4, axis=0)
+    cluster = np.concatenate([rng.normal(0, 0.5, size=(3000, 2)), rng.uniform(-5e4, 5e4, size=(8, 2))])
+    line = np.stack([np.linspace(0, 900, 2500), np.zeros(2500)], 1)
+    for name, loc in (("lattice", lattice), ("dup", dup), ("cluster", cluster), ("line", line)):
+        loc = np.ascontiguousarray(loc[rng.permutation(len(loc))])
+        n = len(loc)
+        tables = {}
+        for mode in ("brute", "grid"):
+            monkeypatch.setenv("ADSEL_KNN", mode)
+            handle.set_pool(loc, np.zeros(n, np.int32), np.ones(n, np.int32))
+            handle.build_knn_graph(8)
+            tables[mode] = handle.get_knn()
+        assert np.array_equal(tables["brute"][1], tables["grid"][1]), name
+        assert np.array_equal(tables["brute"][0].view(np.uint64), tables["grid"][0].view(np.uint64)), name
+    monkeypatch.delenv("ADSEL_KNN")
