@@ -14,8 +14,8 @@ One "step" = one whole selection: kNN graph -> geodesic neighbour lists -> greed
   N > 1 : one process per GPU, the pool SHARDED by column over the N ranks (sharded.DistWorld: kNN rows
           stored into every rank's table over NVLink, one peer-memory mailbox exchange per greedy step,
           DESIGN.md §7).  "weak": the pool grows with N (N x 28,130 frames, the same generator with N x
-          the scenes -- BASELINE.json config 5 is the 10x pool), budget 4800 fixed; value = pool frames /
-          max-over-ranks time.  extras.strong_p28k reports the fixed 28,130-frame pool on the same N ranks.
+          the scenes over N x the area -- BASELINE.json config 5 is the 10x pool), budget 4800 fixed;
+          value = pool frames / max-over-ranks time.  extras.strong_p28k reports the fixed 28,130-frame pool on the same N ranks.
 
 ``--impl reference`` times the CPU implementation of the same workload on the host cores: the
 unmodified reference when /root/reference is present (this container), else the oracle port.
@@ -102,9 +102,11 @@ def workload_name(world):
 
 
 def make_pool(tmp, world=1):
+    """N ranks: N x the scenes over N x the area (box side x sqrt(N)), i.e. the pool's frame density per km^2 is
+    the one of P28K -- per-GPU work is fixed as N grows ("weak")."""
     from adsel_b200 import synthetic
     spec = pool_spec(world)
-    paths = synthetic.write_pool(spec, tmp)
+    paths = synthetic.write_pool(spec, tmp, box_m=1600.0 * max(world, 1) ** 0.5)
     return spec, paths
 
 
@@ -318,6 +320,8 @@ def run_b200_arm(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL's version banner goes to stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

@@ -25,7 +25,7 @@ int build_knn_graph(adsel_handle *h, int32_t k);
 int build_knn_graph_sharded(adsel_handle *h, int32_t k);
 void update_shard(adsel_handle *h);
 int knn_prepare(adsel_handle *h, int32_t k, bool own_tables);
-int greedy_prepare(adsel_handle *h, const adsel_select_params *p, int32_t n_sampled, int32_t out_cap);
+int greedy_prepare(adsel_handle *h, const adsel_select_params *p, int32_t n_sampled, int32_t out_cap, bool sharded);
 void comm_destroy(adsel_handle *h);
 int greedy_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
                                 int32_t first_index, int32_t out_cap);
@@ -255,7 +255,7 @@ int adsel_shard_prepare(adsel_handle *h, int32_t k, const adsel_select_params *p
     ADSEL_REQUIRE(h && p && h->n > 0 && out_cap > 0, "adsel_shard_prepare: set the pool first / null argument");
     ADSEL_CUDA(cudaSetDevice(h->device));
     if (p->spatial == ADSEL_SPATIAL_GEODESIC) ADSEL_TRY(knn_prepare(h, k, false));
-    ADSEL_TRY(greedy_prepare(h, p, n_sampled, out_cap));
+    ADSEL_TRY(greedy_prepare(h, p, n_sampled, out_cap, true));
     ADSEL_CUDA(cudaStreamSynchronize(h->stream));
     return ADSEL_OK;
 }

@@ -22,17 +22,23 @@ constexpr size_t COMM_ERROR_WORD = COMM_BARRIER_WORD + COMM_MAX_WORLD;       // 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct ArenaLayout {
-    size_t knn_idx, knn_dist, levels, norm2, total;
+    size_t knn_idx, knn_dist, levels, norm2, list_cursor, list_off, list_len, list_idx, list_val, total;
 };
-static ArenaLayout arena_layout(int64_t n, int64_t k1, int64_t dim) {
+static ArenaLayout arena_layout(int64_t n, int64_t k1, int64_t dim, int64_t list_cap) {
     ArenaLayout l;
     l.knn_idx = COMM_MAILBOX_BYTES;
     l.knn_dist = l.knn_idx + align256((size_t)n * k1 * sizeof(int32_t));
     l.levels = l.knn_dist + align256((size_t)n * k1 * sizeof(double));
     l.norm2 = l.levels + align256((size_t)n * dim * sizeof(uint16_t));
-    l.total = l.norm2 + align256((size_t)n * sizeof(int32_t));
+    l.list_cursor = l.norm2 + align256((size_t)n * sizeof(int32_t));
+    l.list_off = l.list_cursor + 256;
+    l.list_len = l.list_off + align256((size_t)n * sizeof(int64_t));
+    l.list_idx = l.list_len + align256((size_t)n * sizeof(int32_t));
+    l.list_val = l.list_idx + align256((size_t)list_cap * sizeof(int32_t));
+    l.total = l.list_val + align256((size_t)list_cap * sizeof(double));
     return l;
 }
+static ArenaLayout layout_of(const adsel_handle *h) { return arena_layout(h->arena_n, h->arena_k1, h->arena_dim, h->arena_list_cap); }
 
 void update_shard(adsel_handle *h) {
     if (h->world <= 1 || h->n <= 0) {
@@ -130,7 +136,8 @@ using namespace adsel;
 
 extern "C" {
 
-int adsel_comm_init(adsel_handle *h, int32_t rank, int32_t world, int32_t n, int32_t k, int32_t dim, void *ipc_handle_out) {
+int adsel_comm_init(adsel_handle *h, int32_t rank, int32_t world, int32_t n, int32_t k, int32_t dim, int64_t list_cap,
+                    void *ipc_handle_out) {
     ADSEL_REQUIRE(h, "adsel_comm_init: null handle");
     ADSEL_REQUIRE(world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world, "adsel_comm_init: need 0 <= rank < world <= 8");
     ADSEL_REQUIRE(n > 0 && k >= 0 && k < 64 && dim >= 0, "adsel_comm_init: bad arena shape");
@@ -138,13 +145,16 @@ int adsel_comm_init(adsel_handle *h, int32_t rank, int32_t world, int32_t n, int
     ADSEL_CUDA(cudaSetDevice(h->device));
     ADSEL_CUDA(cudaStreamSynchronize(h->stream));
     comm_release(h);
-    const ArenaLayout l = arena_layout(n, k + 1, dim);
+    // neighbour-list region: generous default (entries), a caller that saw an overflow passes what was needed
+    if (list_cap <= 0) list_cap = k > 0 ? (long long)n * 256 / world + (long long)n * 16 : 0;
+    const ArenaLayout l = arena_layout(n, k + 1, dim, list_cap);
     ADSEL_CUDA(cudaMalloc(&h->arena, l.total));
     ADSEL_CUDA(cudaMemset(h->arena, 0, COMM_MAILBOX_BYTES));
     h->arena_bytes = l.total;
     h->arena_n = n;
     h->arena_k1 = k + 1;
     h->arena_dim = dim;
+    h->arena_list_cap = list_cap;
     h->rank = rank;
     h->world = world;
     h->comm_seq = 0;
@@ -262,17 +272,21 @@ int adsel_shard_range(adsel_handle *h, int32_t *lo, int32_t *hi) {
 namespace adsel {
 
 // arena sub-buffers (same offsets on every rank)
-int32_t *arena_knn_idx(adsel_handle *h, int w) {
-    return reinterpret_cast<int32_t *>(h->peer_arena[w] + arena_layout(h->arena_n, h->arena_k1, h->arena_dim).knn_idx);
-}
-double *arena_knn_dist(adsel_handle *h, int w) {
-    return reinterpret_cast<double *>(h->peer_arena[w] + arena_layout(h->arena_n, h->arena_k1, h->arena_dim).knn_dist);
-}
-uint16_t *arena_levels(adsel_handle *h, int w) {
-    return reinterpret_cast<uint16_t *>(h->peer_arena[w] + arena_layout(h->arena_n, h->arena_k1, h->arena_dim).levels);
-}
-int32_t *arena_norm2(adsel_handle *h, int w) {
-    return reinterpret_cast<int32_t *>(h->peer_arena[w] + arena_layout(h->arena_n, h->arena_k1, h->arena_dim).norm2);
+int32_t *arena_knn_idx(adsel_handle *h, int w) { return reinterpret_cast<int32_t *>(h->peer_arena[w] + layout_of(h).knn_idx); }
+double *arena_knn_dist(adsel_handle *h, int w) { return reinterpret_cast<double *>(h->peer_arena[w] + layout_of(h).knn_dist); }
+uint16_t *arena_levels(adsel_handle *h, int w) { return reinterpret_cast<uint16_t *>(h->peer_arena[w] + layout_of(h).levels); }
+int32_t *arena_norm2(adsel_handle *h, int w) { return reinterpret_cast<int32_t *>(h->peer_arena[w] + layout_of(h).norm2); }
+ListStore arena_lists(adsel_handle *h, int w) {
+    const ArenaLayout l = layout_of(h);
+    unsigned char *a = h->peer_arena[w];
+    ListStore st;
+    st.off = reinterpret_cast<int64_t *>(a + l.list_off);
+    st.len = reinterpret_cast<int32_t *>(a + l.list_len);
+    st.idx = reinterpret_cast<int32_t *>(a + l.list_idx);
+    st.val = reinterpret_cast<double *>(a + l.list_val);
+    st.cursor = reinterpret_cast<unsigned long long *>(a + l.list_cursor);
+    st.capacity = h->arena_list_cap;
+    return st;
 }
 
 }  // namespace adsel

@@ -74,6 +74,17 @@ struct __align__(16) FrameRec {
     double box_cost;      // n_boxes * cost_b, rounded once (the reference's per-frame product)
 };
 
+// Where one rank's neighbour lists live: its own buffers, or the lists region of its arena (sharded, so that
+// the ranks that run the searches can append to it over NVLink).
+struct ListStore {
+    int64_t *off;                  // [n] first entry of every source's list
+    int32_t *len;                  // [n]
+    int32_t *idx;                  // [capacity] column (frame) of the entry
+    double *val;                   // [capacity] final row value distance_map[src][idx]
+    unsigned long long *cursor;    // [0] entries requested so far (may exceed capacity: overflow)
+    long long capacity;
+};
+
 // Parameters the precombined neighbour-list values depend on (lists are rebuilt when any changes).
 struct ListsKey {
     int norm_mode = -1, temporal = 0, aggregate = 0, lo = 0, hi = 0, pad = 0;
@@ -121,7 +132,9 @@ struct adsel_handle {
     adsel::DevBuf<double> list_val;
     adsel::DevBuf<unsigned long long> cursor;   // [0] entries reserved, [1] max finite bits
     int64_t list_total = 0;
-    long long list_capacity = 0;
+    long long list_capacity = 0;                 // capacity of the own buffers
+    adsel::ListStore lists = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};   // store in use (own buffers or arena)
+    long long arena_list_cap = 0;                // entries of the arena's list region
     int lists_mode = -1;                         // normalize mode the lists were built for (-1: none)
     adsel::ListsKey lists_key;
 

@@ -135,74 +135,82 @@ geodesic_rows_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restr
     if (max_finite_bits && threadIdx.x == 0) atomicMax(max_finite_bits, blk_max);
 }
 
-// Neighbour lists: for every source the vertices with d < radius that fall in this rank's column slice
-// [lo, hi), each with the FINAL row value distance_map[src][v]: the normalised spatial term
+// Neighbour lists: for every source of this rank's slice [src_lo, src_hi) the vertices with d < radius, each
+// with the FINAL row value distance_map[src][v]: the normalised spatial term
 // (spatial_temporal_selector.py:138-144) already aggregated with the temporal term of the pair
-// (:131-133,148-155), so that a greedy step needs no further lookups.  Lists are appended to one pool
-// through a global cursor; entries beyond `capacity` are counted but not written (the greedy kernel
-// sees cursor > capacity and reports it; the host grows the pool and reruns).
+// (:131-133,148-155), so that a greedy step needs no further lookups.  An entry belongs to the rank that owns
+// COLUMN v (the greedy loop is sharded by column): the searching CTA reserves room in that rank's pool with
+// one system-scope atomicAdd on its cursor and stores the entries and the list's offset / length there --
+// directly into peer memory when the owner is another GPU (the row -> column transposition of the sharded
+// build is fused into the search kernel).  Entries beyond an owner's capacity are counted but not written
+// (its greedy kernel sees cursor > capacity and reports it; the pool is grown and the build repeated).
 struct ListArgs {
-    int n, lo, hi;
+    int n, src_lo, src_hi;
     double radius;
     int norm_mode, temporal, aggregate;
     double divisor, lambda_t, t_far;
     const int32_t *group_id;
     const double *tlut;
+    int world, per;                 // owner of column v = min(v / per, world - 1)
+    ListStore dest[8];
 };
 
 __global__ void __launch_bounds__(SSSP_THREADS)
 geodesic_lists_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const double *__restrict__ w,
                       const ListArgs la,
-                      unsigned long long *sc_dist, int32_t *sc_stamp, int32_t *sc_q0, int32_t *sc_q1, int32_t *sc_touched,
-                      unsigned long long *__restrict__ cursor, long long capacity,
-                      int64_t *__restrict__ list_off, int32_t *__restrict__ list_len,
-                      int32_t *__restrict__ list_idx, double *__restrict__ list_val) {
+                      unsigned long long *sc_dist, int32_t *sc_stamp, int32_t *sc_q0, int32_t *sc_q1, int32_t *sc_touched) {
     __shared__ SsspShared sh;
-    __shared__ int n_keep, n_written;
-    __shared__ unsigned long long base_off;
+    __shared__ int n_keep[8], n_written[8], fits[8];
+    __shared__ unsigned long long base_off[8];
     if (threadIdx.x == 0) sh.tag = 0;
     const int n = la.n;
     const double radius = la.radius;
     const SsspScratch sc = scratch_of(sc_dist, sc_stamp, sc_q0, sc_q1, sc_touched, (size_t)n);
     __syncthreads();
-    for (int src = blockIdx.x; src < n; src += gridDim.x) {
+    for (int src = la.src_lo + blockIdx.x; src < la.src_hi; src += gridDim.x) {
         sssp_cta(row_ptr, col, w, src, radius, sc, sh);
         const int nt = sh.n_touched;
-        if (threadIdx.x == 0) {
-            n_keep = 0;
-            n_written = 0;
+        if (threadIdx.x < 8) {
+            n_keep[threadIdx.x] = 0;
+            n_written[threadIdx.x] = 0;
         }
         __syncthreads();
-        int mine = 0;
         for (int t = threadIdx.x; t < nt; t += SSSP_THREADS) {
             const int v = sc.touched[t];
             const double d = __longlong_as_double((long long)__ldcg(&sc.dist[v]));
-            mine += (d < radius && v >= la.lo && v < la.hi) ? 1 : 0;
+            if (d < radius) atomicAdd(&n_keep[min(v / la.per, la.world - 1)], 1);
         }
-        if (mine) atomicAdd(&n_keep, mine);
         __syncthreads();
-        if (threadIdx.x == 0) base_off = atomicAdd(cursor, (unsigned long long)n_keep);
+        if (threadIdx.x < la.world) {
+            const int o = threadIdx.x;
+            const unsigned long long b = n_keep[o] ? atomicAdd_system(la.dest[o].cursor, (unsigned long long)n_keep[o]) : 0ull;
+            base_off[o] = b;
+            fits[o] = (long long)(b + n_keep[o]) <= la.dest[o].capacity;
+        }
         __syncthreads();
-        const bool fits = (long long)(base_off + n_keep) <= capacity;
         const int gsrc = la.temporal ? la.group_id[src] : 0;
         for (int t = threadIdx.x; t < nt; t += SSSP_THREADS) {
             const int v = sc.touched[t];
             const double d = __longlong_as_double((long long)__ldcg(&sc.dist[v]));
-            if (d < radius && v >= la.lo && v < la.hi && fits) {
-                const int pos = atomicAdd(&n_written, 1);
-                double val = normalize_value(d, la.norm_mode, la.divisor);
-                if (la.temporal) {
-                    const double tv = la.group_id[v] == gsrc ? la.tlut[abs(v - src)] : la.t_far;
-                    val = aggregate_value(val, tv, la.aggregate, la.lambda_t);
+            if (d < radius) {
+                const int o = min(v / la.per, la.world - 1);
+                if (fits[o]) {
+                    const int pos = atomicAdd(&n_written[o], 1);
+                    double val = normalize_value(d, la.norm_mode, la.divisor);
+                    if (la.temporal) {
+                        const double tv = la.group_id[v] == gsrc ? la.tlut[abs(v - src)] : la.t_far;
+                        val = aggregate_value(val, tv, la.aggregate, la.lambda_t);
+                    }
+                    la.dest[o].idx[base_off[o] + pos] = v;
+                    la.dest[o].val[base_off[o] + pos] = val;
                 }
-                list_idx[base_off + pos] = v;
-                list_val[base_off + pos] = val;
             }
             sc.dist[v] = INF_BITS;
         }
-        if (threadIdx.x == 0) {
-            list_off[src] = (int64_t)base_off;
-            list_len[src] = fits ? n_keep : 0;
+        if (threadIdx.x < la.world) {
+            const int o = threadIdx.x;
+            la.dest[o].off[src] = (int64_t)base_off[o];
+            la.dest[o].len[src] = fits[o] ? n_keep[o] : 0;
         }
         __syncthreads();
     }
@@ -275,10 +283,17 @@ int geodesic_max_finite(adsel_handle *h, double *out) {
     return ADSEL_OK;
 }
 
-// Allocations of the list build (scratch, offsets, entry pool); never shrinks.
-int lists_prepare(adsel_handle *h) {
+ListStore arena_lists(adsel_handle *h, int w);
+int comm_barrier(adsel_handle *h);
+
+// Allocations of the list build (scratch, offsets, entry pool); never shrinks.  Selects the store in use.
+int lists_prepare(adsel_handle *h, bool sharded) {
     const int n = h->n;
     ADSEL_TRY(ensure_scratch(h));
+    if (sharded) {
+        h->lists = arena_lists(h, h->rank);
+        return ADSEL_OK;
+    }
     ADSEL_TRY(h->cursor.reserve(2));
     ADSEL_TRY(h->list_off.reserve(n));
     ADSEL_TRY(h->list_len.reserve(n));
@@ -288,6 +303,7 @@ int lists_prepare(adsel_handle *h) {
         ADSEL_TRY(h->list_val.reserve(capacity));
         h->list_capacity = capacity;
     }
+    h->lists = ListStore{h->list_off.p, h->list_len.p, h->list_idx.p, h->list_val.p, h->cursor.p, h->list_capacity};
     return ADSEL_OK;
 }
 
@@ -297,30 +313,35 @@ int grow_lists(adsel_handle *h, long long needed) {
     ADSEL_TRY(h->list_idx.reserve(capacity));
     ADSEL_TRY(h->list_val.reserve(capacity));
     h->list_capacity = capacity;
+    h->lists = ListStore{h->list_off.p, h->list_len.p, h->list_idx.p, h->list_val.p, h->cursor.p, h->list_capacity};
     h->lists_mode = -1;
     return ADSEL_OK;
 }
 
 // Enqueues the neighbour-list build for these selection parameters unless the resident lists were
 // built for the same ones; radius is 38 for exp, inf otherwise.  h->tlut must already be enqueued.
-int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, int lo, int hi) {
+// sharded: this rank searches from the sources of its slice and appends every entry to the pool of the rank
+// that owns the entry's column; device barriers separate cursor reset / build / use across ranks.
+int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, bool sharded) {
     ADSEL_REQUIRE(h->graph_ready, "adsel_select: call adsel_build_knn_graph first");
+    const int n = h->n;
+    const int lo = sharded ? h->shard_lo : 0, hi = sharded ? h->shard_hi : n;
     ListsKey key;
     key.norm_mode = p->normalize;
     key.temporal = p->temporal ? 1 : 0;
     key.aggregate = key.temporal ? p->aggregate : 0;
     key.lo = lo;
-    key.hi = hi;
+    key.hi = sharded ? -hi : hi;     // a sharded build never matches a single-GPU one
     key.max_spatial = p->normalize == ADSEL_NORM_LINEAR ? p->max_spatial : 0.0;
     key.max_temporal = (key.temporal && p->normalize == ADSEL_NORM_LINEAR) ? p->max_temporal : 0.0;
     key.lambda_t = (key.temporal && p->aggregate == ADSEL_AGG_SUM) ? p->lambda_t : 0.0;
-    if (h->lists_mode >= 0 && memcmp(&key, &h->lists_key, sizeof(key)) == 0) return ADSEL_OK;
-    const int n = h->n;
-    ADSEL_TRY(lists_prepare(h));
+    if (h->lists_mode >= 0 && memcmp(&key, &h->lists_key, sizeof(key)) == 0) return ADSEL_OK;   // same decision on every rank
+    ADSEL_TRY(lists_prepare(h, sharded));
     ListArgs la;
+    memset(&la, 0, sizeof(la));
     la.n = n;
-    la.lo = lo;
-    la.hi = hi;
+    la.src_lo = lo;
+    la.src_hi = hi;
     la.radius = p->normalize == ADSEL_NORM_EXP ? 38.0 : host_inf();
     la.norm_mode = p->normalize;
     la.temporal = key.temporal;
@@ -330,13 +351,26 @@ int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, int
     la.t_far = t_far;
     la.group_id = h->group_id.p;
     la.tlut = h->tlut.p;
+    if (sharded) {
+        la.world = h->world;
+        long long per = ((long long)n + h->world - 1) / h->world;
+        la.per = (int)((per + 255) / 256 * 256);
+        for (int w = 0; w < h->world; ++w) la.dest[w] = arena_lists(h, w);
+    } else {
+        la.world = 1;
+        la.per = n;
+        la.dest[0] = h->lists;
+    }
     ADSEL_TRY(clear_stamps(h));
-    ADSEL_CUDA(cudaMemsetAsync(h->cursor.p, 0, 2 * sizeof(unsigned long long), h->stream));
-    geodesic_lists_kernel<<<min(h->sssp_ctas, n), SSSP_THREADS, 0, h->stream>>>(
-        h->row_ptr.p, h->col.p, h->w.p, la, h->sc_dist.p, h->sc_stamp.p, h->sc_q0.p, h->sc_q1.p, h->sc_touched.p,
-        h->cursor.p, h->list_capacity, h->list_off.p, h->list_len.p, h->list_idx.p, h->list_val.p);
-    h->launches += 1;
-    ADSEL_CUDA(cudaGetLastError());
+    ADSEL_CUDA(cudaMemsetAsync(h->lists.cursor, 0, 2 * sizeof(unsigned long long), h->stream));
+    if (sharded) ADSEL_TRY(comm_barrier(h));      // every rank's cursor is reset before anyone appends
+    if (hi > lo) {
+        geodesic_lists_kernel<<<min(h->sssp_ctas, hi - lo), SSSP_THREADS, 0, h->stream>>>(
+            h->row_ptr.p, h->col.p, h->w.p, la, h->sc_dist.p, h->sc_stamp.p, h->sc_q0.p, h->sc_q1.p, h->sc_touched.p);
+        h->launches += 1;
+        ADSEL_CUDA(cudaGetLastError());
+    }
+    if (sharded) ADSEL_TRY(comm_barrier(h));      // every rank's entries have landed in this rank's pool
     h->lists_mode = p->normalize;
     h->lists_key = key;
     return ADSEL_OK;

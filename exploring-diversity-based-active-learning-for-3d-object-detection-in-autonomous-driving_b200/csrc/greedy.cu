@@ -471,8 +471,8 @@ static double host_normalize_far(int norm_mode, double d, double divisor) {
     return d;
 }
 
-int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, int lo, int hi);
-int lists_prepare(adsel_handle *h);
+int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, bool sharded);
+int lists_prepare(adsel_handle *h, bool sharded);
 int grow_lists(adsel_handle *h, long long needed);
 int comm_view(adsel_handle *h, CommView *view);
 
@@ -550,9 +550,9 @@ static int validate_select(adsel_handle *h, const adsel_select_params *p, const 
 // Allocations of a selection (separate from the enqueue so that a host thread driving several ranks
 // can finish every cudaMalloc/cudaFree -- which may synchronise the device -- before any rank's
 // persistent kernel starts waiting for its peers).
-int greedy_prepare(adsel_handle *h, const adsel_select_params *p, int32_t n_sampled, int32_t out_cap) {
+int greedy_prepare(adsel_handle *h, const adsel_select_params *p, int32_t n_sampled, int32_t out_cap, bool sharded) {
     const int n = h->n;
-    if (p->spatial == ADSEL_SPATIAL_GEODESIC) ADSEL_TRY(lists_prepare(h));
+    if (p->spatial == ADSEL_SPATIAL_GEODESIC) ADSEL_TRY(lists_prepare(h, sharded));
     ADSEL_TRY(h->fps.reserve(n));
     ADSEL_TRY(h->frame_rec.reserve(n));
     ADSEL_TRY(h->is_selected.reserve(n));
@@ -560,7 +560,6 @@ int greedy_prepare(adsel_handle *h, const adsel_select_params *p, int32_t n_samp
     ADSEL_TRY(h->d_sampled.reserve(n_sampled > 0 ? n_sampled : 1));
     ADSEL_TRY(h->d_out.reserve(out_cap));
     ADSEL_TRY(h->d_result.reserve(8));
-    ADSEL_TRY(h->cursor.reserve(2));
     return ADSEL_OK;
 }
 
@@ -577,7 +576,7 @@ static int enqueue_lists(adsel_handle *h, const adsel_select_params *p, bool sha
         ADSEL_CUDA(cudaGetLastError());
     }
     if (p->spatial == ADSEL_SPATIAL_GEODESIC)
-        ADSEL_TRY(build_lists(h, p, far_temporal(p), sharded ? h->shard_lo : 0, sharded ? h->shard_hi : n));
+        ADSEL_TRY(build_lists(h, p, far_temporal(p), sharded));
     return ADSEL_OK;
 }
 
@@ -618,8 +617,8 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
     memcpy(&far_bits, &far, 8);
 
     const bool lists = p->spatial == ADSEL_SPATIAL_GEODESIC;
-    frame_rec_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->frame_rec.p, n, lists ? h->list_off.p : nullptr,
-                                                             lists ? h->list_len.p : nullptr, h->group_id.p, h->group_ptr.p,
+    frame_rec_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->frame_rec.p, n, lists ? h->lists.off : nullptr,
+                                                             lists ? h->lists.len : nullptr, h->group_id.p, h->group_ptr.p,
                                                              h->n_boxes.p, p->cost_b);
     h->launches += 1;
 
@@ -631,13 +630,13 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
     a.n_sampled = n_sampled;
     a.first_index = first_index;
     a.out_cap = out_cap;
-    a.list_capacity = lists ? h->list_capacity : 0;
-    a.list_cursor = lists ? h->cursor.p : nullptr;
+    a.list_capacity = lists ? h->lists.capacity : 0;
+    a.list_cursor = lists ? h->lists.cursor : nullptr;
     a.rec = h->frame_rec.p;
     a.loc = h->loc.p;
     a.group_members = h->group_members.p;
-    a.list_idx = h->list_idx.p;
-    a.list_val = h->list_val.p;
+    a.list_idx = h->lists.idx;
+    a.list_val = h->lists.val;
     a.tlut = h->tlut.p;
     a.fps = h->fps.p;
     a.is_selected = h->is_selected.p;
@@ -703,7 +702,7 @@ int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *
                   int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {
     ADSEL_TRY(validate_select(h, p, sampled, n_sampled, first_index, out_cap));
     ADSEL_REQUIRE(out_idx && out_m, "adsel_select: null argument");
-    ADSEL_TRY(greedy_prepare(h, p, n_sampled, out_cap));
+    ADSEL_TRY(greedy_prepare(h, p, n_sampled, out_cap, false));
     for (int attempt = 0; attempt < 2; ++attempt) {
         ADSEL_TRY(begin_stage(h));
         ADSEL_TRY(enqueue_lists(h, p, false));
@@ -739,7 +738,7 @@ int greedy_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, c
     ADSEL_TRY(validate_select(h, p, sampled, n_sampled, first_index, out_cap));
     ADSEL_REQUIRE(h->comm_ready, "adsel_select_sharded_begin: call adsel_comm_init / adsel_comm_attach first");
     ADSEL_REQUIRE(!h->pending, "adsel_select_sharded_begin: a sharded selection is already pending");
-    ADSEL_TRY(greedy_prepare(h, p, n_sampled, out_cap));
+    ADSEL_TRY(greedy_prepare(h, p, n_sampled, out_cap, true));
     ADSEL_CUDA(cudaEventRecord(h->pending_ev[0], h->stream));
     ADSEL_TRY(enqueue_lists(h, p, true));
     ADSEL_TRY(enqueue_greedy(h, p, sampled, n_sampled, first_index, out_cap, true));
@@ -765,7 +764,9 @@ int greedy_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap
     // moved to a fresh epoch (all ranks observe the same failure through the exchanged abort record)
     if (status == 0 || status == ADSEL_ERR_RESELECTED) h->comm_seq += (unsigned)result[3];
     else h->comm_seq = ((h->comm_seq >> 24) + 1u) << 24;
-    if (status == ADSEL_ERR_CAPACITY && result[4] == -1.0) ADSEL_TRY(grow_lists(h, (long long)result[5]));
+    // an overflowing list region of the arena cannot grow in place: the caller re-creates the arenas with
+    // adsel_comm_init(list_cap = the largest adsel_get_counters()[2] over the ranks) and rebuilds
+    if (status != 0) h->lists_mode = -1;
     return finish_select(h, result, out_idx, out_m, out_cost, "adsel_select_sharded");
 }
 

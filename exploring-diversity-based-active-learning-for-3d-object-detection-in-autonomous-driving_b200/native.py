@@ -70,7 +70,8 @@ _SIGNATURES = {
     "adsel_pairdist_get_rows": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P]),
     "adsel_select_dense": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, _P, ctypes.c_int32, ctypes.c_int32, _P,
                                           ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
-    "adsel_comm_init": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),
+    "adsel_comm_init": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_int64, _P]),
     "adsel_comm_attach": (ctypes.c_int, [_P, _P]),
     "adsel_comm_detach": (ctypes.c_int, [_P]),
     "adsel_comm_attach_local": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
@@ -236,10 +237,10 @@ class Handle:
         return out[: m.value].tolist(), cost.value
 
     # -- pool sharded over several ranks ---------------------------------------
-    def comm_init(self, rank, world, n, k=8, dim=0) -> bytes:
+    def comm_init(self, rank, world, n, k=8, dim=0, list_cap=0) -> bytes:
         """Allocate the peer-visible arena; returns this rank's 64-byte CUDA IPC handle."""
         out = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
-        _check(load().adsel_comm_init(self._h, int(rank), int(world), int(n), int(k), int(dim), out))
+        _check(load().adsel_comm_init(self._h, int(rank), int(world), int(n), int(k), int(dim), int(list_cap), out))
         self.rank, self.world = int(rank), int(world)
         return out.raw
 

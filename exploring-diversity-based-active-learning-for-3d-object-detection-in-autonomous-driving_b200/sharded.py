@@ -46,6 +46,7 @@ class _WorldBase:
         self._pool = None
         self._pool_dirty = False
         self._arena_shape = None
+        self._list_cap = 0          # entries of every rank's neighbour-list region (0: library default)
 
     def set_pool(self, loc_xy, group_id, n_boxes):
         self._pool = (np.ascontiguousarray(loc_xy, dtype=np.float64), np.ascontiguousarray(group_id, dtype=np.int32),
@@ -71,10 +72,10 @@ class LocalWorld(_WorldBase):
         self.handles = []
 
     def _ensure(self, k: int, dim: int = 0):
-        shape = (self.n, int(k), int(dim))
+        shape = (self.n, int(k), int(dim), self._list_cap)
         if self._arena_shape != shape:
             for r, h in enumerate(self.handles):
-                h.comm_init(r, self.world, self.n, k, dim)
+                h.comm_init(r, self.world, self.n, k, dim, self._list_cap)
                 h.comm_set_timeout(self.timeout)
             for h in self.handles:
                 h.comm_attach_local(self.handles)
@@ -167,7 +168,9 @@ class LocalWorld(_WorldBase):
                     error = error or e
             if error is not None and not retry:
                 raise error
-            if retry:
+            if retry:       # a rank's list region overflowed: new arenas sized for the largest need, graph rebuilt
+                self._list_cap = int(max(h.counters()["list_entries"] for h in self.handles) * 1.1) + 1024
+                self.build_knn_graph(self.k)
                 continue
             assert all(r == results[0] for r in results), "ranks disagree on the selection"
             return results[0]
@@ -211,12 +214,12 @@ class DistWorld(_WorldBase):
             self.handle = None
 
     def _ensure(self, k: int, dim: int = 0):
-        shape = (self.n, int(k), int(dim))
+        shape = (self.n, int(k), int(dim), self._list_cap)
         if self._arena_shape != shape:
             if self._arena_shape is not None:       # nobody may still map an arena that is about to be freed
                 self.handle.comm_detach()
                 self._dist.barrier(group=self.group)
-            ipc = self.handle.comm_init(self.rank, self.world, self.n, k, dim)
+            ipc = self.handle.comm_init(self.rank, self.world, self.n, k, dim, self._list_cap)
             self.handle.comm_set_timeout(self.timeout)
             gathered = [None] * self.world
             self._dist.all_gather_object(gathered, ipc, group=self.group)   # 64 bytes per rank, once per pool shape
@@ -263,7 +266,10 @@ class DistWorld(_WorldBase):
             try:
                 return self.handle.select_sharded_end()
             except native.RetrySharded:      # raised on EVERY rank by the same call: the loop stays collective
-                continue
+                needs = [None] * self.world
+                self._dist.all_gather_object(needs, self.handle.counters()["list_entries"], group=self.group)
+                self._list_cap = int(max(needs) * 1.1) + 1024
+                self.build_knn_graph(self.k)    # new arenas sized for the largest need, graph rebuilt
         raise native.NativeError(native.ERR_CAPACITY, "sharded selection kept overflowing its neighbour-list pools")
 
     def get_fps(self):

@@ -132,8 +132,9 @@ int adsel_get_counters(adsel_handle *h, int64_t *c4);
  * calls only enqueue work (no host synchronisation, no allocation after a first call of the same
  * shape), so one host thread may also drive several handles (adsel_comm_attach_local: ranks that live in
  * one process, on one or several devices).  All ranks must make the same sequence of sharded calls. */
-/* n, k, dim size the peer-visible arena (kNN tables [n,k+1], descriptors [n,dim]); identical on all ranks. */
-int adsel_comm_init(adsel_handle *h, int32_t rank, int32_t world, int32_t n, int32_t k, int32_t dim,
+/* n, k, dim, list_cap size the peer-visible arena (kNN tables [n,k+1], descriptors [n,dim], list_cap
+ * neighbour-list entries; 0 = default 256 n / world + 16 n); identical on all ranks. */
+int adsel_comm_init(adsel_handle *h, int32_t rank, int32_t world, int32_t n, int32_t k, int32_t dim, int64_t list_cap,
                     void *ipc_handle_out /* 64 bytes, may be NULL */);
 int adsel_comm_attach(adsel_handle *h, const void *ipc_handles /* world x 64 bytes, rank order */);
 int adsel_comm_detach(adsel_handle *h);   /* unmap the peers' arenas; every rank does this before any rank re-sizes or frees */
@@ -147,8 +148,10 @@ int adsel_shard_range(adsel_handle *h, int32_t *lo, int32_t *hi);   /* this rank
 int adsel_shard_prepare(adsel_handle *h, int32_t k, const adsel_select_params *p, int32_t n_sampled, int32_t out_cap);
 int adsel_build_knn_graph_sharded(adsel_handle *h, int32_t k);
 /* as adsel_select, split in two: `begin` enqueues lists + greedy loop, `end` waits and returns the result
- * (identical on every rank).  ADSEL_ERR_CAPACITY / ADSEL_ERR_PEER_ABORT from `end` on all ranks means a
- * rank's neighbour-list pool was too small; it has been grown -- call begin/end again on every rank. */
+ * (identical on every rank).  The neighbour lists are searched from the sources of the rank's slice and every
+ * entry is appended, over NVLink, to the pool of the rank owning its column.  ADSEL_ERR_CAPACITY /
+ * ADSEL_ERR_PEER_ABORT from `end` on all ranks means a rank's list region was too small: re-create the arenas
+ * with list_cap >= the largest adsel_get_counters()[2] over the ranks, rebuild the graph and call again. */
 int adsel_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled,
                                int32_t n_sampled, int32_t first_index, int32_t out_cap);
 int adsel_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);

@@ -28,7 +28,7 @@ class FakeShardHandle:
         self.calls.append("close")
 
     # -- comm ---------------------------------------------------------------------------------
-    def comm_init(self, rank, world, n, k=8, dim=0):
+    def comm_init(self, rank, world, n, k=8, dim=0, list_cap=0):
         self.rank, self.world, self.arena = rank, world, (n, k, dim)
         self.attached = world == 1
         self.calls.append(("comm_init", rank, world, n, k, dim))

@@ -248,3 +248,30 @@ def test_sharded_bev_pipeline_descriptors_gathered_by_the_histogram_kernel(world
         assert got == ref
     finally:
         w.close()
+
+
+def test_p281k_budget_4800_single_gpu_and_sharded(pools):
+    """BASELINE.json config 5: the 281,300-frame pool.  The dense reference cannot run it (633 GB per map);
+    the fixture comes from the streaming restatement (oracle/make_golden_p281k.py), itself pinned against the
+    reference on the smaller pools."""
+    golden = load_golden("P281K_st_restatement.json")
+    from adsel_b200 import synthetic
+    infos, _ = synthetic.generate_pool(synthetic.P281K)
+    assert len(infos) == golden["n_frames"]
+    loc, run_id, max_td, n_boxes = _arrays(infos)
+    kw = dict(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0, budget=4800,
+              first_index=golden["first_index"])
+    single = native.Handle(0)
+    single.set_pool(loc, run_id, n_boxes)
+    single.build_knn_graph(8)
+    got, _ = single.select(**kw)
+    single.close()
+    assert got == golden["selected_index"]["4800"]
+    w = sharded.LocalWorld(8, timeout=60.0)
+    try:
+        w.set_pool(loc, run_id, n_boxes)
+        w.build_knn_graph(8)
+        got8, _ = w.select(**kw)
+        assert got8 == golden["selected_index"]["4800"]
+    finally:
+        w.close()
