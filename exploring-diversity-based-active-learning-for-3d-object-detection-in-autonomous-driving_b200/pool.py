@@ -72,3 +72,54 @@ def city_groups(names, logs) -> np.ndarray:
 def box_counts(infos) -> np.ndarray:
     """``info["gt_names"].shape[0]`` per frame (base_selector.py:85)."""
     return np.fromiter((info["gt_names"].shape[0] for info in infos), dtype=np.int32, count=len(infos))
+
+
+def extract_spatial_temporal(infos, known_logfiles=None):
+    """Everything SpatialTemporalSelector needs from the infos list: ``(locations, run_id, max_td, n_boxes)``.
+
+    Under torch.distributed (more than one rank) the per-frame python work -- string parsing, stacking the 4x4
+    poses, counting boxes: O(pool) and, at tens of microseconds per frame, most of the end-to-end time -- is
+    done by every rank for ITS slice of the pool only; the slices (a few hundred KB) are exchanged with one
+    ``all_gather_object`` and every rank assembles the same full arrays.  Run ids are consecutive-run ids of
+    the whole list, so the boundaries between slices are merged from the neighbouring names.
+    ``known_logfiles``: the reference raises ``KeyError`` for a frame whose logfile is not in ``logs_file``
+    (spatial_temporal_selector.py:80); here every rank raises it when any rank finds one.
+    """
+    from .dist import get_dist_info
+    rank, world = get_dist_info()
+    n = len(infos)
+    if world <= 1 or n < 4 * world:
+        names = logfile_names(infos)
+        if known_logfiles is not None:
+            for nm in names:
+                if nm not in known_logfiles:
+                    raise KeyError(nm)
+        run_id, max_td = consecutive_runs(names)
+        return ego_locations(infos), run_id, max_td, box_counts(infos)
+    import torch.distributed as dist
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    part = infos[lo:hi]
+    names = logfile_names(part)
+    missing = None
+    if known_logfiles is not None:
+        missing = next((nm for nm in names if nm not in known_logfiles), None)
+    arr = np.asarray(names, dtype=object)
+    change = np.ones(len(names), dtype=bool)            # change[0] is fixed up against the previous slice's last name
+    change[1:] = arr[1:] != arr[:-1]
+    mine = {"lo": lo, "missing": missing, "first": names[0], "last": names[-1], "change": np.packbits(change),
+            "n": len(names), "loc": ego_locations(part), "boxes": box_counts(part)}
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    for p in parts:
+        if p["missing"] is not None:
+            raise KeyError(p["missing"])
+    change = np.concatenate([np.unpackbits(p["change"])[: p["n"]].astype(bool) for p in parts])
+    for prev, cur in zip(parts, parts[1:]):
+        change[cur["lo"]] = prev["last"] != cur["first"]
+    run_id = (np.cumsum(change) - 1).astype(np.int32)
+    starts = np.flatnonzero(change)
+    lengths = np.diff(np.append(starts, n))
+    max_td = int(lengths[:-1].max()) if len(lengths) > 1 else 0
+    loc = np.ascontiguousarray(np.concatenate([p["loc"] for p in parts]))
+    boxes = np.concatenate([p["boxes"] for p in parts]).astype(np.int32)
+    return loc, run_id, max_td, boxes

@@ -39,16 +39,12 @@ class SpatialTemporalSelector(BaseSelector):
 
     def select_samples(self, **kwargs) -> None:
         infos = self.infos_origin
-        names = pool.logfile_names(infos)
-        known = {l["logfile"] for l in load(self.logs_file)}
-        for nm in names:                                  # the reference raises KeyError at :80
-            if nm not in known:
-                raise KeyError(nm)
-        locations = pool.ego_locations(infos)             # :83-91
-        run_id, max_td = pool.consecutive_runs(names)     # :114-129
+        known = {l["logfile"] for l in load(self.logs_file)}           # the reference raises KeyError at :80
+        # :83-91 ego locations, :114-129 consecutive logfile runs, base_selector.py:85 box counts
+        locations, run_id, max_td, n_boxes = pool.extract_spatial_temporal(infos, known)
         handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's shard
         try:
-            handle.set_pool(locations, run_id, pool.box_counts(infos))
+            handle.set_pool(locations, run_id, n_boxes)
             handle.build_knn_graph(self.k)                # :93-101 (+ scipy's dense->CSR rules)
             max_sd = handle.geodesic_max_finite() if self.normalize == "linear" else 0.0   # :139
             self._run_greedy(handle, spatial="geodesic", temporal=True, normalize=self.normalize,
