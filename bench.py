@@ -497,8 +497,12 @@ def run_b200_arm(args):
         alg_bytes = 16.0 * n + 12.0 * 9 * n
         kernel = "knn_bruteforce_kernel"
     achieved = alg_bytes / (stages[dominant] * 1e-3) / 1e9
+    traffic = None        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same workload, N = 1)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if world == 1 and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(kernel, {}).get("bytes")
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "latency-bound dependency chain (one CTA, %d sequential steps, %.2f us/step); see DESIGN.md §6"
                         % (steps_per_sel, stages["greedy"] * 1e3 / max(steps_per_sel, 1))}
 

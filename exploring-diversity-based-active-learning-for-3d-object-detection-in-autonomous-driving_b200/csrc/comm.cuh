@@ -85,14 +85,15 @@ __device__ __forceinline__ ExchangeLane make_exchange_lane(const CommView &c) {
 // every rank (itself included) and returns the global winner, identical on every rank:
 // larger key first, then lower index -- np.argmax's first-maximum rule across shards.
 // index == COMM_ABORT_INDEX posts an abort that every rank observes in the same exchange.
+// post == false: only wait for the records (another CTA of this rank's cluster posts the rank's record).
 __device__ __forceinline__ ExchangeResult exchange_best(const CommView &c, const ExchangeLane &e, unsigned tag,
-                                                        unsigned long long key, unsigned index) {
+                                                        unsigned long long key, unsigned index, bool post = true) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const size_t parity_off = (size_t)(tag & 1u) * COMM_MAX_WORLD * COMM_SLOT_WORDS;
     const int word = lane % 3;
     const bool active = e.active;
-    if (active) {
+    if (active && post) {
         const unsigned long long payload = word == 0 ? (key >> 32) : word == 1 ? (key & 0xffffffffull) : (unsigned long long)index;
         st_relaxed_sys(e.post + parity_off, (payload << 32) | tag);
     }

@@ -159,6 +159,7 @@ struct adsel_handle {
     adsel::DevBuf<double> tlut;
     adsel::DevBuf<int32_t> d_sampled, d_out;
     adsel::DevBuf<double> d_result;              // [0] cost, [1] status, [2] m, [3] steps, [4] offending frame
+    int greedy_cluster = 0;                      // cluster size of the last greedy launch (0: global-memory variant)
     bool groups_contiguous = false;              // every group is one contiguous index range (consecutive runs)
 
     // pool sharding across ranks (comm.cu): this rank owns frames [shard_lo, shard_hi)

@@ -27,6 +27,8 @@
 // exact and "first index among bit-equal maxima" is well defined.
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "comm.cuh"
 #include "common.cuh"
 
@@ -37,11 +39,13 @@ constexpr int MAX_BLKS = 9800;        // 20 B of shared memory per block + 32 KB
 
 struct GreedyArgs {
     int n, nblk, lo, hi, blk_lo, blk_hi, tl_n, sel_words;
+    int csize, cta_cols;   // cluster variant: CTAs per cluster, columns per CTA (multiple of 256)
     int spatial, temporal, aggregate, groups_contiguous, pull;
     double lambda_t, s_far, t_far;
     double cost_b, cost_f, cost_start, budget;
     int forbid_sampled, n_sampled, first_index, out_cap;
     long long list_capacity;
+    unsigned long long far_bits;             // ordered key of the value every untouched row entry takes
     const unsigned long long *list_cursor;   // [0] entries the list build needed (overflow check)
     const FrameRec *rec;
     const double2 *loc;
@@ -439,6 +443,279 @@ __global__ void __launch_bounds__(NT, 1) greedy_select_kernel(const GreedyArgs a
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster variant: fps lives in SHARED memory, split over the CTAs of one thread-block cluster.
+//
+// In the single-CTA kernel above the min-distance vector lives in L2 and every step pays an
+// atomicMin (RED) round trip followed by a re-read of the dirtied blocks -- the longest link of the
+// dependency chain.  Here the rank's columns are cut into `csize` contiguous pieces, one per CTA of a
+// cluster (csize = 2 for the 28,130-frame pool: 110 KB of shared memory each), so that
+//   * a row update is a plain shared-memory min (every touched column is written by exactly one thread:
+//     list entries are unique per list, the group is applied in a second phase),
+//   * the arg-max is a scan of the CTA's own shared-memory slice (no dirty tracking, no block maxima),
+//   * the CTAs exchange their local maxima through distributed shared memory with the mailbox protocol of
+//     comm.cuh (tagged self-validating 8-byte words, st.shared::cluster + poll; no cluster barrier in the
+//     loop, so L1 -- which holds the prefetched frame records and the lists -- is never flushed),
+//   * every CTA does the cost bookkeeping redundantly; cluster rank 0 writes the results and, when the
+//     pool is sharded over GPUs, posts the rank's record to the other ranks while every CTA polls the
+//     rank's mailbox.
+// ---------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+constexpr int CLUSTER_MAX = 8;                  // portable cluster size
+constexpr int XSLOT_WORDS = 4;
+
+__device__ __forceinline__ unsigned long long ld_volatile_shared(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// Warp-level exchange of the CTAs' local maxima through distributed shared memory.  xslot: this CTA's
+// [2][CLUSTER_MAX][XSLOT_WORDS] slots; remote[r]: the same array in CTA r's shared memory.
+__device__ __forceinline__ Best cluster_exchange(unsigned long long *xslot, unsigned long long *const *remote, int crank,
+                                                 int csize, unsigned tag, Best local) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int peer = lane / 3, word = lane - 3 * peer;
+    const size_t parity_off = (size_t)(tag & 1u) * CLUSTER_MAX * XSLOT_WORDS;
+    const bool active = lane < 3 * csize;
+    if (active) {
+        const unsigned long long payload = word == 0 ? (local.v >> 32) : word == 1 ? (local.v & 0xffffffffull)
+                                                                                  : (unsigned long long)(unsigned)local.i;
+        remote[peer][parity_off + (size_t)crank * XSLOT_WORDS + word] = (payload << 32) | tag;   // st.shared::cluster
+    }
+    unsigned long long got = 0;
+    if (active) {
+        const unsigned long long *p = xslot + parity_off + (size_t)peer * XSLOT_WORDS + word;
+        while (true) {
+            got = ld_volatile_shared(p);
+            if ((unsigned)got == tag) break;
+        }
+    }
+    const int src = lane < csize ? 3 * lane : 0;
+    const unsigned long long hi = __shfl_sync(full, got, src) >> 32;
+    const unsigned long long lo = __shfl_sync(full, got, src + 1) >> 32;
+    const unsigned idx = (unsigned)(__shfl_sync(full, got, src + 2) >> 32);
+    Best x{0ull, 0x7fffffff};
+    if (lane < csize) {
+        x.v = (hi << 32) | lo;
+        x.i = (int)idx;
+    }
+    return warp_best(x);
+}
+
+template <int NT, bool SHARDED>
+__global__ void __launch_bounds__(NT, 1) greedy_cluster_kernel(const GreedyArgs a, const CommView comm) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank(), csize = a.csize;
+    const int c_lo = min(a.lo + crank * a.cta_cols, a.hi), c_hi = min(c_lo + a.cta_cols, a.hi);
+    const int c_len = c_hi - c_lo;
+    extern __shared__ unsigned long long greedy_smem[];
+    unsigned long long *fps_s = greedy_smem;                                       // [cta_cols]
+    double *tl = reinterpret_cast<double *>(fps_s + a.cta_cols);                   // [tl_n]
+    unsigned long long *xslot = reinterpret_cast<unsigned long long *>(tl + a.tl_n);   // [2][CLUSTER_MAX][XSLOT_WORDS]
+    unsigned *selbits = reinterpret_cast<unsigned *>(xslot + 2 * CLUSTER_MAX * XSLOT_WORDS);   // [sel_words]
+    __shared__ GreedyShared sh;
+    __shared__ Best wres[NT / 32];
+    __shared__ unsigned long long *remote[CLUSTER_MAX];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NWARPS = NT / 32;
+    const int tl_n = a.tl_n;
+    ExchangeLane xlane;
+    if (SHARDED) xlane = make_exchange_lane(comm);
+
+    const unsigned long long far_bits = a.far_bits;
+    for (int i = threadIdx.x; i < a.cta_cols; i += NT) fps_s[i] = far_bits;
+    for (int d = threadIdx.x; d < tl_n; d += NT) tl[d] = a.tlut[d];
+    for (int wd = threadIdx.x; wd < a.sel_words; wd += NT) selbits[wd] = 0u;
+    for (int i = threadIdx.x; i < 2 * CLUSTER_MAX * XSLOT_WORDS; i += NT) xslot[i] = 0ull;
+    if (threadIdx.x < CLUSTER_MAX)
+        remote[threadIdx.x] = threadIdx.x < csize ? cluster.map_shared_rank(xslot, threadIdx.x) : nullptr;
+    __syncthreads();
+    bool local_abort = false;
+    if (threadIdx.x == 0) {
+        sh.stop = 0;
+        sh.m = 0;
+        sh.cur = -1;
+        sh.cost = a.cost_start;
+        const unsigned long long needed = a.list_cursor ? *a.list_cursor : 0ull;
+        if (crank == 0) a.result[5] = (double)needed;
+        if ((long long)needed > a.list_capacity) {   // neighbour-list pool too small: the host grows it and reruns
+            local_abort = true;
+            if (crank == 0) {
+                a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                a.result[4] = -1.0;
+            }
+            sh.stop = SHARDED ? 3 : 1;
+        } else if (a.n_sampled == 0) {
+            const int first = a.first_index;
+            if (crank == 0) a.out[0] = first;
+            sh.m = 1;
+            set_selected(a, selbits, first);
+            sh.cost = __dadd_rn(sh.cost, a.cost_f);
+            fetch_frame(a, sh, first);
+            sh.cost = __dadd_rn(sh.cost, sh.rec.box_cost);
+        }
+    }
+    cluster.sync();   // every CTA's slots are zeroed and mapped before anyone posts
+    if (!SHARDED && sh.stop) {
+        cluster.sync();
+        return;
+    }
+    if (a.forbid_sampled)
+        for (int t = threadIdx.x; t < a.n_sampled; t += NT) set_selected(a, selbits, a.sampled[t]);
+
+    // one row update on this CTA's slice: list entries, barrier, group members
+    auto apply = [&]() {
+        const int src = sh.cur;
+        const long long off = sh.rec.list_off;
+        const int len = a.spatial == ADSEL_SPATIAL_GEODESIC ? sh.rec.list_len : 0;
+        for (int t = threadIdx.x; t < len; t += NT) {
+            const int j = a.list_idx[off + t];
+            const unsigned long long v = (unsigned long long)__double_as_longlong(a.list_val[off + t]);   // same round trip
+            if (j >= c_lo && j < c_hi && v < fps_s[j - c_lo]) fps_s[j - c_lo] = v;
+        }
+        __syncthreads();
+        int g0 = 0, g1 = 0;
+        if (a.temporal || a.spatial == ADSEL_SPATIAL_EUCLID) {
+            g0 = sh.rec.e0;
+            g1 = sh.rec.e1;
+        }
+        if (a.groups_contiguous) {
+            g0 = max(g0, c_lo);
+            g1 = min(g1, c_hi);
+            for (int j = g0 + threadIdx.x; j < g1; j += NT) {
+                const unsigned long long v = (unsigned long long)__double_as_longlong(group_value(a, sh, tl, tl_n, src, j));
+                if (v < fps_s[j - c_lo]) fps_s[j - c_lo] = v;
+            }
+        } else {
+            for (int t = g0 + threadIdx.x; t < g1; t += NT) {
+                const int j = a.group_members[t];
+                if (j >= c_lo && j < c_hi) {
+                    const unsigned long long v = (unsigned long long)__double_as_longlong(group_value(a, sh, tl, tl_n, src, j));
+                    if (v < fps_s[j - c_lo]) fps_s[j - c_lo] = v;
+                }
+            }
+        }
+    };
+
+    if (sh.stop == 0) {
+        for (int t = 0; t < a.n_sampled; ++t) {   // fps = min over the rows of the frames already in the buffer (:160-164)
+            __syncthreads();
+            if (threadIdx.x == 0) fetch_frame(a, sh, a.sampled[t]);
+            __syncthreads();
+            apply();
+        }
+    }
+    long long steps = 0;
+    bool seeding = a.n_sampled > 0;
+    while (true) {
+        if (!seeding && sh.stop == 0) apply();
+        __syncthreads();
+        // arg-max of this CTA's slice, first index among equal maxima
+        Best acc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = Best{0ull, 0x7fffffff};
+        for (int i0 = threadIdx.x; i0 < c_len; i0 += 4 * NT) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + q * NT;
+                if (i < c_len) {
+                    const unsigned long long v = fps_s[i];
+                    if (v > acc[q].v || acc[q].i == 0x7fffffff) {   // ascending i per accumulator: strict '>' keeps the first
+                        acc[q].v = v;
+                        acc[q].i = c_lo + i;
+                    }
+                }
+            }
+        }
+        Best x = better(better(acc[0], acc[1]), better(acc[2], acc[3]));
+        x = warp_best(x);
+        if (lane == 0) wres[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            Best y = lane < NWARPS ? wres[lane] : Best{0ull, 0x7fffffff};
+            y = warp_best(y);
+            if (y.i != 0x7fffffff && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rec + y.i));
+            const unsigned tag = 1u + (unsigned)steps;
+            if (csize > 1) y = cluster_exchange(xslot, remote, crank, csize, tag, y);
+            int comm_status = 0;
+            if (SHARDED) {
+                const bool abort_now = __shfl_sync(0xffffffffu, local_abort ? 1 : 0, 0) != 0;
+                const ExchangeResult r = exchange_best(comm, xlane, comm.seq_base + tag, y.v,
+                                                       abort_now ? COMM_ABORT_INDEX : (unsigned)y.i, crank == 0);
+                y.v = r.key;
+                y.i = r.index;
+                comm_status = r.status;
+            }
+            if (lane == 0) {
+                const int nxt = y.i;
+                if (comm_status != 0) {
+                    if (crank == 0 && a.result[1] == 0.0)
+                        a.result[1] = (double)(comm_status == 2 ? ADSEL_ERR_COMM : ADSEL_ERR_PEER_ABORT);
+                    sh.stop = 2;
+                } else if (nxt < 0 || nxt >= a.n) {
+                    if (crank == 0) a.result[1] = (double)ADSEL_ERR_INVALID;
+                    sh.stop = 2;
+                } else {
+                    const FrameRec rec = a.rec[nxt];
+                    const bool was_selected = get_selected(a, selbits, nxt);
+                    const double2 me = a.spatial == ADSEL_SPATIAL_EUCLID ? a.loc[nxt] : make_double2(0.0, 0.0);
+                    if (seeding) {
+                        if (crank == 0) a.out[0] = nxt;
+                        sh.m = 1;
+                        set_selected(a, selbits, nxt);
+                        sh.cost = __dadd_rn(sh.cost, a.cost_f);
+                        sh.cost = __dadd_rn(sh.cost, rec.box_cost);
+                        sh.rec = rec;
+                        sh.me = me;
+                        sh.cur = nxt;
+                    } else if (was_selected) {   // :182 assert
+                        if (crank == 0) {
+                            a.result[1] = (double)ADSEL_ERR_RESELECTED;
+                            a.result[4] = (double)nxt;
+                        }
+                        sh.stop = 1;
+                    } else {
+                        sh.cost = __dadd_rn(sh.cost, a.cost_f);          // :184
+                        sh.cost = __dadd_rn(sh.cost, rec.box_cost);      // :185
+                        if (sh.cost > a.budget) {                        // :186
+                            sh.stop = 1;
+                        } else if (sh.m >= a.out_cap) {
+                            if (crank == 0) {
+                                a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                                a.result[4] = -2.0;
+                            }
+                            sh.stop = 1;
+                        } else {
+                            if (crank == 0) a.out[sh.m] = nxt;
+                            sh.m += 1;
+                            set_selected(a, selbits, nxt);
+                            sh.rec = rec;
+                            sh.me = me;
+                            sh.cur = nxt;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        ++steps;
+        if (sh.stop == 2) break;
+        if (seeding) {
+            seeding = false;
+            continue;
+        }
+        if (sh.stop) break;
+    }
+    for (int i = threadIdx.x; i < c_len; i += NT) a.fps[c_lo + i] = fps_s[i];   // adsel_get_fps
+    if (threadIdx.x == 0 && crank == 0) {
+        a.result[0] = sh.cost;
+        a.result[2] = (double)sh.m;
+        a.result[3] = (double)steps;
+    }
+    cluster.sync();   // no CTA leaves while a peer may still store into its slots
+}
+
 __global__ void temporal_lut_kernel(double *tlut, int n, int norm_mode, double divisor) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d < n) tlut[d] = normalize_value((double)d, norm_mode, divisor);
@@ -488,6 +765,57 @@ static int greedy_threads() {
     return (t == 256 || t == 512 || t == 1024) ? t : 512;
 }
 
+// Cluster size for the shared-memory-resident variant, 0 when it is not used.
+// MEASURED SLOWER than the single-CTA kernel on B200 (P28K, budget 4800: 16.2 / 15.3 / 13.6 ms with 2 / 4 / 8 CTAs
+// against 10.4 ms): what the shared-memory fps saves (the RED -> ld.cg round trip) is spent again on the scan of the
+// whole slice, the two-level arg-max, the DSMEM exchange (~215 cycles one way) and the frame-record fetch that now
+// misses L1 in every CTA but the winner's.  It is therefore OFF unless ADSEL_GREEDY_CLUSTER=1/2/4/8 asks for it
+// (negative or unset: off); it passes the same parity tests and is kept as the measured alternative of DESIGN.md §5.
+static int pick_cluster(const GreedyArgs &a, int nt, size_t *smem_out, int *cta_cols_out, int *sel_words_out) {
+    const char *e = getenv("ADSEL_GREEDY_CLUSTER");
+    const int forced = e ? atoi(e) : 0;
+    if (forced <= 0) return 0;
+    const long long cols = a.hi - a.lo;
+    const size_t budget = 220 * 1024;   // of the 227 KB opt-in maximum: room for the static shared variables
+    for (int c = 1; c <= CLUSTER_MAX; c *= 2) {
+        if (forced > 0 && c != forced) continue;
+        long long per = (cols + c - 1) / c;
+        per = (per + 255) / 256 * 256;
+        if (per < 256) per = 256;
+        const size_t base = (size_t)per * 8 + (size_t)a.tl_n * 8 + 2 * CLUSTER_MAX * XSLOT_WORDS * 8 + 64;
+        if (base > budget) continue;
+        // the selected-frame bitmap goes to shared memory when it still fits, else global bytes are used
+        const size_t bitmap = (size_t)((a.n + 31) / 32) * 4;
+        const int sel_words = (a.n <= 524288 && base + bitmap <= budget) ? (a.n + 31) / 32 : 0;
+        // default: the smallest cluster that fits, but no more than 16 slice entries per thread
+        if (forced <= 0 && c < CLUSTER_MAX && per > 16LL * nt && ((cols + 2 * c - 1) / (2 * c)) >= 256) continue;
+        *smem_out = base + (size_t)sel_words * 4;
+        *cta_cols_out = (int)per;
+        *sel_words_out = sel_words;
+        return c;
+    }
+    return 0;
+}
+
+template <int NT, bool SHARDED>
+static cudaError_t launch_cluster_nt(adsel_handle *h, const GreedyArgs &a, const CommView &view, size_t smem) {
+    cudaFuncSetAttribute(greedy_cluster_kernel<NT, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)a.csize, 1, 1);
+    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)a.csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, greedy_cluster_kernel<NT, SHARDED>, a, view);
+}
+
 template <bool SHARDED>
 static void launch_greedy(adsel_handle *h, const GreedyArgs &a, const CommView &view, size_t smem) {
     if (a.prof) {   // ADSEL_GREEDY_PROFILE=1: per-phase cycle counters (development aid)
@@ -520,6 +848,12 @@ int greedy_preload() {
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<256, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<512, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<1024, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<256, true>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<512, true>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<1024, true>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<256, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<512, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<1024, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, temporal_lut_kernel));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, fill_u64_kernel2));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, frame_rec_kernel));
@@ -653,13 +987,29 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     a.sel_words = n <= 524288 ? (n + 31) / 32 : 0;
-    const size_t smem = (size_t)nblk * 20 + (size_t)a.tl_n * 8 + (size_t)a.sel_words * 4 + 16;
+    a.far_bits = far_bits;
     CommView view;
-    if (sharded) {
-        ADSEL_TRY(comm_view(h, &view));
-        launch_greedy<true>(h, a, view, smem);
+    if (sharded) ADSEL_TRY(comm_view(h, &view));
+    size_t csmem = 0;
+    int cta_cols = 0, csel = 0;
+    const int nt = greedy_threads();
+    const int csize = a.prof ? 0 : pick_cluster(a, nt, &csmem, &cta_cols, &csel);
+    if (csize > 0) {   // shared-memory-resident fps, one CTA per slice piece, exchange over distributed shared memory
+        a.csize = csize;
+        a.cta_cols = cta_cols;
+        a.sel_words = csel;
+        cudaError_t e;
+        if (sharded) e = nt == 256 ? launch_cluster_nt<256, true>(h, a, view, csmem) : nt == 1024 ? launch_cluster_nt<1024, true>(h, a, view, csmem)
+                                                                                                  : launch_cluster_nt<512, true>(h, a, view, csmem);
+        else e = nt == 256 ? launch_cluster_nt<256, false>(h, a, view, csmem) : nt == 1024 ? launch_cluster_nt<1024, false>(h, a, view, csmem)
+                                                                                           : launch_cluster_nt<512, false>(h, a, view, csmem);
+        ADSEL_CUDA(e);
+        h->greedy_cluster = csize;
     } else {
-        launch_greedy<false>(h, a, view, smem);
+        const size_t smem = (size_t)nblk * 20 + (size_t)a.tl_n * 8 + (size_t)a.sel_words * 4 + 16;
+        if (sharded) launch_greedy<true>(h, a, view, smem);
+        else launch_greedy<false>(h, a, view, smem);
+        h->greedy_cluster = 0;
     }
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());

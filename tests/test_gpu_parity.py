@@ -228,3 +228,23 @@ def test_grid_knn_equals_bruteforce_on_tie_heavy_and_degenerate_inputs(handle, m
         assert np.array_equal(tables["brute"][1], tables["grid"][1]), name
         assert np.array_equal(tables["brute"][0].view(np.uint64), tables["grid"][0].view(np.uint64)), name
     monkeypatch.delenv("ADSEL_KNN")
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "8"])
+def test_cluster_variant_of_the_greedy_loop_selects_identically(handle, pools, monkeypatch, cluster):
+    """ADSEL_GREEDY_CLUSTER: fps in shared memory, split over a thread-block cluster, exchange through DSMEM
+    (the measured alternative of DESIGN.md §5; off by default)."""
+    infos = pools("P8K")["infos"]
+    loc, run_id, max_td = _set_spatial_pool(handle, infos)
+    handle.build_knn_graph(8)
+    kw = dict(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0, budget=600, first_index=4242)
+    want, want_cost = handle.select(**kw)
+    want_fps = handle.get_fps()
+    monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", cluster)
+    got, cost = handle.select(**kw)
+    assert got == want and cost == want_cost
+    assert np.array_equal(handle.get_fps().view(np.uint64), want_fps.view(np.uint64))
+    got2, _ = handle.select(**{**kw, "budget": 900, "sampled": got, "first_index": -1, "cost_start": cost})
+    monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
+    want2, _ = handle.select(**{**kw, "budget": 900, "sampled": want, "first_index": -1, "cost_start": want_cost})
+    assert got2 == want2
