@@ -142,3 +142,13 @@ def test_cli_first_invocation_writes_indented_empty_buffer(pools, tmp_path):
     assert cli.main(["--config", str(cfg), "--budget", "100"]) == 0
     assert open(buf).read() == json.dumps({"0": []}, indent=4)      # tools/active_select.py:68-71
     assert cli.load_selector_cfg(str(cfg))["type"] == "SpatialTemporalSelector"
+
+
+def test_logfile_names_fast_path_is_the_reference_expression():
+    """pool.logfile_names skips re-parsing when a path continues the previous ``<dir>/<logfile>__`` prefix; the
+    result must be exactly ``path.split("/")[-1].split("__")[0]`` (spatial_temporal_selector.py:79) for any path."""
+    from adsel_b200 import pool
+    paths = ["a/L1__x.jpg", "a/L1__y/z.jpg", "a/L1__y__z.jpg", "b/L1__x.jpg", "L2__q", "L2__r", "noseparator",
+             "a/L1__x.jpg", "a/L1x__1", "a/L1__", "a/L1__/w__e", "", "/", "__", "a/__b", "a/__c"]
+    infos = [{"cam_front_path": p} for p in paths]
+    assert pool.logfile_names(infos) == [p.split("/")[-1].split("__")[0] for p in paths]
