@@ -325,8 +325,14 @@ int comm_barrier(adsel_handle *h);
 // gathered descriptors (a next build) while a peer still reads its copy.
 int pairdist_build_sharded(adsel_handle *h) {
     ADSEL_REQUIRE(h->comm_ready, "adsel_pairdist_build_sharded: call adsel_comm_init / adsel_comm_attach first");
-    ADSEL_REQUIRE(h->bev_frames == h->arena_n && h->bev_cells == h->arena_dim && h->desc_levels,
+    ADSEL_REQUIRE(h->arena_dim > 0, "adsel_pairdist_build_sharded: the arena has no descriptor region (adsel_comm_init dim = 0)");
+    // the arena defines the descriptor matrix; a rank whose slice is empty has built nothing itself
+    ADSEL_REQUIRE(h->bev_frames == 0 || h->desc_levels == nullptr || h->desc_levels == arena_levels(h, h->rank),
                   "adsel_pairdist_build_sharded: descriptors were not built into the arena (arena sized for another pool?)");
+    h->bev_frames = h->arena_n;
+    h->bev_cells = h->arena_dim;
+    h->desc_levels = arena_levels(h, h->rank);
+    h->desc_norm2 = arena_norm2(h, h->rank);
     int lo = 0, hi = h->bev_frames;
     if (h->world > 1) {
         long long per = ((long long)h->bev_frames + h->world - 1) / h->world;

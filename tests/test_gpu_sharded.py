@@ -215,6 +215,31 @@ def test_sharded_distance_columns_and_dense_selection(world, n, dim):
         w.close()
 
 
+def test_sharded_dense_path_with_empty_slices():
+    """Fewer than 256 frames: every rank but the first owns an empty slice and builds no descriptor itself."""
+    n = 40
+    sizes = 3000 + (np.arange(n) * 131) % 301
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    single = native.Handle(0)
+    single.bev_generate(off, n_sweeps=3, seed=3)
+    single.bev_build()
+    single.pairdist_build()
+    n_boxes = (np.arange(n) % 7).astype(np.int32)
+    want, _ = single.select_dense(n_boxes, budget=5, first_index=3)
+    single.close()
+
+    def load_batch(h, lo, hi):
+        h.bev_generate(np.concatenate([[0], np.cumsum(sizes[lo:hi])]).astype(np.int64), n_sweeps=3, seed=3, first_frame=lo)
+
+    w = sharded.LocalWorld(3, timeout=10.0)
+    try:
+        w.dense_build(n, 16, load_batch)
+        got, _ = w.dense_select(n_boxes, budget=5, first_index=3)
+        assert got == want
+    finally:
+        w.close()
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_bev_pipeline_descriptors_gathered_by_the_histogram_kernel(world):
     """points -> histogram on the owner rank -> descriptors stored into every rank's arena -> column-sharded
