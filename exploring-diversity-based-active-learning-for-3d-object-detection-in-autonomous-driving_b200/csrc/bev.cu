@@ -16,6 +16,7 @@
 // are binned into a shared-memory-privatised int32 histogram with warp-aggregated atomics, and the
 // histogram is written once.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -77,7 +78,7 @@ template <bool AGGREGATE>
 __global__ void __launch_bounds__(BEV_THREADS, 2)
 bev_histogram_kernel(const float *__restrict__ pts, const int64_t *__restrict__ frame_off, int n_frames, BevGrid g,
                      int32_t *__restrict__ counts, const BevOut out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int cells = g.nx * g.ny;
     int *hist = reinterpret_cast<int *>(smem_raw);
     float4 *stage = reinterpret_cast<float4 *>(smem_raw + (size_t)((cells + 3) & ~3) * sizeof(int)) +
@@ -128,6 +129,180 @@ bev_histogram_kernel(const float *__restrict__ pts, const int64_t *__restrict__ 
         for (int c = threadIdx.x; c < cells; c += BEV_THREADS) {
             const int cnt = hist[c];
             const int level = min(31, 32 - __clz(cnt));     // bit length: 0,1,2,2,3,3,3,3,4,...
+            counts[(size_t)f * cells + c] = cnt;
+            const __nv_bfloat16 lv = __int2bfloat16_rn(level);
+            for (int w = 0; w < out.world; ++w) out.levels[w][(size_t)f * cells + c] = lv;
+            local += level * level;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if (lane == 0) atomicAdd(&s_norm, local);
+        __syncthreads();
+        if (threadIdx.x < out.world) out.norm2[threadIdx.x][f] = s_norm;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA variant: every warp owns a ring of BEV_STAGES 2,560-byte buffers in shared memory and keeps them
+// filled with bulk asynchronous copies (cp.async.bulk global -> shared, completion on an mbarrier): no
+// registers and no staging stores on the load path, and BEV_STAGES chunks in flight per warp whatever the
+// warp is doing -- including across frame boundaries, because a warp's chunk stream is enumerated over
+// (frame, chunk) pairs independently of the CTA's per-frame barriers.  One CTA per SM: the 64 KB histogram
+// plus 16 rings leave no room for a second one.
+//
+// Binning uses a reciprocal multiply with an exact fallback: c' = floor((p - lo) * (1/voxel)) can differ
+// from the reference's floor((p - lo) / voxel) only when the quotient is within a few ulp of an integer;
+// those (rare) points are re-evaluated with the IEEE division, so the counts stay bit-exact.
+// ---------------------------------------------------------------------------------------------
+constexpr int CHUNK_BYTES = CHUNK_POINTS * 20;   // 2,560
+
+struct BevGridR {
+    float lo[3], vs[3], inv[3];
+    int nx, ny, nz;
+};
+
+__device__ __forceinline__ bool coord_fast(float p, float lo, float vs, float inv, int n, int &c) {
+    const float t = __fsub_rn(p, lo);
+    float q = __fmul_rn(t, inv);
+    const float fl = floorf(q);
+    const float frac = q - fl;
+    // within 8 ulp of an integer (or not finite): decide with the reference's division
+    const float band = 9.5367431640625e-07f * fmaxf(1.0f, fabsf(q));
+    if (!(frac > band && frac < 1.0f - band)) {
+        q = __fdiv_rn(t, vs);
+        const float fe = floorf(q);
+        const bool ok = (fe >= 0.0f) && (fe < (float)n);
+        c = ok ? (int)fe : -1;
+        return ok;
+    }
+    const bool ok = (fl >= 0.0f) && (fl < (float)n);
+    c = ok ? (int)fl : -1;
+    return ok;
+}
+
+__device__ __forceinline__ int bev_cell_fast(const BevGridR &g, float x, float y, float z) {
+    int cx, cy, cz;
+    const bool okx = coord_fast(x, g.lo[0], g.vs[0], g.inv[0], g.nx, cx);
+    const bool oky = coord_fast(y, g.lo[1], g.vs[1], g.inv[1], g.ny, cy);
+    const bool okz = coord_fast(z, g.lo[2], g.vs[2], g.inv[2], g.nz, cz);
+    return (okx && oky && okz) ? cy * g.nx + cx : -1;
+}
+
+__device__ __forceinline__ uint32_t bev_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Enumerates the chunks of one warp over the frames of this CTA: (frame, chunk index) -> byte address.
+struct ChunkCursor {
+    int f;            // frame
+    int64_t c;        // chunk of this warp inside the frame
+    int64_t body0, n_chunks;
+};
+__device__ __forceinline__ void cursor_load_frame(ChunkCursor &k, const int64_t *__restrict__ frame_off, int n_frames) {
+    if (k.f < n_frames) {
+        const int64_t p0 = frame_off[k.f], p1 = frame_off[k.f + 1];
+        k.body0 = min(p1, (p0 + 3) & ~(int64_t)3);
+        k.n_chunks = (p1 - k.body0) / CHUNK_POINTS;
+    } else {
+        k.body0 = 0;
+        k.n_chunks = 0;
+    }
+}
+// advance to the next existing chunk (possibly in a later frame); returns false at the end of the stream
+__device__ __forceinline__ bool cursor_settle(ChunkCursor &k, const int64_t *__restrict__ frame_off, int n_frames, int wid,
+                                              int frame_stride) {
+    while (k.f < n_frames && k.c >= k.n_chunks) {
+        k.f += frame_stride;
+        k.c = wid;
+        cursor_load_frame(k, frame_off, n_frames);
+    }
+    return k.f < n_frames;
+}
+
+template <bool AGGREGATE, int NW, int NS>
+__global__ void __launch_bounds__(NW * 32, 1)
+bev_histogram_tma_kernel(const float *__restrict__ pts, const int64_t *__restrict__ frame_off, int n_frames, BevGridR g,
+                         int32_t *__restrict__ counts, const BevOut out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cells = g.nx * g.ny;
+    int *hist = reinterpret_cast<int *>(smem_raw);
+    unsigned char *ring_base = smem_raw + (((size_t)cells * sizeof(int) + 127) & ~(size_t)127);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char *ring = ring_base + (size_t)wid * NS * CHUNK_BYTES;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(ring_base + (size_t)NW * NS * CHUNK_BYTES) + wid * NS;
+    __shared__ int s_norm;
+
+    if (lane == 0) {
+        for (int s = 0; s < NS; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bev_smem_u32(&mbar[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned char *pts_b = reinterpret_cast<const unsigned char *>(pts);
+    ChunkCursor prod;
+    prod.f = blockIdx.x;
+    prod.c = wid;
+    cursor_load_frame(prod, frame_off, n_frames);
+    auto issue = [&](int stage) {   // whole warp calls; lane 0 issues
+        if (!cursor_settle(prod, frame_off, n_frames, wid, gridDim.x)) return;
+        if (lane == 0) {
+            const unsigned char *src = pts_b + (prod.body0 + prod.c * CHUNK_POINTS) * 20;
+            const uint32_t bar = bev_smem_u32(&mbar[stage]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(CHUNK_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(bev_smem_u32(ring + (size_t)stage * CHUNK_BYTES)), "l"(src), "r"(CHUNK_BYTES), "r"(bar) : "memory");
+        }
+        prod.c += NW;
+    };
+    for (int s = 0; s < NS; ++s) issue(s);
+    int stage = 0;
+    uint32_t phase = 0;
+
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        for (int c = threadIdx.x; c < cells; c += (NW * 32)) hist[c] = 0;
+        if (threadIdx.x == 0) s_norm = 0;
+        __syncthreads();
+        const int64_t p0 = frame_off[f], p1 = frame_off[f + 1];
+        const int64_t body0 = min(p1, (p0 + 3) & ~(int64_t)3);
+        const int64_t n_chunks = (p1 - body0) / CHUNK_POINTS;
+        const int64_t body1 = body0 + n_chunks * CHUNK_POINTS;
+        for (int64_t c = wid; c < n_chunks; c += NW) {
+            const uint32_t bar = bev_smem_u32(&mbar[stage]);
+            uint32_t done;
+            do {
+                asm volatile(
+                    "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                    : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+            } while (!done);
+            const float *stage_f = reinterpret_cast<const float *>(ring + (size_t)stage * CHUNK_BYTES);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int p = lane + 32 * i;          // stride-5 float reads: 5 is odd -> conflict-free
+                hist_add<AGGREGATE>(hist, bev_cell_fast(g, stage_f[5 * p], stage_f[5 * p + 1], stage_f[5 * p + 2]));
+            }
+            __syncwarp();                              // every lane is done with the buffer before it is refilled
+            issue(stage);
+            if (++stage == NS) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+        // unaligned head (< 4 points) and tail (< 128 points): scalar loads, whole warps stay converged
+        const int64_t n_edge = (body0 - p0) + (p1 - body1);
+        for (int64_t e0 = 0; e0 < n_edge; e0 += (NW * 32)) {
+            const int64_t e = e0 + threadIdx.x;
+            int cell = -1;
+            if (e < n_edge) {
+                const int64_t p = e < (body0 - p0) ? p0 + e : body1 + (e - (body0 - p0));
+                cell = bev_cell_fast(g, pts[5 * p], pts[5 * p + 1], pts[5 * p + 2]);
+            }
+            hist_add<AGGREGATE>(hist, cell);
+        }
+        __syncthreads();
+        int local = 0;
+        for (int c = threadIdx.x; c < cells; c += (NW * 32)) {
+            const int cnt = hist[c];
+            const int level = min(31, 32 - __clz(cnt));
             counts[(size_t)f * cells + c] = cnt;
             const __nv_bfloat16 lv = __int2bfloat16_rn(level);
             for (int w = 0; w < out.world; ++w) out.levels[w][(size_t)f * cells + c] = lv;
@@ -277,12 +452,47 @@ int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics,
         h->desc_levels = h->bev_levels.p;
         h->desc_norm2 = h->bev_norm2.p;
     }
-    const size_t smem = (size_t)((cells + 3) & ~3) * sizeof(int) + (size_t)BEV_WARPS * CHUNK_VEC4 * sizeof(float4);
-    auto kern = aggregate_atomics ? bev_histogram_kernel<true> : bev_histogram_kernel<false>;
-    ADSEL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = min(h->bev_batch, 2 * h->num_sms);
+    const char *mode = getenv("ADSEL_BEV");   // "ldg": register-staged loads; "tma" / "tma16x3" / "tma24x2" / "tma32x2": bulk-copy rings
+    // measured on B200, 2,048 frames x ~300k points: ldg 4.75 TB/s, tma16x3 4.96, tma24x2 6.36, tma32x2 6.66 TB/s -- the
+    // default is the largest ring configuration whose shared memory fits next to the histogram
+    const int configs[3][2] = {{32, 2}, {24, 2}, {16, 3}};
+    int tw = 0, ts = 0;
+    size_t smem_tma = 0;
+    for (int c = 0; c < 3 && tw == 0; ++c) {
+        const int w = configs[c][0], st = configs[c][1];
+        char name[16];
+        snprintf(name, sizeof(name), "tma%dx%d", w, st);
+        if (mode && !strncmp(mode, "tma", 3) && strlen(mode) > 3 && strcmp(mode, name)) continue;   // a specific one was asked for
+        const size_t need = (((size_t)cells * sizeof(int) + 127) & ~(size_t)127) + (size_t)w * st * CHUNK_BYTES +
+                            (size_t)w * st * sizeof(uint64_t);
+        if (need <= 225 * 1024) tw = w, ts = st, smem_tma = need;
+    }
+    const bool use_tma = !(mode && !strcmp(mode, "ldg")) && tw > 0;
     ADSEL_TRY(begin_stage(h));
-    kern<<<grid, BEV_THREADS, smem, h->stream>>>(h->bev_pts.p, h->bev_off.p, h->bev_batch, g, h->bev_counts.p + o, out);
+    if (use_tma) {
+        BevGridR gr;
+        for (int a = 0; a < 3; ++a) {
+            gr.lo[a] = g.lo[a];
+            gr.vs[a] = g.vs[a];
+            gr.inv[a] = 1.0f / g.vs[a];
+        }
+        gr.nx = g.nx;
+        gr.ny = g.ny;
+        gr.nz = g.nz;
+        void (*kern)(const float *, const int64_t *, int, BevGridR, int32_t *, const BevOut);
+        if (tw == 32) kern = aggregate_atomics ? bev_histogram_tma_kernel<true, 32, 2> : bev_histogram_tma_kernel<false, 32, 2>;
+        else if (tw == 24) kern = aggregate_atomics ? bev_histogram_tma_kernel<true, 24, 2> : bev_histogram_tma_kernel<false, 24, 2>;
+        else kern = aggregate_atomics ? bev_histogram_tma_kernel<true, 16, 3> : bev_histogram_tma_kernel<false, 16, 3>;
+        ADSEL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+        const int grid = min(h->bev_batch, h->num_sms);
+        kern<<<grid, tw * 32, smem_tma, h->stream>>>(h->bev_pts.p, h->bev_off.p, h->bev_batch, gr, h->bev_counts.p + o, out);
+    } else {
+        const size_t smem = (size_t)((cells + 3) & ~3) * sizeof(int) + (size_t)BEV_WARPS * CHUNK_VEC4 * sizeof(float4);
+        auto kern = aggregate_atomics ? bev_histogram_kernel<true> : bev_histogram_kernel<false>;
+        ADSEL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = min(h->bev_batch, 2 * h->num_sms);
+        kern<<<grid, BEV_THREADS, smem, h->stream>>>(h->bev_pts.p, h->bev_off.p, h->bev_batch, g, h->bev_counts.p + o, out);
+    }
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     ADSEL_TRY(end_stage(h, 5));
