@@ -108,7 +108,7 @@ int adsel_destroy(adsel_handle *h) {
     h->list_off.release(); h->list_len.release(); h->list_idx.release(); h->list_val.release(); h->cursor.release();
     h->fps.release(); h->frame_rec.release(); h->is_selected.release(); h->tlut.release();
     h->d_sampled.release(); h->d_out.release(); h->d_result.release();
-    h->pd_d2.release(); h->pd_norm.release(); h->pd_fps.release(); h->pd_boxes.release();
+    h->pd_d2.release(); h->pd_tiles.release(); h->pd_norm.release(); h->pd_fps.release(); h->pd_boxes.release();
     h->bev_pts.release(); h->bev_off.release(); h->bev_counts.release(); h->bev_norm2.release(); h->bev_levels.release();
     cudaEventDestroy(h->ev[0]);
     cudaEventDestroy(h->ev[1]);

@@ -466,6 +466,7 @@ int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics,
         const size_t need = (((size_t)cells * sizeof(int) + 127) & ~(size_t)127) + (size_t)w * st * CHUNK_BYTES +
                             (size_t)w * st * sizeof(uint64_t);
         if (need <= 225 * 1024) tw = w, ts = st, smem_tma = need;
+        (void)ts;
     }
     const bool use_tma = !(mode && !strcmp(mode, "ldg")) && tw > 0;
     ADSEL_TRY(begin_stage(h));

@@ -21,6 +21,7 @@
 // and columns of X through L2 (X itself is 0.92 GB at N=28,130, L2 is 126 MB).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "comm.cuh"
 #include "common.cuh"
@@ -113,7 +114,8 @@ __device__ __forceinline__ PdTile pd_tile(int t, int blocks_m, int blocks_n) {
 
 __global__ void __launch_bounds__(PD_THREADS, 1)
 pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ norm2,
-                        int32_t *__restrict__ out, int ld, int blocks_m, int blocks_n, int k_blocks, int col0) {
+                        int32_t *__restrict__ out, int ld, const int2 *__restrict__ tiles, int n_tiles, int k_blocks, int col0,
+                        int mirror_rows) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t *stage_mem = base;                                             // PD_STAGES x (A | B)
@@ -123,7 +125,6 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * PD_STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = blocks_m * blocks_n;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -152,7 +153,8 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const PdTile tl = pd_tile(t, blocks_m, blocks_n);
+                const int2 tt = tiles[t];
+                const PdTile tl{tt.x, tt.y};
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t *a = stage_mem + (size_t)stage * PD_STAGE_BYTES, *b = a + PD_A_BYTES;
@@ -210,7 +212,8 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const PdTile tl = pd_tile(t, blocks_m, blocks_n);
+            const int2 tt = tiles[t];
+            const PdTile tl{tt.x, tt.y};
             const int m0 = tl.m_blk * PD_BLOCK_M, n0 = tl.n_blk * PD_BLOCK_N;
             int *nn = norm_n + acc * PD_BLOCK_N;
             nn[et] = norm2[col0 + n0 + et];
@@ -233,6 +236,14 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
                     o.z = ni + nn[c * 32 + 4 * v + 2] - 2 * __float2int_rn(__uint_as_float(r[4 * v + 2]));
                     o.w = ni + nn[c * 32 + 4 * v + 3] - 2 * __float2int_rn(__uint_as_float(r[4 * v + 3]));
                     __stcs(reinterpret_cast<int4 *>(orow + c * 32) + v, o);
+                    if (mirror_rows) {   // d2 is symmetric: this tile also provides d2[j][i]; the 32 lanes hold 32 consecutive i
+                        const int j = n0 + c * 32 + 4 * v;
+                        int32_t *mcol = out + (size_t)j * ld + (m0 + row_in_tile);
+                        if (j + 0 < mirror_rows) __stcs(mcol, o.x);
+                        if (j + 1 < mirror_rows) __stcs(mcol + ld, o.y);
+                        if (j + 2 < mirror_rows) __stcs(mcol + 2 * (size_t)ld, o.z);
+                        if (j + 3 < mirror_rows) __stcs(mcol + 3 * (size_t)ld, o.w);
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -252,6 +263,32 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
 
 uint16_t *arena_levels(adsel_handle *h, int w);
 int32_t *arena_norm2(adsel_handle *h, int w);
+
+// Fills the tile list on the device (one thread per group of 16 row-blocks; the build stays enqueue-only).
+__global__ void __launch_bounds__(1024) pd_tile_list_kernel(int2 *__restrict__ tiles, int blocks_m, int blocks_n, int symmetric) {
+    __shared__ int start[1025];
+    const int groups = (blocks_m + PD_GROUP_M - 1) / PD_GROUP_M;
+    const int g = threadIdx.x;
+    int count = 0;
+    if (g < groups) {
+        const int first_m = g * PD_GROUP_M, gsz = min(PD_GROUP_M, blocks_m - first_m);
+        for (int mb = first_m; mb < first_m + gsz; ++mb) count += symmetric ? max(0, blocks_n - mb / 2) : blocks_n;
+    }
+    start[g + 1] = count;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        start[0] = 0;
+        for (int i = 0; i < groups; ++i) start[i + 1] += start[i];
+    }
+    __syncthreads();
+    if (g < groups) {
+        const int first_m = g * PD_GROUP_M, gsz = min(PD_GROUP_M, blocks_m - first_m);
+        int pos = start[g];
+        for (int nb = 0; nb < blocks_n; ++nb)
+            for (int mb = first_m; mb < first_m + gsz; ++mb)
+                if (!symmetric || nb >= mb / 2) tiles[pos++] = make_int2(mb, nb);
+    }
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -303,9 +340,20 @@ static int pairdist_enqueue(adsel_handle *h, int col0, int cols) {
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ADSEL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
     ADSEL_CUDA(cudaFuncSetAttribute(pairdist_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM));
-    const int grid = min(h->num_sms, blocks_m * blocks_n);
-    pairdist_tcgen05_kernel<<<grid, PD_THREADS, PD_SMEM, h->stream>>>(tmap, h->pd_norm.p, h->pd_d2.p, ld, blocks_m, blocks_n,
-                                                                      k_blocks, col0);
+    // Tile list in visiting order: groups of 16 row-blocks so that the ~148 concurrently resident tiles share rows and
+    // columns of X through L2.  A full (not column-sliced) matrix is symmetric: only the tiles that touch the upper
+    // triangle are computed (n_blk >= m_blk / 2 covers every j >= i) and each writes its mirror image as well.
+    const bool symmetric = col0 == 0 && cols == n && !getenv("ADSEL_PAIRDIST_FULL");
+    int n_tiles = 0;
+    for (int mb = 0; mb < blocks_m; ++mb) n_tiles += symmetric ? max(0, blocks_n - mb / 2) : blocks_n;
+    ADSEL_TRY(h->pd_tiles.reserve((size_t)blocks_m * blocks_n));
+    const int groups = (blocks_m + PD_GROUP_M - 1) / PD_GROUP_M;
+    ADSEL_REQUIRE(groups <= 1024, "adsel_pairdist_build: pool too large for the tile list kernel");
+    pd_tile_list_kernel<<<1, 1024, 0, h->stream>>>(h->pd_tiles.p, blocks_m, blocks_n, symmetric ? 1 : 0);   // no host data: enqueue only
+    h->launches += 1;
+    const int grid = min(h->num_sms, n_tiles);
+    pairdist_tcgen05_kernel<<<grid, PD_THREADS, PD_SMEM, h->stream>>>(tmap, h->pd_norm.p, h->pd_d2.p, ld, h->pd_tiles.p, n_tiles,
+                                                                      k_blocks, col0, symmetric ? rows : 0);
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     return ADSEL_OK;
@@ -725,6 +773,7 @@ int dense_preload() {
     cudaFuncAttributes attr;
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, pairdist_tcgen05_kernel));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, levels_norm_kernel));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, pd_tile_list_kernel));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, dense_greedy_kernel<8, true>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, dense_greedy_kernel<16, true>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, dense_greedy_kernel<32, true>));
