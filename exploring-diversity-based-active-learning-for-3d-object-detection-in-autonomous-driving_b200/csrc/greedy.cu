@@ -34,8 +34,11 @@
 
 namespace adsel {
 
-constexpr int BLK = 256;              // frames per block-max entry
-constexpr int MAX_BLKS = 9800;        // 20 B of shared memory per block + 32 KB LUT: n <= 2,508,800 frames
+#ifndef ADSEL_BLK
+#define ADSEL_BLK 128
+#endif
+constexpr int BLK = ADSEL_BLK;        // frames per block-max entry
+constexpr int MAX_BLKS = 9800;        // 20 B of shared memory per block + 32 KB LUT: n <= 1,254,400 frames
 
 struct GreedyArgs {
     int n, nblk, lo, hi, blk_lo, blk_hi, tl_n, sel_words;
@@ -362,7 +365,21 @@ __global__ void __launch_bounds__(NT, 1) greedy_select_kernel(const GreedyArgs a
             // arg-reduce over this rank's block maxima
             Best y{0ull, 0x7fffffff};
             PROF_MARK(8)   // calibration: cost of one mark
-            for (int b = a.blk_lo + lane; b < a.blk_hi; b += 32) y = better(y, Best{blk_val[b], blk_idx[b]});
+            // 8 block maxima per lane at a time: independent shared-memory loads, then a depth-3 tree
+            // (a serial compare/select chain over them would be exposed latency on this lone warp)
+            for (int b0 = a.blk_lo + lane; b0 < a.blk_hi; b0 += 8 * 32) {
+                Best e[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int b = b0 + 32 * q;
+                    e[q] = b < a.blk_hi ? Best{blk_val[b], blk_idx[b]} : Best{0ull, 0x7fffffff};
+                }
+#pragma unroll
+                for (int w = 1; w < 8; w <<= 1)
+#pragma unroll
+                    for (int q = 0; q + w < 8; q += 2 * w) e[q] = better(e[q], e[q + w]);
+                y = better(y, e[0]);
+            }
             PROF_MARK(9)
             y = warp_best(y);
             PROF_MARK(10)
@@ -873,7 +890,7 @@ static int validate_select(adsel_handle *h, const adsel_select_params *p, const 
     ADSEL_REQUIRE(n_sampled >= 0 && (n_sampled == 0 || sampled), "adsel_select: bad sampled list");
     ADSEL_REQUIRE(n_sampled > 0 || (first_index >= 0 && first_index < h->n), "adsel_select: first_index out of range");
     for (int i = 0; i < n_sampled; ++i) ADSEL_REQUIRE(sampled[i] >= 0 && sampled[i] < h->n, "adsel_select: sampled index out of range");
-    ADSEL_REQUIRE((h->n + BLK - 1) / BLK <= MAX_BLKS, "adsel_select: pool larger than 2,508,800 frames");
+    ADSEL_REQUIRE((h->n + BLK - 1) / BLK <= MAX_BLKS, "adsel_select: pool larger than 1,254,400 frames");
     if (p->normalize == ADSEL_NORM_LINEAR) {
         ADSEL_REQUIRE(p->spatial != ADSEL_SPATIAL_GEODESIC || p->max_spatial > 0.0, "adsel_select: linear needs max_spatial");
         ADSEL_REQUIRE(!p->temporal || p->max_temporal > 0.0, "adsel_select: linear needs max_temporal");

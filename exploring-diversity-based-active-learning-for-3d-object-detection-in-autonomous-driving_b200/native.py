@@ -108,7 +108,11 @@ def load():
     """Load (building in-tree if sources are newer) and type the library; raises if unavailable."""
     global _lib
     if _lib is None:
-        path = _build.build() if (_build.needs_build() and _nvcc_available()) else _build.LIB
+        override = os.environ.get("ADSEL_LIB")          # an alternative build of the same sources (experiments)
+        if override:
+            path = override
+        else:
+            path = _build.build() if (_build.needs_build() and _nvcc_available()) else _build.LIB
         if not os.path.exists(path):
             raise ImportError(
                 f"{path} is missing and nvcc is not available to build it: the selection hot path has "
