@@ -51,6 +51,7 @@ int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics,
 int pairdist_build(adsel_handle *h);
 int pairdist_set_descriptors(adsel_handle *h, const uint16_t *levels_host, int32_t n, int32_t dim);
 int pairdist_build_sharded(adsel_handle *h);
+int feature_distance_build(adsel_handle *h, const float *feats_host, int32_t n, int32_t dim, int32_t p);
 int dense_prepare(adsel_handle *h, int32_t n_sampled, int32_t out_cap);
 int dense_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
                                int32_t n_sampled, int32_t first_index, int32_t out_cap);
@@ -108,7 +109,7 @@ int adsel_destroy(adsel_handle *h) {
     h->list_off.release(); h->list_len.release(); h->list_idx.release(); h->list_val.release(); h->cursor.release();
     h->fps.release(); h->frame_rec.release(); h->is_selected.release(); h->tlut.release();
     h->d_sampled.release(); h->d_out.release(); h->d_result.release();
-    h->pd_d2.release(); h->pd_tiles.release(); h->pd_norm.release(); h->pd_fps.release(); h->pd_boxes.release();
+    h->pd_d2.release(); h->feat.release(); h->pd_tiles.release(); h->pd_norm.release(); h->pd_fps.release(); h->pd_boxes.release();
     h->bev_pts.release(); h->bev_off.release(); h->bev_counts.release(); h->bev_norm2.release(); h->bev_levels.release();
     cudaEventDestroy(h->ev[0]);
     cudaEventDestroy(h->ev[1]);
@@ -374,6 +375,12 @@ int adsel_select_dense(adsel_handle *h, const adsel_select_params *p, const int3
     ADSEL_REQUIRE(h, "adsel_select_dense: null handle");
     ADSEL_CUDA(cudaSetDevice(h->device));
     return dense_select(h, p, n_boxes, sampled, n_sampled, first_index, out_idx, out_cap, out_m, out_cost);
+}
+
+int adsel_feature_distance_build(adsel_handle *h, const float *feats, int32_t n, int32_t dim, int32_t p) {
+    ADSEL_REQUIRE(h, "adsel_feature_distance_build: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return feature_distance_build(h, feats, n, dim, p);
 }
 
 int adsel_pairdist_build_sharded(adsel_handle *h) {

@@ -151,6 +151,7 @@ struct adsel_handle {
     // pairwise squared distances of the descriptors (dense path)
     int32_t pd_n = 0, pd_ld = 0, pd_col0 = 0, pd_cols = 0;   // pool frames, row pitch, first / number of local columns
     adsel::DevBuf<int32_t> pd_d2, pd_norm, pd_fps, pd_boxes;
+    adsel::DevBuf<float> feat;                   // detector features [n, dim] (feature-distance map)
     adsel::DevBuf<int2> pd_tiles;                // (row block, column block) of every distance tile, in visiting order
 
     // greedy state

@@ -85,6 +85,7 @@ _SIGNATURES = {
                                                   ctypes.c_int32]),
     "adsel_select_sharded_end": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                                 ctypes.POINTER(ctypes.c_double)]),
+    "adsel_feature_distance_build": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "adsel_pairdist_build_sharded": (ctypes.c_int, [_P]),
     "adsel_select_dense_prepare": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32]),
     "adsel_select_dense_sharded_begin": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, _P, ctypes.c_int32,
@@ -383,6 +384,16 @@ class Handle:
     def pairdist_build(self):
         _check(load().adsel_pairdist_build(self._h))
         self.pd_cols = self.pd_n
+
+    def feature_distance_build(self, feats, p=2):
+        """float32 [n, dim] features -> the reference's N x N feature-distance map (feature_selector.py:87-109)."""
+        feats = np.ascontiguousarray(feats, dtype=np.float32)
+        assert feats.ndim == 2
+        self.pd_n = self.pd_cols = feats.shape[0]
+        _check(load().adsel_feature_distance_build(self._h, _ptr(feats), feats.shape[0], feats.shape[1], int(p)))
+
+    def feature_distance_rows(self, row0, rows):
+        return self.pairdist_get_rows(row0, rows).view(np.float32)
 
     def pairdist_build_sharded(self):
         _check(load().adsel_pairdist_build_sharded(self._h))

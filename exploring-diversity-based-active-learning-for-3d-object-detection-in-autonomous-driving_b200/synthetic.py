@@ -164,3 +164,14 @@ def write_lidar_files(infos, out_dir: str, n_points: int = 1500, nsweeps: int = 
             tm = np.eye(4)
             tm[:2, 3] = 0.3 * s, -0.2 * s
             info["sweeps"].append({"lidar_path": path, "transform_matrix": tm, "time_lag": 0.05 * s})
+
+
+def synthetic_features(n: int, dim: int = 512, seed: int = 11) -> np.ndarray:
+    """float32 [n, dim] stand-in for the mean-pooled FPN features the reference's feature selectors store with
+    ``torch.save`` (feature_selector.py:66-78): non-negative, post-ReLU-like, a few latent "scene types" plus
+    per-frame noise so that distances are structured rather than uniform."""
+    rng = np.random.default_rng(seed)
+    centres = np.abs(rng.normal(0.0, 1.0, size=(24, dim))).astype(np.float32)
+    mix = rng.dirichlet(np.full(24, 0.3), size=n).astype(np.float32)
+    feats = mix @ centres + np.abs(rng.normal(0.0, 0.05, size=(n, dim))).astype(np.float32)
+    return np.ascontiguousarray(feats, dtype=np.float32)

@@ -197,6 +197,14 @@ int adsel_select_dense(adsel_handle *h, const adsel_select_params *p, const int3
                        int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m,
                        double *out_cost);
 
+/* ---- feature-distance map of the detector-feature selectors (replaces the row loop of
+ *      det3d/selectors/feature_selector.py:87-109, same in spatial_feature / spatial_temporal_feature / badge /
+ *      uwe selectors).  feats: float32 [n, dim] host array (the reference's mean-pooled FPN features);
+ *      p = 1: sum |a-b|; p = 2: the reference's sqrt((a-b)**2).sum(1) (also an L1 distance).  The float32 map
+ *      replaces the descriptor distance matrix of the handle: adsel_pairdist_get_rows returns the float32 bit
+ *      patterns (non-negative floats order like their int32 bits) and adsel_select_dense runs the greedy loop. */
+int adsel_feature_distance_build(adsel_handle *h, const float *feats, int32_t n, int32_t dim, int32_t p);
+
 /* ---- the BEV / dense path sharded over ranks (after adsel_comm_init with dim = cells, n = pool frames) ----
  * adsel_bev_build then stores each frame's descriptor into EVERY rank's arena (the all-gather is fused into
  * the histogram kernel's epilogue); every rank builds the frames of its own slice [adsel_shard_range), at

@@ -73,9 +73,30 @@ def load_reference_selectors():
     from det3d.selectors.temporal_selector import TemporalSelector
     from det3d.selectors.euclidean_spatial_selector import EuSpatialSelector
 
-    return {
+    out = {
         "SpatialTemporalSelector": SpatialTemporalSelector,
         "SpatialSelector": SpatialSelector,
         "TemporalSelector": TemporalSelector,
         "EuSpatialSelector": EuSpatialSelector,
     }
+    try:
+        # feature_selector.py imports ``example_to_device`` from det3d.torchie.apis.train, which pulls in the whole
+        # detector stack; it is only used by ``buffer_pred`` (pred=True, needs the trained detector).  A placeholder
+        # module lets the UNMODIFIED class be imported and run with pred=False on stored features.
+        if "det3d.torchie.apis.train" not in sys.modules:
+            apis = sys.modules.get("det3d.torchie.apis") or types.ModuleType("det3d.torchie.apis")
+            apis.__path__ = []
+            train = types.ModuleType("det3d.torchie.apis.train")
+
+            def example_to_device(*a, **k):   # noqa: D401 - never called with pred=False
+                raise RuntimeError("detector forward is out of scope of the oracle")
+
+            train.example_to_device = example_to_device
+            apis.train = train
+            sys.modules.setdefault("det3d.torchie.apis", apis)
+            sys.modules["det3d.torchie.apis.train"] = train
+        from det3d.selectors.feature_selector import FeatureSelector
+        out["FeatureSelector"] = FeatureSelector
+    except Exception:   # pragma: no cover - torch missing etc.; the other selectors stay usable
+        pass
+    return out

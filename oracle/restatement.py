@@ -291,3 +291,45 @@ def select(kind, infos, logs, buffer, budget, first_index, cost_b=0.04, cost_f=0
     selected = greedy_select(prov.row, prov.n, n_boxes, sampled, first_index, current_budget, cost_b, cost_f,
                              forbid_sampled=(kind != "spatial_temporal"))
     return current_budget, sampled + selected
+
+
+# --------------------------------------------------------------------------------------------
+# feature-distance selector (det3d/selectors/feature_selector.py:87-172), restated with the reference's own
+# torch expressions (float32 on the CPU), rows computed lazily
+# --------------------------------------------------------------------------------------------
+def feature_row(feats, i: int, p: int = 2) -> np.ndarray:
+    """``distance_map[i]`` of feature_selector.py:96-101 as float32 numpy (``feats``: float32 [N, C] array)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(feats, dtype=np.float32))
+    if p == 1:
+        return torch.abs(t - t[i]).sum(1).numpy()
+    return torch.sqrt((t - t[i]) ** 2).sum(1).numpy()
+
+
+def feature_select(feats, n_boxes, buffer, budget, p=2, cost_b=0.04, cost_f=0.12):
+    """One ``FeatureSelector.select_samples()`` round: ``(current_budget_key, new + sampled)`` (:143-172)."""
+    max_key = str(max(int(k) for k in buffer))
+    current_budget = str(budget + int(max_key))
+    sampled = list(buffer[max_key])
+    rows = {}
+
+    def row(i):
+        if i not in rows:
+            rows[i] = feature_row(feats, i, p)
+        return rows[i]
+
+    fps = np.stack([row(i) for i in sampled]).min(0)
+    selected = [int(np.argmax(fps))]
+    cost = cost_of_sampled(n_boxes, sampled, cost_b, cost_f)
+    cost += cost_f
+    cost += int(n_boxes[selected[-1]]) * cost_b
+    while True:
+        fps = np.minimum(fps, row(selected[-1]))
+        nxt = int(np.argmax(fps))
+        assert nxt not in selected, f"id: {nxt} has been selected"
+        cost += cost_f
+        cost += int(n_boxes[nxt]) * cost_b
+        if cost > int(current_budget):
+            break
+        selected.append(nxt)
+    return current_budget, selected + sampled
