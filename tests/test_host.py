@@ -152,3 +152,41 @@ def test_logfile_names_fast_path_is_the_reference_expression():
              "a/L1__x.jpg", "a/L1x__1", "a/L1__", "a/L1__/w__e", "", "/", "__", "a/__b", "a/__c"]
     infos = [{"cam_front_path": p} for p in paths]
     assert pool.logfile_names(infos) == [p.split("/")[-1].split("__")[0] for p in paths]
+
+
+def test_emitted_files_drive_the_downstream_consumers(pools, tmp_path):
+    """the buffer JSON and the infos-subset pkl must keep feeding the training pipelines.
+
+    * bevfusion/tools/data_converter/nuscenes_converter.py:111-113 --
+      ``buffer = json.load(open(path, encoding='utf8')); infos = [infos[i] for i in buffer[str(budget)]]``
+    * tools/train.py:125-127 -- ``train_anno.replace(".pkl", f"_{budget}.pkl")`` is the training info file
+    * tools/create_data.py:30-37 -- the gt database is built from ``infos_train_10sweeps_withvelo_{suffix}.pkl``
+      (suffix = cumulative budget): a pickled ``list`` of the ORIGINAL info dicts.
+    """
+    pl = pools("P300")
+    buf = str(tmp_path / "buffer.json")
+    fileio.dump({"0": []}, buf, indent=4)                       # first CLI invocation (tools/active_select.py:68-71)
+    for budget, picked in ((600, [17, 3, 250]), (600, [8, 299])):
+        sel = BaseSelector(budget=budget, buffer_file=buf, infos_origin=pl["paths"]["infos"])
+        sampled = list(sel.buffer[sel.get_max_key()])
+        sel.selected_index[sel.current_budget] = sampled + picked
+        sel.dump_file()
+    # --- BEVFusion converter's access pattern
+    with open(buf, "r", encoding="utf8") as fe:
+        buffer = json.load(fe)
+    assert list(buffer) == ["0", "600", "1200"]                 # cumulative cost budgets as string keys
+    infos = pickle.load(open(pl["paths"]["infos"], "rb"))
+    for budget in (600, 1200):
+        subset = [infos[i] for i in buffer[str(budget)]]        # ints, in range, selection order
+        assert all(isinstance(i, int) for i in buffer[str(budget)])
+        # --- tools/train.py / tools/create_data.py naming rule and content
+        train_anno = pl["paths"]["infos"]
+        assert os.path.basename(train_anno) == "infos_train_10sweeps_withvelo.pkl"
+        path = train_anno.replace(".pkl", f"_{budget}.pkl")
+        assert os.path.basename(path) == f"infos_train_10sweeps_withvelo_{budget}.pkl"
+        stored = pickle.load(open(path, "rb"))
+        assert isinstance(stored, list) and len(stored) == len(subset)
+        for a, b in zip(stored, subset):
+            assert a.keys() == b.keys() and a["token"] == b["token"]
+            assert np.array_equal(a["car_from_global"], b["car_from_global"]) and np.array_equal(a["gt_names"], b["gt_names"])
+    assert buffer["1200"][:3] == buffer["600"]                  # a later round extends the earlier one
