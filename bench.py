@@ -555,6 +555,7 @@ def run_b200_arm(args):
             "stages_ms": stages, "selection_ms_per_budget": per_budget, "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": n / e2e_sec, "unit": "frames/s", "ms_per_step": e2e_sec * 1e3,
+                    "rank0_host_ms_last_step": selector.last_stats.get("host_ms"),
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clock_info,
             "extras": extras,

@@ -36,5 +36,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOSTEXT = os.path.join(CSRC, "_adsel_hostext.so")
+
+
+def build_hostext(force: bool = False):
+    """Compile the optional CPython helper for the host-side extraction (csrc/hostext.c); returns its path or
+    None when Python.h / gcc are not available (pool.py then keeps its pure-python implementation)."""
+    import shutil
+    import sysconfig
+    src = os.path.join(CSRC, "hostext.c")
+    if not force and os.path.exists(HOSTEXT) and os.path.getmtime(HOSTEXT) >= os.path.getmtime(src):
+        return HOSTEXT
+    inc = sysconfig.get_paths()["include"]
+    if not os.path.exists(os.path.join(inc, "Python.h")) or shutil.which("gcc") is None:
+        return HOSTEXT if os.path.exists(HOSTEXT) else None
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", f"-I{inc}", src, "-o", HOSTEXT, "-lm"])
+    return HOSTEXT
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

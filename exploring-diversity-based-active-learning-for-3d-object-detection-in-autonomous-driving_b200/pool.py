@@ -6,6 +6,10 @@ euclidean_spatial_selector.py:57-60,75-76 (city per frame).  String parsing stay
 numeric part is vectorised but keeps the reference's own numpy expressions, so the float64 ego
 locations are bit-identical to the reference loop (checked on a sample at run time and in tests).
 """
+import importlib.machinery
+import importlib.util
+import os
+
 import numpy as np
 
 
@@ -97,6 +101,52 @@ def box_counts(infos) -> np.ndarray:
     return np.fromiter((len(info["gt_names"]) for info in infos), dtype=np.int32, count=len(infos))
 
 
+_HOSTEXT = None
+
+
+def _hostext():
+    """The optional CPython helper (csrc/hostext.c), loaded from the in-tree build; ``False`` when unavailable."""
+    global _HOSTEXT
+    if _HOSTEXT is None:
+        _HOSTEXT = False
+        if os.environ.get("ADSEL_HOSTEXT", "1") != "0":
+            try:
+                from . import build as _build
+                path = _build.build_hostext()
+                if path and os.path.exists(path):
+                    loader = importlib.machinery.ExtensionFileLoader("_adsel_hostext", path)
+                    spec = importlib.util.spec_from_loader("_adsel_hostext", loader)
+                    mod = importlib.util.module_from_spec(spec)
+                    loader.exec_module(mod)
+                    _HOSTEXT = mod
+            except Exception:          # host-side convenience only: the python implementation below is equivalent
+                _HOSTEXT = False
+    return _HOSTEXT
+
+
+def extract_slice(infos, lo=0, hi=None, check: int = 64):
+    """``(names, locations, n_boxes)`` of ``infos[lo:hi]`` -- logfile_names / ego_locations / box_counts in one pass
+    over the list, in C when the helper is built.  The helper's ego locations are compared bit-for-bit with the
+    reference's literal expression on ``check`` probe frames (numpy's vector-matrix product uses fused
+    multiply-adds on FMA hosts and separately rounded products elsewhere: both orders are tried) and the python
+    implementation is used if neither matches or the infos are not the plain dicts / float64 matrices expected."""
+    hi = len(infos) if hi is None else hi
+    ext = _hostext()
+    if ext and isinstance(infos, list) and hi > lo:
+        probe = np.unique(np.linspace(lo, hi - 1, num=min(check, hi - lo)).astype(np.int64))
+        try:
+            want = _location_loop([infos[i]["car_from_global"] for i in probe]).view(np.uint64)
+            for fused in (True, False):
+                loc_b, box_b, names = ext.extract(infos, lo, hi, fused)
+                loc = np.frombuffer(loc_b, dtype=np.float64).reshape(-1, 2)
+                if np.array_equal(loc[probe - lo].view(np.uint64), want):
+                    return names, loc, np.frombuffer(box_b, dtype=np.int32)
+        except (TypeError, KeyError, ValueError):
+            pass
+    part = infos[lo:hi]
+    return logfile_names(part), ego_locations(part, check), box_counts(part)
+
+
 def extract_spatial_temporal(infos, known_logfiles=None):
     """Everything SpatialTemporalSelector needs from the infos list: ``(locations, run_id, max_td, n_boxes)``.
 
@@ -112,17 +162,18 @@ def extract_spatial_temporal(infos, known_logfiles=None):
     rank, world = get_dist_info()
     n = len(infos)
     if world <= 1 or n < 4 * world:
-        names = logfile_names(infos)
+        names, loc, boxes = extract_slice(infos)
         if known_logfiles is not None:
             for nm in names:
                 if nm not in known_logfiles:
                     raise KeyError(nm)
         run_id, max_td = consecutive_runs(names)
-        return ego_locations(infos), run_id, max_td, box_counts(infos)
+        return loc, run_id, max_td, boxes
+    import time
     import torch.distributed as dist
+    t0 = time.perf_counter()
     lo, hi = rank * n // world, (rank + 1) * n // world
-    part = infos[lo:hi]
-    names = logfile_names(part)
+    names, loc_mine, boxes_mine = extract_slice(infos, lo, hi)
     missing = None
     if known_logfiles is not None:
         missing = next((nm for nm in names if nm not in known_logfiles), None)
@@ -130,9 +181,11 @@ def extract_spatial_temporal(infos, known_logfiles=None):
     change = np.ones(len(names), dtype=bool)            # change[0] is fixed up against the previous slice's last name
     change[1:] = arr[1:] != arr[:-1]
     mine = {"lo": lo, "missing": missing, "first": names[0], "last": names[-1], "change": np.packbits(change),
-            "n": len(names), "loc": ego_locations(part), "boxes": box_counts(part)}
-    parts = [None] * world
-    dist.all_gather_object(parts, mine)
+            "n": len(names), "loc": loc_mine, "boxes": boxes_mine}
+    t1 = time.perf_counter()
+    parts = _all_gather_slices(dist, world, mine, -(-n // world))
+    t2 = time.perf_counter()
+    LAST_TIMING.update({"parse_own_slice_ms": (t1 - t0) * 1e3, "all_gather_ms": (t2 - t1) * 1e3})
     for p in parts:
         if p["missing"] is not None:
             raise KeyError(p["missing"])
@@ -146,3 +199,60 @@ def extract_spatial_temporal(infos, known_logfiles=None):
     loc = np.ascontiguousarray(np.concatenate([p["loc"] for p in parts]))
     boxes = np.concatenate([p["boxes"] for p in parts]).astype(np.int32)
     return loc, run_id, max_td, boxes
+
+
+LAST_TIMING = {}   # host-side timing of the last sharded extraction (reported by bench.py)
+_TEXT = 256   # bytes reserved per string field of a gathered slice header
+
+
+def _all_gather_slices(dist, world, mine, cap):
+    """All-gather of the per-rank slice records as ONE fixed-size byte tensor per rank (a single NCCL / gloo
+    collective; ``all_gather_object`` costs tens of milliseconds in pickling and staging for the same data).
+    Layout: int64 lo, n | three length-prefixed utf-8 fields (missing, first, last) | loc f64[cap,2] |
+    boxes i32[cap] | packed change bits u8[ceil(cap/8)]."""
+    import torch
+    nbits = -(-cap // 8)
+    size = 16 + 3 * (8 + _TEXT) + cap * 16 + cap * 4 + nbits
+    buf = np.zeros(size, dtype=np.uint8)
+    buf[:16] = np.array([mine["lo"], mine["n"]], dtype=np.int64).view(np.uint8)
+    off = 16
+    for key in ("missing", "first", "last"):
+        raw = b"" if mine[key] is None else mine[key].encode("utf-8")
+        if len(raw) > _TEXT:
+            raise ValueError(f"logfile name longer than {_TEXT} bytes: {mine[key][:40]}...")
+        flag = -1 if mine[key] is None else len(raw)
+        buf[off:off + 8] = np.array([flag], dtype=np.int64).view(np.uint8)
+        buf[off + 8:off + 8 + len(raw)] = np.frombuffer(raw, dtype=np.uint8)
+        off += 8 + _TEXT
+    k = mine["n"]
+    buf[off:off + k * 16] = np.ascontiguousarray(mine["loc"], dtype=np.float64).view(np.uint8).reshape(-1)
+    off += cap * 16
+    buf[off:off + k * 4] = np.ascontiguousarray(mine["boxes"], dtype=np.int32).view(np.uint8)
+    off += cap * 4
+    buf[off:off + len(mine["change"])] = mine["change"]
+    if dist.get_backend() == "nccl":
+        t = torch.from_numpy(buf).cuda()
+        out = torch.empty(world * size, dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        allb = out.cpu().numpy().reshape(world, size)
+    else:
+        outs = [torch.empty(size, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(outs, torch.from_numpy(buf))
+        allb = np.stack([o.numpy() for o in outs])
+    parts = []
+    for r in range(world):
+        b = allb[r]
+        lo, k = (int(v) for v in b[:16].view(np.int64))
+        rec = {"lo": lo, "n": k}
+        off = 16
+        for key in ("missing", "first", "last"):
+            flag = int(b[off:off + 8].view(np.int64)[0])
+            rec[key] = None if flag < 0 else bytes(b[off + 8:off + 8 + flag]).decode("utf-8")
+            off += 8 + _TEXT
+        rec["loc"] = b[off:off + k * 16].view(np.float64).reshape(k, 2)
+        off += cap * 16
+        rec["boxes"] = b[off:off + k * 4].view(np.int32)
+        off += cap * 4
+        rec["change"] = b[off:off + nbits]
+        parts.append(rec)
+    return parts

@@ -25,15 +25,15 @@ class EuSpatialSelector(BaseSelector):
 
     def select_samples(self, **kwargs) -> None:
         infos = self.infos_origin
-        city = pool.city_groups(pool.logfile_names(infos), load(self.logs_file))   # :57-60,75-76
-        locations = pool.ego_locations(infos)
+        names, locations, n_boxes = pool.extract_slice(infos)
+        city = pool.city_groups(names, load(self.logs_file))   # :57-60,75-76
         # rows take the cross-city margin 1e6 as their maximum; the sparse update relies on it
         extent = float(np.hypot(*(locations.max(0) - locations.min(0))))
         if not extent < 1e6:
             raise NotImplementedError("ego locations span >= 1e6 m: exceeds the reference's cross-city margin")
         handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's shard
         try:
-            handle.set_pool(locations, city, pool.box_counts(infos))
+            handle.set_pool(locations, city, n_boxes)
             self._run_greedy(handle, spatial="euclid", temporal=False, normalize="raw", forbid_sampled=True)
         finally:
             handle.close()

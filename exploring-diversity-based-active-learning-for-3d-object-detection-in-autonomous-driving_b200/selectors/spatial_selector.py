@@ -24,7 +24,7 @@ class SpatialSelector(BaseSelector):
 
     def select_samples(self, **kwargs) -> None:
         infos = self.infos_origin
-        names = pool.logfile_names(infos)
+        names, locations, n_boxes = pool.extract_slice(infos)
         known = {l["logfile"] for l in load(self.logs_file)}
         for nm in names:                                  # KeyError like spatial_selector.py:71
             if nm not in known:
@@ -32,7 +32,7 @@ class SpatialSelector(BaseSelector):
         run_id, _ = pool.consecutive_runs(names)
         handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's shard
         try:
-            handle.set_pool(pool.ego_locations(infos), run_id, pool.box_counts(infos))
+            handle.set_pool(locations, run_id, n_boxes)
             handle.build_knn_graph(self.k)
             self._run_greedy(handle, spatial="geodesic", temporal=False, normalize="raw", forbid_sampled=True)
         finally:

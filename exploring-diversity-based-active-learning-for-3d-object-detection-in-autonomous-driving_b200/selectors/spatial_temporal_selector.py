@@ -38,17 +38,24 @@ class SpatialTemporalSelector(BaseSelector):
         self.logger.info(f"lambda_t: {self.lambda_t}")
 
     def select_samples(self, **kwargs) -> None:
+        import time
+        t0 = time.perf_counter()
         infos = self.infos_origin
         known = {l["logfile"] for l in load(self.logs_file)}           # the reference raises KeyError at :80
         # :83-91 ego locations, :114-129 consecutive logfile runs, base_selector.py:85 box counts
         locations, run_id, max_td, n_boxes = pool.extract_spatial_temporal(infos, known)
+        t1 = time.perf_counter()
         handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's shard
         try:
             handle.set_pool(locations, run_id, n_boxes)
             handle.build_knn_graph(self.k)                # :93-101 (+ scipy's dense->CSR rules)
             max_sd = handle.geodesic_max_finite() if self.normalize == "linear" else 0.0   # :139
+            t2 = time.perf_counter()
             self._run_greedy(handle, spatial="geodesic", temporal=True, normalize=self.normalize,
                              aggregate=self.aggregate, lambda_t=self.lambda_t, max_spatial=max_sd,
                              max_temporal=max_td)
+            t3 = time.perf_counter()
+            self.last_stats["host_ms"] = {"extract": (t1 - t0) * 1e3, "pool+graph": (t2 - t1) * 1e3,
+                                          "lists+greedy+readback": (t3 - t2) * 1e3, **pool.LAST_TIMING}
         finally:
             handle.close()

@@ -190,3 +190,31 @@ def test_emitted_files_drive_the_downstream_consumers(pools, tmp_path):
             assert a.keys() == b.keys() and a["token"] == b["token"]
             assert np.array_equal(a["car_from_global"], b["car_from_global"]) and np.array_equal(a["gt_names"], b["gt_names"])
     assert buffer["1200"][:3] == buffer["600"]                  # a later round extends the earlier one
+
+
+def test_c_host_helper_equals_the_python_extraction(pools, monkeypatch):
+    """csrc/hostext.c (optional CPython helper) must return exactly what the python loops return: names, bit-equal
+    ego locations, box counts -- on a real pool, on a slice of it and on adversarial paths (incl. non-ASCII)."""
+    from adsel_b200 import pool as P
+    if not P._hostext():
+        pytest.skip("hostext helper not built (no Python.h / gcc)")
+    infos = pools("P2K")["infos"]
+    for lo, hi in ((0, len(infos)), (700, 1501), (5, 6)):
+        names, loc, boxes = P.extract_slice(infos, lo, hi)
+        part = infos[lo:hi]
+        assert names == [i["cam_front_path"].split("/")[-1].split("__")[0] for i in part]
+        assert np.array_equal(loc.view(np.uint64), R.ego_locations(part).view(np.uint64))
+        assert np.array_equal(boxes, [i["gt_names"].shape[0] for i in part])
+    paths = ["a/L1__x.jpg", "a/L1__y/z.jpg", "a/L1__y__z.jpg", "b/L1__x.jpg", "L2__q", "L2__r", "noseparator", "a/L1__x.jpg",
+             "a/L1x__1", "a/L1__", "a/L1__/w__e", "", "/", "__", "a/__b", "a/__c", "é/Ω__z", "é/Ω__w", "é/Ω_z"]
+    rng = np.random.default_rng(2)
+    adv = [{"cam_front_path": p, "car_from_global": rng.normal(size=(4, 4)), "gt_names": np.zeros(k % 5)} for k, p in enumerate(paths)]
+    names, loc, boxes = P.extract_slice(adv)
+    assert names == [p.split("/")[-1].split("__")[0] for p in paths]
+    assert np.array_equal(loc.view(np.uint64), R.ego_locations(adv).view(np.uint64))       # general matrices, not rotations
+    assert boxes.tolist() == [k % 5 for k in range(len(paths))]
+    # float32 matrices are not what the helper expects: the python path takes over, same result as the reference loop
+    adv32 = [dict(a, car_from_global=a["car_from_global"].astype(np.float32)) for a in adv]
+    _, loc32, _ = P.extract_slice(adv32)
+    assert np.array_equal(loc32.astype(np.float64), np.stack([(-(a["car_from_global"][:3, 3].T @ a["car_from_global"][:3, :3]))[:2]
+                                                               for a in adv32]).astype(np.float64))
