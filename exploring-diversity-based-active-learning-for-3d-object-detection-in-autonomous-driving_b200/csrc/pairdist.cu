@@ -461,6 +461,12 @@ struct BestI {
     int v, i;
 };
 __device__ __forceinline__ BestI better_i(BestI a, BestI b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+// warp arg-max with the first-maximum rule in two REDUX operations (the values are int32)
+__device__ __forceinline__ BestI warp_best_i(BestI x) {
+    const int mv = __reduce_max_sync(0xffffffffu, x.v);
+    const int mi = __reduce_min_sync(0xffffffffu, x.v == mv ? x.i : 0x7fffffff);
+    return BestI{mv, mi};
+}
 
 // fps lives in registers (ITEMS columns per thread, column j = threadIdx.x + 1024*i), so a step is one
 // fully unrolled wave of independent streaming row loads (one memory latency) plus the arg-reduce.
@@ -545,20 +551,11 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
                 }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            BestI y{__shfl_xor_sync(0xffffffffu, x.v, o), __shfl_xor_sync(0xffffffffu, x.i, o)};
-            x = better_i(x, y);
-        }
+        x = warp_best_i(x);
         if (lane == 0) warp_res[wid] = x;
         __syncthreads();
         if (wid == 0) {
-            BestI y = warp_res[lane];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                BestI z{__shfl_xor_sync(0xffffffffu, y.v, o), __shfl_xor_sync(0xffffffffu, y.i, o)};
-                y = better_i(y, z);
-            }
+            BestI y = warp_best_i(warp_res[lane]);
             int comm_status = 0;
             if (SHARDED) {   // squared distances are >= 0: the int value is its own ordered key; -1 marks an empty slice
                 const ExchangeResult r = exchange_best(comm, xlane, comm.seq_base + 1u + (unsigned)steps,
