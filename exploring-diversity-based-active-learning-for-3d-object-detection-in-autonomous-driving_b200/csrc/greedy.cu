@@ -8,16 +8,18 @@
 // distance_map[idx] differs from one constant `far` (the largest value a row can take) only on the
 // "touched" set: idx's geodesic neighbour list and idx's temporal group.  Since every fps entry is
 // already <= far, min(fps, row) only changes touched entries, so a step is a sparse update plus an
-// arg-reduce over per-256-frame block maxima (recomputed only for dirtied blocks).  One CTA runs
+// arg-reduce over per-128-frame block maxima (recomputed only for dirtied blocks).  One CTA runs
 // the whole loop: steps are strictly sequential and a step is about a microsecond, so a grid-wide
 // barrier per step would cost more than the work.
 //
 // A step is a chain of dependent L2 round trips, so the kernel is organised to need as few as
 // possible: (1) lane 0 fetches the selected frame's 32-byte FrameRec (list range, group range, box
-// count) together with its is_selected flag; (2) every thread loads one precombined (index, value)
-// list entry and one group entry; (3) atomicMin into fps; (4) the dirtied 256-frame blocks are
-// re-read.  Block maxima, dirty flags and the dirty list live in shared memory; warp 0 alone does
-// the final arg-reduce and the cost bookkeeping, so a step has three CTA barriers.
+// cost) -- an L1 hit thanks to the prefetch issued when its block was last refreshed; the selected-frame
+// flags are a bitmap in shared memory; (2) the first two warps load the precombined (index, value)
+// list entries while the others compute the group entries from a shared-memory LUT; (3) atomicMin
+// into fps; (4) the dirtied 128-frame blocks are re-read, one warp per block, tree + REDUX arg-max.
+// Block maxima, dirty flags and the dirty list live in shared memory; warp 0 alone does the final
+// arg-reduce and the cost bookkeeping, so a step has three CTA barriers.
 //
 // SHARDED = true: the rank owns columns [lo, hi) only (its lists hold only those columns), and the
 // step's local maximum is exchanged with the other ranks through peer-memory mailboxes (comm.cuh)
@@ -295,7 +297,6 @@ __global__ void __launch_bounds__(NT, 1) greedy_select_kernel(const GreedyArgs a
     for (int d = threadIdx.x; d < tl_n; d += NT) tl[d] = a.tlut[d];
     __shared__ GreedyShared sh;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int NWARPS = NT / 32;
     ExchangeLane xlane;
     if (SHARDED) xlane = make_exchange_lane(comm);
 

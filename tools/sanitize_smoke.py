@@ -48,7 +48,7 @@ def main():
     h.select(spatial="none", temporal=True, normalize="raw", forbid_sampled=True, budget=40, first_index=first)
     h.set_pool(loc, pool.city_groups(names, logs), nb)
     h.select(spatial="euclid", temporal=False, normalize="raw", forbid_sampled=True, budget=40, first_index=first)
-    h.geodesic_rows([0, 5, 299]) if False else None
+    h.geodesic_rows([0, 5, 299])
     # BEV descriptors, tcgen05 tiles, dense greedy
     sizes = 3000 + (np.arange(40) * 131) % 301
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
