@@ -267,7 +267,7 @@ def bev_extras(native, device, n_frames, n_boxes, first, peaks, reps=3, batch=20
 
 
 def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_ranks, barrier, reps=2, batch=1024,
-                       pts_per_frame=300_000):
+                       pts_per_frame=300_000, budget=1200, key="bev_sharded_budget1200"):
     """BASELINE.json config 3 shape on N ranks: every rank histograms its own slice of the 28,130 frames x ~300k
     points (descriptors stored into every rank's arena by the kernel epilogue), computes the tcgen05 distance
     tiles of its column slice and runs the dense greedy loop (budget 1200) with one exchange per step."""
@@ -297,7 +297,7 @@ def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_r
             timed_bev_build.ms = 0.0
             barrier()
             w.dense_build(n_frames, batch, load_batch)
-            sel, _ = w.dense_select(n_boxes, budget=1200, first_index=first)
+            sel, _ = w.dense_select(n_boxes, budget=budget, first_index=first)
             st = h.stage_ms()
             if rep > 0:
                 hist_ms.append(timed_bev_build.ms)
@@ -313,8 +313,9 @@ def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_r
     gbs_rank = (20.0 * my_pts + (hi - lo) * (16384 * (4 + 2 * w.world) + 4)) / (sum(hist_ms) / len(hist_ms) * 1e-3) / 1e9
     tf_rank = 2.0 * n_frames * (hi - lo) * 16384 / (sum(pd_ms) / len(pd_ms) * 1e-3) / 1e12
     total = ms_h + ms_p + ms_g
-    return {"bev_sharded_budget1200": {
-        "workload": "BevSpatialSelector/budget1200/%d frames x ~300k points sharded over %d GPUs" % (n_frames, w.world),
+    return {key: {
+        "workload": "BevSpatialSelector/budget%d/%d frames x ~300k points sharded over %d GPUs" % (budget, n_frames, w.world),
+        "distance_matrix_GB_total": 4.0 * n_frames * n_frames / 1e9, "distance_matrix_GB_per_rank": 4.0 * n_frames * (hi - lo) / 1e9,
         "selected_frames": len(sel), "histogram_ms": ms_h, "pairdist_ms_incl_2_barriers": ms_p, "greedy_ms": ms_g,
         "us_per_step": ms_g * 1e3 / max(len(sel), 1), "ms_total": total, "frames_per_s": n_frames / (total * 1e-3),
         "rank0_histogram_GBps": gbs_rank, "rank0_histogram_frac_of_hbm_peak": gbs_rank / peaks["hbm"],
@@ -497,6 +498,11 @@ def run_b200_arm(args):
                     os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
                 peaks = {"hbm": float(pk.get("hbm_gbs", 6650.0)), "bf16": float(pk.get("bf16_tflops", 1590.0))}
                 bev_sh = bev_extras_sharded(h, len(infos28), pool.box_counts(infos28), first28, peaks, max_over_ranks, barrier)
+                if args.bev_scale > 1:      # BASELINE.json config 5 shape on the dense path: a pool whose int32 distance
+                    nbig = len(infos28) * args.bev_scale          # matrix (4 N^2 bytes) does not fit one GPU
+                    boxes_big = np.random.default_rng(1).integers(0, 60, size=nbig).astype(np.int32)
+                    bev_sh.update(bev_extras_sharded(h, nbig, boxes_big, first_index(nbig), peaks, max_over_ranks, barrier, reps=1,
+                                                     budget=BUDGET, key="bev_sharded_scaled_pool"))
         h.close()
 
         # ---- BEV-descriptor configuration: HBM-bound histogram and tensor-core distance tiles ----
@@ -575,6 +581,8 @@ def main():
     ap.add_argument("--port", action="store_true", help="--impl reference: force the oracle port even if /root/reference exists")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bev", action="store_true", help="skip the BEV-descriptor extras (histogram / tcgen05 tiles)")
+    ap.add_argument("--bev-scale", type=int, default=1, help="N > 1 only: also run the dense BEV path on a pool of "
+                    "28,130 x this many frames, budget 4800 (10 = the 281,300-frame pool: a 316 GB distance matrix)")
     args = ap.parse_args()
     logging.basicConfig(level=logging.WARNING)
     if args.impl == "reference":

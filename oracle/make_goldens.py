@@ -81,7 +81,7 @@ def run_case(classes, sel_name, paths, kwargs, rounds, workdir, keep_store=None)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pool", default="P2K")
-    ap.add_argument("--only", default="all", help="all | st (SpatialTemporal exp/sum only)")
+    ap.add_argument("--only", default="all", help="all | st (SpatialTemporal exp/sum only) | temporal (TemporalSelector only)")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
     ap.add_argument("--budget", type=int, default=600, help="base budget B; chained cases use B/2,B/2,B")
     args = ap.parse_args()
@@ -99,7 +99,10 @@ def main():
         paths = synthetic.write_pool(spec, wd)
         store = os.path.join(wd, "geodesic.npy")   # shared: the geodesic map is identical across ST cases
         cases = []
-        if args.only == "st":
+        if args.only == "temporal":     # BASELINE.json config 4: temporal-only selector, 850 scenes, budget 1200
+            cases += [("temporal_1200", "TemporalSelector", {}, [1200]),
+                      ("temporal_rounds", "TemporalSelector", {}, [600, 600])]
+        elif args.only == "st":
             cases += [("st_exp_sum", "SpatialTemporalSelector", {}, [600]),
                       ("st_exp_sum_1200", "SpatialTemporalSelector", {}, [1200]),
                       ("st_exp_sum_4800", "SpatialTemporalSelector", {}, [4800]),

@@ -248,3 +248,12 @@ def test_cluster_variant_of_the_greedy_loop_selects_identically(handle, pools, m
     monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
     want2, _ = handle.select(**{**kw, "budget": 900, "sampled": want, "first_index": -1, "cost_start": want_cost})
     assert got2 == want2
+
+
+def test_p850_temporal_selector_budget_1200_identical_to_reference(pools, tmp_path):
+    """BASELINE.json config 4: temporal-only selector over the 850-scene pool (28,130 frames, 71 logs), budget 1200."""
+    golden = load_golden("P850_temporal.json")
+    pl = pools("P850")
+    for cid, case in golden["cases"].items():
+        res, _ = _run_case_through_selectors(pl, case, tmp_path)
+        assert res == case["selected_index"], cid

@@ -63,3 +63,12 @@ def test_consecutive_runs_ignores_last_run_for_max():
     run_id, max_td = R.consecutive_runs(infos)
     assert run_id.tolist() == [0, 0, 1, 1, 1, 2, 2, 3, 3, 3, 3]
     assert max_td == 3      # the final run of 4 is never counted (reference :127-129)
+
+
+def test_restatement_reproduces_the_p850_temporal_golden(pools):
+    """BASELINE.json config 4 (TemporalSelector, 850 scenes, budget 1200): oracle port vs the unmodified reference."""
+    golden = load_golden("P850_temporal.json")
+    pl = pools("P850")
+    case = golden["cases"]["temporal_1200"]
+    key, sel = R.select("temporal", pl["infos"], pl["logs"], {"0": []}, 1200, first_index_for(len(pl["infos"])))
+    assert sel == case["selected_index"][key]
