@@ -501,7 +501,7 @@ def run_b200_arm(args):
                 if args.bev_scale > 1:      # BASELINE.json config 5 shape on the dense path: a pool whose int32 distance
                     nbig = len(infos28) * args.bev_scale          # matrix (4 N^2 bytes) does not fit one GPU
                     boxes_big = np.random.default_rng(1).integers(0, 60, size=nbig).astype(np.int32)
-                    bev_sh.update(bev_extras_sharded(h, nbig, boxes_big, first_index(nbig), peaks, max_over_ranks, barrier, reps=1,
+                    bev_sh.update(bev_extras_sharded(h, nbig, boxes_big, first_index(nbig), peaks, max_over_ranks, barrier, reps=2,
                                                      budget=BUDGET, key="bev_sharded_scaled_pool"))
         h.close()
 

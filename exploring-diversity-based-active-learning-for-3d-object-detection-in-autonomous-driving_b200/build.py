@@ -26,13 +26,39 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+class _BuildLock:
+    """Inter-process lock for in-tree builds: under torchrun every rank imports the package at the same time, and
+    two compilers writing the same output (or a rank loading a half-written library) must never happen."""
+
+    def __enter__(self):
+        import fcntl
+        self._f = open(os.path.join(CSRC, ".build.lock"), "w")
+        fcntl.flock(self._f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self._f, fcntl.LOCK_UN)
+        self._f.close()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu for sm_100a into one shared library; returns its path."""
+    """Compile every .cu for sm_100a into one shared library; returns its path.  The library is written to a
+    temporary name and renamed into place, under a lock, so concurrent ranks never see a partial file."""
     if not force and not needs_build():
         return LIB
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources() + ["-lcuda"]
-    subprocess.check_call(cmd, cwd=CSRC)
+    with _BuildLock():
+        if not force and not needs_build():          # another process built it while this one waited
+            return LIB
+        nvcc = os.environ.get("NVCC", "nvcc")
+        tmp = f"{LIB}.tmp{os.getpid()}"
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources() + ["-lcuda"]
+        try:
+            subprocess.check_call(cmd, cwd=CSRC)
+            os.replace(tmp, LIB)
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
     return LIB
 
 
@@ -50,7 +76,16 @@ def build_hostext(force: bool = False):
     inc = sysconfig.get_paths()["include"]
     if not os.path.exists(os.path.join(inc, "Python.h")) or shutil.which("gcc") is None:
         return HOSTEXT if os.path.exists(HOSTEXT) else None
-    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", f"-I{inc}", src, "-o", HOSTEXT, "-lm"])
+    with _BuildLock():
+        if not force and os.path.exists(HOSTEXT) and os.path.getmtime(HOSTEXT) >= os.path.getmtime(src):
+            return HOSTEXT
+        tmp = f"{HOSTEXT}.tmp{os.getpid()}"
+        try:
+            subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", f"-I{inc}", src, "-o", tmp, "-lm"])
+            os.replace(tmp, HOSTEXT)
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
     return HOSTEXT
 
 

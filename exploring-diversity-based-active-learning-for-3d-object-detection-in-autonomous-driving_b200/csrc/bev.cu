@@ -456,7 +456,7 @@ int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics,
     // measured on B200, 2,048 frames x ~300k points: ldg 4.75 TB/s, tma16x3 4.96, tma24x2 6.36, tma32x2 6.66 TB/s -- the
     // default is the largest ring configuration whose shared memory fits next to the histogram
     const int configs[3][2] = {{32, 2}, {24, 2}, {16, 3}};
-    int tw = 0, ts = 0;
+    int tw = 0;
     size_t smem_tma = 0;
     for (int c = 0; c < 3 && tw == 0; ++c) {
         const int w = configs[c][0], st = configs[c][1];
@@ -465,8 +465,7 @@ int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics,
         if (mode && !strncmp(mode, "tma", 3) && strlen(mode) > 3 && strcmp(mode, name)) continue;   // a specific one was asked for
         const size_t need = (((size_t)cells * sizeof(int) + 127) & ~(size_t)127) + (size_t)w * st * CHUNK_BYTES +
                             (size_t)w * st * sizeof(uint64_t);
-        if (need <= 225 * 1024) tw = w, ts = st, smem_tma = need;
-        (void)ts;
+        if (need <= 225 * 1024) tw = w, smem_tma = need;
     }
     const bool use_tma = !(mode && !strcmp(mode, "ldg")) && tw > 0;
     ADSEL_TRY(begin_stage(h));
