@@ -275,7 +275,6 @@ def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_r
     w = world_engine
     h = w.handle
     sizes = pts_per_frame + (np.arange(n_frames, dtype=np.int64) * 977) % 4001 - 2000
-    lo, hi = w.handle.shard_range() if w._arena_shape else (0, 0)
     hist_ms, pd_ms, g_ms, sel = [], [], [], None
 
     def load_batch(handle, a, b):
@@ -305,7 +304,8 @@ def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_r
                 g_ms.append(st["dense_greedy"])
     finally:
         h.bev_build = orig_bev_build
-    lo, hi = h.shard_range()
+    from adsel_b200 import sharded as _sh
+    lo, hi = _sh.shard_bounds(n_frames, w.world, w.rank)      # the dense pool's slices (the handle's range is the sparse pool's)
     my_pts = int(sizes[lo:hi].sum())
     ms_h = max_over_ranks(sum(hist_ms) / len(hist_ms))
     ms_p = max_over_ranks(sum(pd_ms) / len(pd_ms))

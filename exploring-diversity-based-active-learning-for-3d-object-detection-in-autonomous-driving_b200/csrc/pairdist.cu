@@ -449,6 +449,7 @@ constexpr int DG_THREADS = 1024;
 struct DenseArgs {
     int n, ld;        // n: columns owned by this rank (the whole pool when not sharded); ld: row pitch of d2
     int col0;         // pool index of local column 0
+    int smem_fps;     // generic variant: the min-distance vector lives in dynamic shared memory (n <= 51,200 columns)
     const int32_t *d2, *n_boxes, *sampled;
     int32_t *fps, *out;
     unsigned char *is_selected;
@@ -481,6 +482,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr int NREG = ITEMS > 0 ? ITEMS : 1;
     int fps_reg[NREG];
+    extern __shared__ int dg_smem[];
+    int *fps = (ITEMS == 0 && a.smem_fps) ? dg_smem : a.fps;   // generic variant: shared memory when the slice fits
     ExchangeLane xlane;
     if (SHARDED) xlane = make_exchange_lane(comm);
     if (threadIdx.x == 0) {
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
         for (int j = threadIdx.x; j < a.n; j += DG_THREADS) {
             int v = 0x7fffffff;
             for (int t = 0; t < a.n_sampled; ++t) v = min(v, a.d2[(size_t)a.sampled[t] * a.ld + j]);
-            a.fps[j] = v;
+            fps[j] = v;
         }
     }
     __syncthreads();
@@ -539,15 +542,24 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
                 }
             }
         } else {
-            for (int j = threadIdx.x; j < a.n; j += DG_THREADS) {
-                int v = a.fps[j];
-                if (row) {
-                    v = min(v, __ldcs(row + j));
-                    a.fps[j] = v;
+            for (int j0 = threadIdx.x; j0 < a.n; j0 += 4 * DG_THREADS) {   // 4 independent row loads in flight per thread
+                int r[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = j0 + q * DG_THREADS;
+                    r[q] = (row && j < a.n) ? __ldcs(row + j) : 0x7fffffff;
                 }
-                if (v > x.v) {
-                    x.v = v;
-                    x.i = a.col0 + j;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = j0 + q * DG_THREADS;
+                    if (j < a.n) {
+                        const int v = min(fps[j], r[q]);
+                        if (row) fps[j] = v;
+                        if (v > x.v) {
+                            x.v = v;
+                            x.i = a.col0 + j;
+                        }
+                    }
                 }
             }
         }
@@ -612,6 +624,8 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
             const int j = threadIdx.x + DG_THREADS * i;
             if (j < a.n) a.fps[j] = fps_reg[i];
         }
+    } else if (a.smem_fps) {
+        for (int j = threadIdx.x; j < a.n; j += DG_THREADS) a.fps[j] = fps[j];
     }
     if (threadIdx.x == 0) {
         a.result[0] = s_cost;
@@ -649,7 +663,11 @@ static void launch_dense(adsel_handle *h, const DenseArgs &a, const CommView &vi
     if (a.n <= 8 * DG_THREADS) dense_greedy_kernel<8, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
     else if (a.n <= 16 * DG_THREADS) dense_greedy_kernel<16, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
     else if (a.n <= 32 * DG_THREADS) dense_greedy_kernel<32, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
-    else dense_greedy_kernel<0, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
+    else {
+        const size_t smem = a.smem_fps ? (size_t)a.n * sizeof(int) : 0;
+        cudaFuncSetAttribute(dense_greedy_kernel<0, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dense_greedy_kernel<0, SHARDED><<<1, DG_THREADS, smem, h->stream>>>(a, view);
+    }
 }
 
 static int dense_enqueue(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
@@ -660,6 +678,7 @@ static int dense_enqueue(adsel_handle *h, const adsel_select_params *p, const in
     a.n = h->pd_cols;
     a.ld = h->pd_ld;
     a.col0 = h->pd_col0;
+    a.smem_fps = (a.n > 32 * DG_THREADS && (size_t)a.n * sizeof(int) <= 200 * 1024) ? 1 : 0;
     a.d2 = h->pd_d2.p;
     a.n_boxes = h->pd_boxes.p;
     a.sampled = h->d_sampled.p;

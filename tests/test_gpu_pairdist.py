@@ -132,3 +132,24 @@ def test_bev_spatial_selector_drop_in(pools, tmp_path):
     r2 = R.greedy_select(lambda i: d2[i], len(infos), n_boxes, r1, -1, "80", forbid_sampled=True)
     assert res == {"40": r1, "80": r1 + r2}
     assert json.load(open(buf)) == {"0": [], "40": r1, "80": r1 + r2}
+
+
+def test_dense_greedy_generic_variant_beyond_32k_columns(handle):
+    """More than 32,768 columns: the min-distance vector moves from registers to shared memory (<= 51,200 columns) or
+    global memory; both must select like the oracle loop (short descriptors keep the matrix small: 40k x 40k int32)."""
+    for n in (33_000, 52_000):
+        dim = 8
+        rng = np.random.default_rng(n)
+        lv = rng.integers(0, 32, size=(n, dim))
+        n_boxes = rng.integers(0, 60, size=n).astype(np.int32)
+        handle.pairdist_set_descriptors(B.bf16_bits(lv))
+        handle.pairdist_build()
+        lv64 = lv.astype(np.int64)
+        norms = (lv64 ** 2).sum(1)
+
+        def row(i):
+            return (norms + norms[i] - 2 * (lv64 @ lv64[i])).astype(np.float64)
+
+        ref = R.greedy_select(row, n, n_boxes, [], 7, "40", forbid_sampled=True)
+        got, _ = handle.select_dense(n_boxes, budget=40, first_index=7)
+        assert got == ref
