@@ -542,23 +542,31 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
                 }
             }
         } else {
-            for (int j0 = threadIdx.x; j0 < a.n; j0 += 4 * DG_THREADS) {   // 4 independent row loads in flight per thread
-                int r[4];
+            // 16-byte row loads, two per thread in flight (the row pitch and the slice start are 16-byte aligned);
+            // a thread's columns ascend, so strict '>' keeps its first maximum
+            const int n4 = (a.n + 3) / 4;
+            for (int c0 = threadIdx.x; c0 < n4; c0 += 2 * DG_THREADS) {
+                int4 r[2];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int j = j0 + q * DG_THREADS;
-                    r[q] = (row && j < a.n) ? __ldcs(row + j) : 0x7fffffff;
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c0 + q * DG_THREADS;
+                    r[q] = (row && c < n4) ? __ldcs(reinterpret_cast<const int4 *>(row) + c) : make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int j = j0 + q * DG_THREADS;
-                    if (j < a.n) {
-                        const int v = min(fps[j], r[q]);
-                        if (row) fps[j] = v;
-                        if (v > x.v) {
-                            x.v = v;
-                            x.i = a.col0 + j;
-                        }
+                for (int q = 0; q < 2; ++q) {
+                    const int c = c0 + q * DG_THREADS;
+                    if (c < n4) {
+                        int4 f = reinterpret_cast<int4 *>(fps)[c];
+                        f.x = min(f.x, r[q].x);
+                        f.y = min(f.y, r[q].y);
+                        f.z = min(f.z, r[q].z);
+                        f.w = min(f.w, r[q].w);
+                        if (row) reinterpret_cast<int4 *>(fps)[c] = f;
+                        const int j = 4 * c;
+                        if (j + 0 < a.n && f.x > x.v) { x.v = f.x; x.i = a.col0 + j; }
+                        if (j + 1 < a.n && f.y > x.v) { x.v = f.y; x.i = a.col0 + j + 1; }
+                        if (j + 2 < a.n && f.z > x.v) { x.v = f.z; x.i = a.col0 + j + 2; }
+                        if (j + 3 < a.n && f.w > x.v) { x.v = f.w; x.i = a.col0 + j + 3; }
                     }
                 }
             }
@@ -647,7 +655,7 @@ static int dense_validate(adsel_handle *h, const adsel_select_params *p, const i
 
 int dense_prepare(adsel_handle *h, int32_t n_sampled, int32_t out_cap) {
     ADSEL_REQUIRE(h->pd_n > 0, "adsel_select_dense: call adsel_pairdist_build first");
-    ADSEL_TRY(h->pd_fps.reserve(h->pd_cols > 0 ? h->pd_cols : 1));
+    ADSEL_TRY(h->pd_fps.reserve((size_t)h->pd_cols + 4));   // the generic greedy variant touches it in 16-byte words
     ADSEL_TRY(h->pd_boxes.reserve(h->pd_n));
     ADSEL_TRY(h->is_selected.reserve(h->pd_n));
     ADSEL_TRY(h->d_sampled.reserve(n_sampled > 0 ? n_sampled : 1));
@@ -664,7 +672,7 @@ static void launch_dense(adsel_handle *h, const DenseArgs &a, const CommView &vi
     else if (a.n <= 16 * DG_THREADS) dense_greedy_kernel<16, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
     else if (a.n <= 32 * DG_THREADS) dense_greedy_kernel<32, SHARDED><<<1, DG_THREADS, 0, h->stream>>>(a, view);
     else {
-        const size_t smem = a.smem_fps ? (size_t)a.n * sizeof(int) : 0;
+        const size_t smem = a.smem_fps ? ((size_t)a.n + 4) * sizeof(int) : 0;
         cudaFuncSetAttribute(dense_greedy_kernel<0, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dense_greedy_kernel<0, SHARDED><<<1, DG_THREADS, smem, h->stream>>>(a, view);
     }
