@@ -364,7 +364,7 @@ int adsel_pairdist_get_rows(adsel_handle *h, int32_t row0, int32_t rows, int32_t
     ADSEL_CUDA(cudaStreamSynchronize(h->stream));
     // out is [rows, pd_cols]: the columns this handle holds (all of them unless the matrix is a column shard)
     if (h->pd_cols > 0)
-        ADSEL_CUDA(cudaMemcpy2D(out, sizeof(int32_t) * h->pd_cols, h->pd_d2.p + (size_t)row0 * h->pd_ld, sizeof(int32_t) * h->pd_ld,
+        ADSEL_CUDA(cudaMemcpy2D(out, sizeof(int32_t) * h->pd_cols, h->d2_p + (size_t)row0 * h->pd_ld, sizeof(int32_t) * h->pd_ld,
                                 sizeof(int32_t) * h->pd_cols, rows, cudaMemcpyDeviceToHost));
     return ADSEL_OK;
 }

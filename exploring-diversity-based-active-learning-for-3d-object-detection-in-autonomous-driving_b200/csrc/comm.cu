@@ -22,9 +22,9 @@ constexpr size_t COMM_ERROR_WORD = COMM_BARRIER_WORD + COMM_MAX_WORLD;       // 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct ArenaLayout {
-    size_t knn_idx, knn_dist, levels, norm2, list_cursor, list_off, list_len, list_idx, list_val, total;
+    size_t knn_idx, knn_dist, levels, norm2, list_cursor, list_off, list_len, list_idx, list_val, d2, total;
 };
-static ArenaLayout arena_layout(int64_t n, int64_t k1, int64_t dim, int64_t list_cap) {
+static ArenaLayout arena_layout(int64_t n, int64_t k1, int64_t dim, int64_t list_cap, int64_t world) {
     ArenaLayout l;
     l.knn_idx = COMM_MAILBOX_BYTES;
     l.knn_dist = l.knn_idx + align256((size_t)n * k1 * sizeof(int32_t));
@@ -35,10 +35,20 @@ static ArenaLayout arena_layout(int64_t n, int64_t k1, int64_t dim, int64_t list
     l.list_len = l.list_off + align256((size_t)n * sizeof(int64_t));
     l.list_idx = l.list_len + align256((size_t)n * sizeof(int32_t));
     l.list_val = l.list_idx + align256((size_t)list_cap * sizeof(int32_t));
-    l.total = l.list_val + align256((size_t)list_cap * sizeof(double));
+    l.d2 = l.list_val + align256((size_t)list_cap * sizeof(double));
+    // column slice of the descriptor distance matrix (dense path on several ranks): [rows_pad, per] int32, where
+    // per = columns per rank; it lives in the arena because peers store the mirror images of their tiles into it
+    size_t d2_bytes = 0;
+    if (dim > 0 && world > 1) {
+        const int64_t rows = (n + 127) / 128 * 128;
+        int64_t per = (n + world - 1) / world;
+        per = (per + 255) / 256 * 256;
+        d2_bytes = (size_t)rows * per * sizeof(int32_t);
+    }
+    l.total = l.d2 + align256(d2_bytes);
     return l;
 }
-static ArenaLayout layout_of(const adsel_handle *h) { return arena_layout(h->arena_n, h->arena_k1, h->arena_dim, h->arena_list_cap); }
+static ArenaLayout layout_of(const adsel_handle *h) { return arena_layout(h->arena_n, h->arena_k1, h->arena_dim, h->arena_list_cap, h->world); }
 
 void update_shard(adsel_handle *h) {
     if (h->world <= 1 || h->n <= 0) {
@@ -147,7 +157,7 @@ int adsel_comm_init(adsel_handle *h, int32_t rank, int32_t world, int32_t n, int
     comm_release(h);
     // neighbour-list region: generous default (entries), a caller that saw an overflow passes what was needed
     if (list_cap <= 0) list_cap = k > 0 ? (long long)n * 256 / world + (long long)n * 16 : 0;
-    const ArenaLayout l = arena_layout(n, k + 1, dim, list_cap);
+    const ArenaLayout l = arena_layout(n, k + 1, dim, list_cap, world);
     ADSEL_CUDA(cudaMalloc(&h->arena, l.total));
     ADSEL_CUDA(cudaMemset(h->arena, 0, COMM_MAILBOX_BYTES));
     h->arena_bytes = l.total;
@@ -276,6 +286,7 @@ int32_t *arena_knn_idx(adsel_handle *h, int w) { return reinterpret_cast<int32_t
 double *arena_knn_dist(adsel_handle *h, int w) { return reinterpret_cast<double *>(h->peer_arena[w] + layout_of(h).knn_dist); }
 uint16_t *arena_levels(adsel_handle *h, int w) { return reinterpret_cast<uint16_t *>(h->peer_arena[w] + layout_of(h).levels); }
 int32_t *arena_norm2(adsel_handle *h, int w) { return reinterpret_cast<int32_t *>(h->peer_arena[w] + layout_of(h).norm2); }
+int32_t *arena_d2(adsel_handle *h, int w) { return reinterpret_cast<int32_t *>(h->peer_arena[w] + layout_of(h).d2); }
 ListStore arena_lists(adsel_handle *h, int w) {
     const ArenaLayout l = layout_of(h);
     unsigned char *a = h->peer_arena[w];

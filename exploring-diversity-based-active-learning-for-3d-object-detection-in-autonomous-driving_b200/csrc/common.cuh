@@ -151,6 +151,7 @@ struct adsel_handle {
     // pairwise squared distances of the descriptors (dense path)
     int32_t pd_n = 0, pd_ld = 0, pd_col0 = 0, pd_cols = 0;   // pool frames, row pitch, first / number of local columns
     adsel::DevBuf<int32_t> pd_d2, pd_norm, pd_fps, pd_boxes;
+    int32_t *d2_p = nullptr;                     // distance matrix in use: pd_d2, or the arena's slice (sharded: peers store mirrored tiles into it)
     adsel::DevBuf<float> feat;                   // detector features [n, dim] (feature-distance map)
     adsel::DevBuf<int2> pd_tiles;                // (row block, column block) of every distance tile, in visiting order
 

@@ -103,13 +103,14 @@ int feature_distance_build(adsel_handle *h, const float *feats_host, int32_t n, 
     ADSEL_TRY(h->feat.reserve((size_t)n * dim));
     ADSEL_TRY(h->pd_d2.reserve((size_t)n * ld));
     ADSEL_CUDA(cudaMemcpyAsync(h->feat.p, feats_host, sizeof(float) * (size_t)n * dim, cudaMemcpyHostToDevice, h->stream));
+    h->d2_p = h->pd_d2.p;
     h->pd_n = n;
     h->pd_ld = ld;
     h->pd_col0 = 0;
     h->pd_cols = n;
     ADSEL_TRY(begin_stage(h));
     dim3 grid((n + FD_TILE - 1) / FD_TILE, (n + FD_TILE - 1) / FD_TILE);
-    feature_l1_kernel<<<grid, FD_THREADS, 0, h->stream>>>(h->feat.p, n, dim, p == 2 ? 1 : 0, reinterpret_cast<float *>(h->pd_d2.p), ld);
+    feature_l1_kernel<<<grid, FD_THREADS, 0, h->stream>>>(h->feat.p, n, dim, p == 2 ? 1 : 0, reinterpret_cast<float *>(h->d2_p), ld);
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     ADSEL_TRY(end_stage(h, 6));

@@ -104,6 +104,24 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 struct PdTile {
     int m_blk, n_blk;
 };
+
+// Which tiles are computed and where their mirror images go (the matrix is symmetric).
+//   mode 0: every tile, no mirror (a column slice computed on its own)
+//   mode 1: one GPU: tiles with n_blk >= m_blk / 2 (they cover every j >= i), mirror into the same matrix
+//   mode 2: sharded: in 256 x 256 macro-tiles (I = m_blk / 2, J = global column block) a rank computes, of its own
+//           columns J, the diagonal, the macro-tiles above it with I + J even and those below it with I + J odd, and
+//           stores each mirror image into the slice of the rank that owns columns I -- every rank computes about
+//           half of its slice and every cell of every slice is written exactly once.
+struct PdMirror {
+    int mode, rows, per, world;
+    int32_t *out[8];
+};
+__host__ __device__ __forceinline__ bool pd_tile_wanted(int mode, int mb, int nb, int j0) {
+    if (mode == 0) return true;
+    if (mode == 1) return nb >= mb / 2;
+    const int I = mb / 2, J = j0 + nb;
+    return I == J || (I < J && ((I + J) & 1) == 0) || (I > J && ((I + J) & 1) == 1);
+}
 __device__ __forceinline__ PdTile pd_tile(int t, int blocks_m, int blocks_n) {
     const int per_group = PD_GROUP_M * blocks_n;
     const int group = t / per_group, in_group = t - group * per_group;
@@ -115,7 +133,7 @@ __device__ __forceinline__ PdTile pd_tile(int t, int blocks_m, int blocks_n) {
 __global__ void __launch_bounds__(PD_THREADS, 1)
 pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t *__restrict__ norm2,
                         int32_t *__restrict__ out, int ld, const int2 *__restrict__ tiles, int n_tiles, int k_blocks, int col0,
-                        int mirror_rows) {
+                        const PdMirror mirror) {
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     uint8_t *stage_mem = base;                                             // PD_STAGES x (A | B)
@@ -223,6 +241,18 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
             mbar_wait(&tmem_full[acc], acc_phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int32_t *orow = out + (size_t)(m0 + row_in_tile) * ld + n0;
+            // where the mirror image of this tile goes: the same matrix (one GPU), or the slice of the rank that owns
+            // columns m0.. (sharded: peer memory); nullptr for diagonal macro-tiles and unmirrored builds
+            int32_t *mirror_base = nullptr;
+            size_t mirror_ld = 0;
+            if (mirror.mode == 1) {
+                mirror_base = out + m0;
+                mirror_ld = (size_t)ld;
+            } else if (mirror.mode == 2 && m0 / 256 != (col0 + n0) / 256) {
+                const int w = min(m0 / mirror.per, mirror.world - 1);
+                mirror_base = mirror.out[w] + (m0 - w * mirror.per);
+                mirror_ld = (size_t)mirror.per;
+            }
 #pragma unroll 1
             for (int c = 0; c < PD_BLOCK_N / 32; ++c) {
                 uint32_t r[32];
@@ -236,13 +266,13 @@ pairdist_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const int32_t 
                     o.z = ni + nn[c * 32 + 4 * v + 2] - 2 * __float2int_rn(__uint_as_float(r[4 * v + 2]));
                     o.w = ni + nn[c * 32 + 4 * v + 3] - 2 * __float2int_rn(__uint_as_float(r[4 * v + 3]));
                     __stcs(reinterpret_cast<int4 *>(orow + c * 32) + v, o);
-                    if (mirror_rows) {   // d2 is symmetric: this tile also provides d2[j][i]; the 32 lanes hold 32 consecutive i
-                        const int j = n0 + c * 32 + 4 * v;
-                        int32_t *mcol = out + (size_t)j * ld + (m0 + row_in_tile);
-                        if (j + 0 < mirror_rows) __stcs(mcol, o.x);
-                        if (j + 1 < mirror_rows) __stcs(mcol + ld, o.y);
-                        if (j + 2 < mirror_rows) __stcs(mcol + 2 * (size_t)ld, o.z);
-                        if (j + 3 < mirror_rows) __stcs(mcol + 3 * (size_t)ld, o.w);
+                    if (mirror_base) {   // d2 is symmetric: this tile also provides d2[j][i]; the 32 lanes hold 32 consecutive i
+                        const int j = col0 + n0 + c * 32 + 4 * v;
+                        int32_t *mcol = mirror_base + (size_t)j * mirror_ld + row_in_tile;
+                        if (j + 0 < mirror.rows) __stcs(mcol, o.x);
+                        if (j + 1 < mirror.rows) __stcs(mcol + mirror_ld, o.y);
+                        if (j + 2 < mirror.rows) __stcs(mcol + 2 * (size_t)mirror_ld, o.z);
+                        if (j + 3 < mirror.rows) __stcs(mcol + 3 * (size_t)mirror_ld, o.w);
                     }
                 }
             }
@@ -265,14 +295,15 @@ uint16_t *arena_levels(adsel_handle *h, int w);
 int32_t *arena_norm2(adsel_handle *h, int w);
 
 // Fills the tile list on the device (one thread per group of 16 row-blocks; the build stays enqueue-only).
-__global__ void __launch_bounds__(1024) pd_tile_list_kernel(int2 *__restrict__ tiles, int blocks_m, int blocks_n, int symmetric) {
+__global__ void __launch_bounds__(1024) pd_tile_list_kernel(int2 *__restrict__ tiles, int blocks_m, int blocks_n, int mode, int j0) {
     __shared__ int start[1025];
     const int groups = (blocks_m + PD_GROUP_M - 1) / PD_GROUP_M;
     const int g = threadIdx.x;
     int count = 0;
     if (g < groups) {
         const int first_m = g * PD_GROUP_M, gsz = min(PD_GROUP_M, blocks_m - first_m);
-        for (int mb = first_m; mb < first_m + gsz; ++mb) count += symmetric ? max(0, blocks_n - mb / 2) : blocks_n;
+        for (int mb = first_m; mb < first_m + gsz; ++mb)
+            for (int nb = 0; nb < blocks_n; ++nb) count += pd_tile_wanted(mode, mb, nb, j0) ? 1 : 0;
     }
     start[g + 1] = count;
     __syncthreads();
@@ -286,7 +317,7 @@ __global__ void __launch_bounds__(1024) pd_tile_list_kernel(int2 *__restrict__ t
         int pos = start[g];
         for (int nb = 0; nb < blocks_n; ++nb)
             for (int mb = first_m; mb < first_m + gsz; ++mb)
-                if (!symmetric || nb >= mb / 2) tiles[pos++] = make_int2(mb, nb);
+                if (pd_tile_wanted(mode, mb, nb, j0)) tiles[pos++] = make_int2(mb, nb);
     }
 }
 
@@ -305,9 +336,13 @@ static int get_encode_fn(EncodeTiledFn *fn) {
     return ADSEL_OK;
 }
 
+int32_t *arena_d2(adsel_handle *h, int w);
+
 // d2 [rows_pad, ld] int32 for the columns [col0, col0 + cols) of the pool, from levels bf16 [n, dim] and
 // norm2 int32 [n] (h->desc_levels / h->desc_norm2: own buffers, or the arena's gathered copy when sharded).
-static int pairdist_enqueue(adsel_handle *h, int col0, int cols) {
+// sharded: the slice lives in the arena with the uniform pitch `per` (columns per rank) so that peers can store the
+// mirror images of their tiles into it.
+static int pairdist_enqueue(adsel_handle *h, int col0, int cols, bool sharded) {
     ADSEL_REQUIRE(h->bev_cells > 0 && h->bev_frames > 0 && h->desc_levels,
                   "adsel_pairdist_build: call adsel_bev_build (or adsel_pairdist_set_descriptors) first");
     const int n = h->bev_frames, dim = h->bev_cells;
@@ -315,15 +350,27 @@ static int pairdist_enqueue(adsel_handle *h, int col0, int cols) {
     ADSEL_REQUIRE((long long)dim * 31 * 31 < (1ll << 24), "adsel_pairdist_build: descriptor too long for exact fp32 accumulation");
     const int blocks_m = (n + PD_BLOCK_M - 1) / PD_BLOCK_M, blocks_n = (cols + PD_BLOCK_N - 1) / PD_BLOCK_N;
     const int k_blocks = (dim + PD_BLOCK_K - 1) / PD_BLOCK_K;
-    const int ld = blocks_n * PD_BLOCK_N, rows = blocks_m * PD_BLOCK_M;
+    const int rows = blocks_m * PD_BLOCK_M;
+    const bool peers = sharded && h->world > 1;
+    int per = 0;
+    if (peers) {
+        long long p = ((long long)n + h->world - 1) / h->world;
+        per = (int)((p + 255) / 256 * 256);
+    }
+    const int ld = peers ? per : blocks_n * PD_BLOCK_N;
     h->pd_n = n;
     h->pd_ld = ld;
     h->pd_col0 = col0;
     h->pd_cols = cols;
+    if (peers) {
+        h->d2_p = arena_d2(h, h->rank);
+    } else if (blocks_n > 0) {
+        ADSEL_TRY(h->pd_d2.reserve((size_t)rows * ld));
+        h->d2_p = h->pd_d2.p;
+    }
     if (blocks_n == 0) return ADSEL_OK;   // this rank owns no column (more ranks than 256-frame slices)
-    ADSEL_TRY(h->pd_d2.reserve((size_t)rows * ld));
     // padded norms (zeros beyond n) so the epilogue needs no bounds checks
-    const size_t norm_len = (size_t)max(rows, col0 + ld);
+    const size_t norm_len = (size_t)max(rows, col0 + blocks_n * PD_BLOCK_N);
     ADSEL_TRY(h->pd_norm.reserve(norm_len));
     ADSEL_CUDA(cudaMemsetAsync(h->pd_norm.p, 0, sizeof(int32_t) * norm_len, h->stream));
     ADSEL_CUDA(cudaMemcpyAsync(h->pd_norm.p, h->desc_norm2, sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, h->stream));
@@ -341,27 +388,42 @@ static int pairdist_enqueue(adsel_handle *h, int col0, int cols) {
     ADSEL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
     ADSEL_CUDA(cudaFuncSetAttribute(pairdist_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD_SMEM));
     // Tile list in visiting order: groups of 16 row-blocks so that the ~148 concurrently resident tiles share rows and
-    // columns of X through L2.  A full (not column-sliced) matrix is symmetric: only the tiles that touch the upper
-    // triangle are computed (n_blk >= m_blk / 2 covers every j >= i) and each writes its mirror image as well.
-    const bool symmetric = col0 == 0 && cols == n && !getenv("ADSEL_PAIRDIST_FULL");
+    // columns of X through L2; which tiles are computed and where their mirror images go: see PdMirror.
+    PdMirror mirror;
+    memset(&mirror, 0, sizeof(mirror));
+    mirror.rows = rows;
+    if (!getenv("ADSEL_PAIRDIST_FULL")) {
+        if (peers) {
+            mirror.mode = 2;
+            mirror.per = per;
+            mirror.world = h->world;
+            for (int w = 0; w < h->world; ++w) mirror.out[w] = arena_d2(h, w);
+        } else if (col0 == 0 && cols == n) {
+            mirror.mode = 1;
+        }
+    }
+    const int j0 = col0 / PD_BLOCK_N;
     int n_tiles = 0;
-    for (int mb = 0; mb < blocks_m; ++mb) n_tiles += symmetric ? max(0, blocks_n - mb / 2) : blocks_n;
+    for (int mb = 0; mb < blocks_m; ++mb)
+        for (int nb = 0; nb < blocks_n; ++nb) n_tiles += pd_tile_wanted(mirror.mode, mb, nb, j0) ? 1 : 0;
     ADSEL_TRY(h->pd_tiles.reserve((size_t)blocks_m * blocks_n));
     const int groups = (blocks_m + PD_GROUP_M - 1) / PD_GROUP_M;
     ADSEL_REQUIRE(groups <= 1024, "adsel_pairdist_build: pool too large for the tile list kernel");
-    pd_tile_list_kernel<<<1, 1024, 0, h->stream>>>(h->pd_tiles.p, blocks_m, blocks_n, symmetric ? 1 : 0);   // no host data: enqueue only
+    pd_tile_list_kernel<<<1, 1024, 0, h->stream>>>(h->pd_tiles.p, blocks_m, blocks_n, mirror.mode, j0);   // no host data: enqueue only
     h->launches += 1;
-    const int grid = min(h->num_sms, n_tiles);
-    pairdist_tcgen05_kernel<<<grid, PD_THREADS, PD_SMEM, h->stream>>>(tmap, h->pd_norm.p, h->pd_d2.p, ld, h->pd_tiles.p, n_tiles,
-                                                                      k_blocks, col0, symmetric ? rows : 0);
-    h->launches += 1;
+    if (n_tiles > 0) {
+        const int grid = min(h->num_sms, n_tiles);
+        pairdist_tcgen05_kernel<<<grid, PD_THREADS, PD_SMEM, h->stream>>>(tmap, h->pd_norm.p, h->d2_p, ld, h->pd_tiles.p, n_tiles,
+                                                                          k_blocks, col0, mirror);
+        h->launches += 1;
+    }
     ADSEL_CUDA(cudaGetLastError());
     return ADSEL_OK;
 }
 
 int pairdist_build(adsel_handle *h) {
     ADSEL_TRY(begin_stage(h));
-    ADSEL_TRY(pairdist_enqueue(h, 0, h->bev_frames));
+    ADSEL_TRY(pairdist_enqueue(h, 0, h->bev_frames, false));
     ADSEL_TRY(end_stage(h, 6));
     return ADSEL_OK;
 }
@@ -392,13 +454,13 @@ int pairdist_build_sharded(adsel_handle *h) {
         const int blocks_m = (h->bev_frames + PD_BLOCK_M - 1) / PD_BLOCK_M, blocks_n = (hi - lo + PD_BLOCK_N - 1) / PD_BLOCK_N;
         const int ld = blocks_n * PD_BLOCK_N, rows = blocks_m * PD_BLOCK_M;
         if (blocks_n > 0) {
-            ADSEL_TRY(h->pd_d2.reserve((size_t)rows * ld));
+            if (h->world == 1) ADSEL_TRY(h->pd_d2.reserve((size_t)rows * ld));   // several ranks: the slice lives in the arena
             ADSEL_TRY(h->pd_norm.reserve((size_t)max(rows, lo + ld)));
         }
     }
     ADSEL_CUDA(cudaEventRecord(h->knn_ev[0], h->stream));
     ADSEL_TRY(comm_barrier(h));
-    ADSEL_TRY(pairdist_enqueue(h, lo, hi - lo));
+    ADSEL_TRY(pairdist_enqueue(h, lo, hi - lo, true));
     ADSEL_TRY(comm_barrier(h));
     ADSEL_CUDA(cudaEventRecord(h->knn_ev[1], h->stream));
     h->pd_pending_timing = true;
@@ -687,7 +749,7 @@ static int dense_enqueue(adsel_handle *h, const adsel_select_params *p, const in
     a.ld = h->pd_ld;
     a.col0 = h->pd_col0;
     a.smem_fps = (a.n > 32 * DG_THREADS && (size_t)a.n * sizeof(int) <= 200 * 1024) ? 1 : 0;
-    a.d2 = h->pd_d2.p;
+    a.d2 = h->d2_p;
     a.n_boxes = h->pd_boxes.p;
     a.sampled = h->d_sampled.p;
     a.fps = h->pd_fps.p;
