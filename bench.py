@@ -311,7 +311,13 @@ def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_r
     ms_p = max_over_ranks(sum(pd_ms) / len(pd_ms))
     ms_g = max_over_ranks(sum(g_ms) / len(g_ms))
     gbs_rank = (20.0 * my_pts + (hi - lo) * (16384 * (4 + 2 * w.world) + 4)) / (sum(hist_ms) / len(hist_ms) * 1e-3) / 1e9
-    tf_rank = 2.0 * n_frames * (hi - lo) * 16384 / (sum(pd_ms) / len(pd_ms) * 1e-3) / 1e12
+    # tiles this rank executes: of its 256-wide column blocks J, the diagonal macro-tile, those above it with I + J even
+    # and those below it with I + J odd (csrc/pairdist.cu: PdMirror mode 2); the mirror images go to the owning rank
+    bm, j0, bn = -(-n_frames // 128), lo // 256, -(-(hi - lo) // 256)
+    tiles_done = sum(1 for mb in range(bm) for nb in range(bn)
+                     if (mb // 2 == j0 + nb) or (mb // 2 < j0 + nb and (mb // 2 + j0 + nb) % 2 == 0)
+                     or (mb // 2 > j0 + nb and (mb // 2 + j0 + nb) % 2 == 1))
+    tf_rank = 2.0 * tiles_done * 128 * 256 * 16384 / (sum(pd_ms) / len(pd_ms) * 1e-3) / 1e12
     total = ms_h + ms_p + ms_g
     return {key: {
         "workload": "BevSpatialSelector/budget%d/%d frames x ~300k points sharded over %d GPUs" % (budget, n_frames, w.world),
@@ -319,6 +325,7 @@ def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_r
         "selected_frames": len(sel), "histogram_ms": ms_h, "pairdist_ms_incl_2_barriers": ms_p, "greedy_ms": ms_g,
         "us_per_step": ms_g * 1e3 / max(len(sel), 1), "ms_total": total, "frames_per_s": n_frames / (total * 1e-3),
         "rank0_histogram_GBps": gbs_rank, "rank0_histogram_frac_of_hbm_peak": gbs_rank / peaks["hbm"],
+        "rank0_tiles_computed": tiles_done, "rank0_tiles_of_slice": bm * bn,
         "rank0_tiles_TFLOPs": tf_rank, "rank0_tiles_frac_of_bf16_peak": tf_rank / peaks["bf16"],
         "selected_crc32": __import__("zlib").crc32(np.asarray(sel, dtype=np.int32).tobytes())}}
 
