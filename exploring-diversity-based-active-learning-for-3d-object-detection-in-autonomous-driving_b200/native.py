@@ -155,6 +155,13 @@ def shard_bounds_256(n, world, rank):
     return lo, min(n, lo + per)
 
 
+def bf16_bits(levels) -> np.ndarray:
+    """uint16 bf16 bit patterns of small non-negative integers (exact for 0..256): the descriptor format of
+    ``Handle.pairdist_set_descriptors``."""
+    f = np.asarray(levels, dtype=np.float32)
+    return (f.view(np.uint32) >> 16).astype(np.uint16)
+
+
 def device_count() -> int:
     c = ctypes.c_int(0)
     _check(load().adsel_device_count(ctypes.byref(c)))

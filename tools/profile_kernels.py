@@ -1,10 +1,9 @@
 """Small driver for ncu captures of the two roofline kernels (bev histogram, tcgen05 distance tiles)."""
 import sys
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle')
+sys.path.insert(0, '/root/repo')
 import numpy as np
 import adsel_b200
 from adsel_b200 import native
-import bev_oracle as B
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 768
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 9472
 h = native.Handle(0)
@@ -17,7 +16,7 @@ print("bev ms", h.stage_ms()["bev_histogram"], "GB/s", off[-1] * 20 / h.stage_ms
 rng = np.random.default_rng(0)
 lv = rng.integers(0, 20, size=(N, 16384), dtype=np.int64)
 lv[rng.random((N, 16384)) < 0.7] = 0
-h.pairdist_set_descriptors(B.bf16_bits(lv))
+h.pairdist_set_descriptors(native.bf16_bits(lv))
 for it in range(3):
     h.pairdist_build()
 ms = h.stage_ms()["pairdist"]
