@@ -15,6 +15,7 @@ from adsel_b200 import native, sharded
 
 class FakeShardHandle:
     instances = []
+    overflow_once = False      # tests: the first select of every handle reports a neighbour-list overflow
 
     def __init__(self, device=0):
         self.device, self.n, self.k = device, 0, 0
@@ -99,6 +100,10 @@ class FakeShardHandle:
         return sharded.pick_global_best(records)[1]
 
     def select_sharded_end(self):
+        if FakeShardHandle.overflow_once and not getattr(self, "_overflowed", False):
+            self._overflowed = True                              # like the device: rank 0 overflows, the others see its abort
+            dist.barrier()
+            raise native.RetrySharded(native.ERR_CAPACITY if self.rank == 0 else native.ERR_PEER_ABORT, "neighbour-list pool too small")
         kw = self.pending
         lo, hi = self.shard_range()
         sampled = list(kw.get("sampled", ()))
@@ -129,4 +134,4 @@ class FakeShardHandle:
         return {}
 
     def counters(self):
-        return {"launches": 0}
+        return {"launches": 0, "list_entries": 1000 + 10 * self.rank}

@@ -74,6 +74,19 @@ def _worker(rank, world, init_file, pool_dir, out_dir):
         result["temporal"], _ = w.select(spatial="none", temporal=True, normalize="raw", forbid_sampled=True, cost_b=0.04,
                                          cost_f=0.12, cost_start=0, budget=100, first_index=first)
         result["range"] = list(w.shard_range())
+
+        # 3. a neighbour-list overflow is retried collectively: arenas re-created for the largest need, graph rebuilt
+        fake_native.FakeShardHandle.overflow_once = True
+        w2 = sharded.DistWorld(rank)
+        loc = pool.ego_locations(infos)
+        run_id, _ = pool.consecutive_runs(pool.logfile_names(infos))
+        w2.set_pool(loc, run_id, pool.box_counts(infos))
+        w2.build_knn_graph(8)
+        result["retry"], _ = w2.select(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0,
+                                       cost_b=0.04, cost_f=0.12, cost_start=0, budget=50, first_index=first)
+        result["retry_calls"] = [c if isinstance(c, str) else c[0] for c in w2.handle.calls]
+        result["retry_list_cap"] = w2._list_cap
+        fake_native.FakeShardHandle.overflow_once = False
         json.dump(result, open(os.path.join(out_dir, f"rank{rank}.json"), "w"))
         dist.barrier()
         dist.destroy_process_group()
@@ -98,5 +111,9 @@ def test_two_ranks_select_like_the_reference_and_only_rank0_writes(pools, tmp_pa
         assert r["engine"] == "DistWorld"
         assert r["handle_calls"].count("comm_init") == 1                      # engine (arena, peer mappings) reused across rounds
     assert r0["range"] == [0, 256] and r1["range"] == [256, 300]
+    for r in (r0, r1):
+        assert r["retry"] == want["50"]                                      # same selection after the collective retry
+        assert r["retry_calls"].count("comm_init") == 2                       # arenas re-created once ...
+        assert r["retry_list_cap"] == int(1010 * 1.1) + 1024                  # ... sized for the largest need over the ranks
     assert json.load(open(os.path.join(out_dir, "buffer.json"))) == {"0": [], "50": want["50"], "100": want["100"]}
     assert os.path.exists(pl["paths"]["infos"].replace(".pkl", "_100.pkl"))
