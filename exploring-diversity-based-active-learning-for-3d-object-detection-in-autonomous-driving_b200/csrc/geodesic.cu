@@ -221,10 +221,10 @@ geodesic_lists_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__rest
 static int ensure_scratch(adsel_handle *h) {
     // Searches in flight per SM.  A search is a chain of dependent L2 round trips, so the kernel is latency-bound and
     // scales with concurrency (measured at P28K: 4 / 8 / 12 / 16 CTAs per SM -> 0.91 / 0.53 / 0.40 / 0.37 ms); every
-    // resident CTA needs 24 N bytes of scratch, so the default of 16 is lowered for very large pools (<= 16 GB).
+    // resident CTA needs 24 N bytes of scratch, so the default of 16 is lowered for very large pools (<= 4 GB of scratch per handle).
     const char *e = getenv("ADSEL_SSSP_CTAS_PER_SM");
     int per_sm = 16;
-    const long long fit = 16000000000ll / ((long long)h->num_sms * 24ll * (h->n > 0 ? h->n : 1));
+    const long long fit = 4000000000ll / ((long long)h->num_sms * 24ll * (h->n > 0 ? h->n : 1));
     if (fit < per_sm) per_sm = fit < 4 ? 4 : (int)fit;
     if (e && atoi(e) > 0) per_sm = atoi(e);
     const int ctas = h->num_sms * per_sm;
