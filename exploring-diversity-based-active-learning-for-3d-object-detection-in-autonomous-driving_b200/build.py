@@ -80,8 +80,16 @@ def build_hostext(force: bool = False):
         if not force and os.path.exists(HOSTEXT) and os.path.getmtime(HOSTEXT) >= os.path.getmtime(src):
             return HOSTEXT
         tmp = f"{HOSTEXT}.tmp{os.getpid()}"
+        flags = []
+        try:                                  # numpy's headers allow reading ndarray fields without the buffer protocol
+            import numpy
+            npinc = numpy.get_include()
+            if os.path.exists(os.path.join(npinc, "numpy", "ndarraytypes.h")):
+                flags = [f"-I{npinc}", "-DADSEL_HAVE_NUMPY_HEADERS"]
+        except Exception:
+            pass
         try:
-            subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", f"-I{inc}", src, "-o", tmp, "-lm"])
+            subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", f"-I{inc}"] + flags + [src, "-o", tmp, "-lm"])
             os.replace(tmp, HOSTEXT)
         finally:
             if os.path.exists(tmp):

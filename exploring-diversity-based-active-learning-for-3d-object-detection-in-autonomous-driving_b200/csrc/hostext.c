@@ -19,6 +19,27 @@
 #include <stdint.h>
 #include <string.h>
 
+#ifdef ADSEL_HAVE_NUMPY_HEADERS
+/* Direct access to the fields of a numpy.ndarray (data, shape, strides, dtype number): the buffer protocol costs
+ * more than everything else this function does per frame.  Only exact ``numpy.ndarray`` instances take this path, it
+ * is validated against the buffer protocol on the first array it sees, and pool.py checks the resulting ego
+ * locations against the reference expression before trusting the helper at all. */
+#define NPY_NO_DEPRECATED_API NPY_1_7_API_VERSION
+#include <numpy/ndarraytypes.h>
+static int g_fast = -1; /* -1 not validated yet, 0 disabled, 1 enabled */
+static int is_exact_ndarray(PyObject *o) { return strcmp(Py_TYPE(o)->tp_name, "numpy.ndarray") == 0; }
+static int read_cal_fields(PyObject *cal, double m[4][4]) {
+    const PyArrayObject_fields *a = (const PyArrayObject_fields *)cal;
+    if (a->nd != 2 || a->dimensions[0] < 3 || a->dimensions[1] < 4) return -1;
+    const PyArray_Descr *d = a->descr;
+    if (d->type_num != NPY_DOUBLE || d->byteorder == '>') return -1;
+    const char *base = a->data;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j) memcpy(&m[i][j], base + i * a->strides[0] + j * a->strides[1], 8);
+    return 0;
+}
+#endif
+
 static int read_cal(PyObject *cal, double m[4][4]) {
     Py_buffer view;
     if (PyObject_GetBuffer(cal, &view, PyBUF_STRIDES | PyBUF_FORMAT) != 0) return -1;
@@ -98,14 +119,38 @@ static PyObject *extract(PyObject *self, PyObject *args) {
             goto fail;
         }
         double c[4][4];
+#ifdef ADSEL_HAVE_NUMPY_HEADERS
+        int done = 0;
+        if (g_fast != 0 && is_exact_ndarray(cal)) {
+            if (g_fast < 0) { /* first array: the field access must agree with the buffer protocol */
+                double ref[4][4];
+                memset(ref, 0, sizeof(ref));
+                memset(c, 0, sizeof(c));
+                if (read_cal(cal, ref) != 0) goto fail;
+                g_fast = (read_cal_fields(cal, c) == 0 && memcmp(ref, c, sizeof(double) * 12) == 0) ? 1 : 0;
+                memcpy(c, ref, sizeof(ref));
+                done = 1;
+            } else if (read_cal_fields(cal, c) == 0) {
+                done = 1;
+            }
+        }
+        if (!done && read_cal(cal, c) != 0) goto fail;
+#else
         if (read_cal(cal, c) != 0) goto fail;
+#endif
         for (int j = 0; j < 2; ++j) {
             double v;
             if (fused) v = fma(c[2][3], c[2][j], fma(c[1][3], c[1][j], c[0][3] * c[0][j]));
             else v = (c[0][3] * c[0][j] + c[1][3] * c[1][j]) + c[2][3] * c[2][j];
             loc[2 * i + j] = -v;
         }
-        const Py_ssize_t nb = PyObject_Length(gt);
+        Py_ssize_t nb;
+#ifdef ADSEL_HAVE_NUMPY_HEADERS
+        if (g_fast == 1 && is_exact_ndarray(gt) && ((const PyArrayObject_fields *)gt)->nd >= 1)
+            nb = ((const PyArrayObject_fields *)gt)->dimensions[0];
+        else
+#endif
+            nb = PyObject_Length(gt);
         if (nb < 0) goto fail;
         box[i] = (int32_t)nb;
         /* same "<dir>/<name>__" prefix as the previous frame and no further "/": the name is the previous one */
