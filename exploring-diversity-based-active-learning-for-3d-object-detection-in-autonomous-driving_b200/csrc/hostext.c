@@ -7,7 +7,10 @@
  * its python implementation when this module is not built, and checks the ego locations of a probe of frames
  * bit-for-bit against the reference's literal numpy expression before trusting them.
  *
- *   extract(infos, lo, hi, fused) -> (loc: bytes f64[m,2], boxes: bytes i32[m], names: list[str])
+ *   extract(infos, lo, hi, fused) -> (loc: bytes f64[m,2], boxes: bytes i32[m], names: list[str], change: bytes u8[m])
+ *
+ * change[i] = 1 when names[i] != names[i-1] (change[0] = 1): the consecutive-run boundaries of
+ * spatial_temporal_selector.py:114-129, found while the names are parsed.
  *
  * loc[j] = -(t0*R0j + t1*R1j + t2*R2j) with t = cal[:3,3], R = cal[:3,:3], evaluated in index order either with
  * fused multiply-adds (what numpy's vector-matrix product does on FMA hosts) or with separately rounded
@@ -98,12 +101,15 @@ static PyObject *extract(PyObject *self, PyObject *args) {
     }
     const Py_ssize_t m = hi - lo;
     PyObject *loc_b = PyBytes_FromStringAndSize(NULL, m * 16), *box_b = PyBytes_FromStringAndSize(NULL, m * 4);
+    PyObject *chg_b = PyBytes_FromStringAndSize(NULL, m);
     PyObject *names = PyList_New(m);
     PyObject *k_cal = PyUnicode_InternFromString("car_from_global"), *k_path = PyUnicode_InternFromString("cam_front_path"),
              *k_gt = PyUnicode_InternFromString("gt_names");
-    if (!loc_b || !box_b || !names || !k_cal || !k_path || !k_gt) goto fail;
+    if (!loc_b || !box_b || !chg_b || !names || !k_cal || !k_path || !k_gt) goto fail;
     double *loc = (double *)PyBytes_AS_STRING(loc_b);
     int32_t *box = (int32_t *)PyBytes_AS_STRING(box_b);
+    unsigned char *chg = (unsigned char *)PyBytes_AS_STRING(chg_b);
+    PyObject *last_name = NULL; /* names[i-1], borrowed from the list */
     PyObject *prev_name = NULL, *prev_path = NULL;
     Py_ssize_t prev_prefix = 0; /* length of "<dir>/<name>__" in prev_path */
     for (Py_ssize_t i = 0; i < m; ++i) {
@@ -191,15 +197,29 @@ static PyObject *extract(PyObject *self, PyObject *args) {
                 prev_name = NULL;
             }
         }
+        if (last_name == NULL) {
+            chg[i] = 1;
+        } else if (name == last_name) {
+            chg[i] = 0;
+        } else {
+            const int cmp = PyUnicode_Compare(name, last_name);
+            if (cmp == -1 && PyErr_Occurred()) {
+                Py_DECREF(name);
+                goto fail;
+            }
+            chg[i] = cmp != 0;
+        }
+        last_name = name;
         PyList_SET_ITEM(names, i, name);
     }
     Py_DECREF(k_cal);
     Py_DECREF(k_path);
     Py_DECREF(k_gt);
-    return Py_BuildValue("(NNN)", loc_b, box_b, names);
+    return Py_BuildValue("(NNNN)", loc_b, box_b, names, chg_b);
 fail:
     Py_XDECREF(loc_b);
     Py_XDECREF(box_b);
+    Py_XDECREF(chg_b);
     Py_XDECREF(names);
     Py_XDECREF(k_cal);
     Py_XDECREF(k_path);

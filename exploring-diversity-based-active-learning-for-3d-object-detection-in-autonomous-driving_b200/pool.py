@@ -124,7 +124,24 @@ def _hostext():
     return _HOSTEXT
 
 
-def extract_slice(infos, lo=0, hi=None, check: int = 64):
+def _change_flags(names) -> np.ndarray:
+    """bool [m]: names[i] != names[i-1] (first entry True) -- the consecutive-run boundaries (:114-129)."""
+    arr = np.asarray(names, dtype=object)
+    change = np.ones(len(names), dtype=bool)
+    change[1:] = arr[1:] != arr[:-1]
+    return change
+
+
+def runs_from_change(change):
+    """``(run_id int32 [m], max_temporal_distance)`` from run-boundary flags, as ``consecutive_runs`` defines them."""
+    run_id = (np.cumsum(change) - 1).astype(np.int32)
+    starts = np.flatnonzero(change)
+    lengths = np.diff(np.append(starts, len(change)))
+    max_td = int(lengths[:-1].max()) if len(lengths) > 1 else 0
+    return run_id, max_td
+
+
+def extract_slice(infos, lo=0, hi=None, check: int = 64, with_change: bool = False):
     """``(names, locations, n_boxes)`` of ``infos[lo:hi]`` -- logfile_names / ego_locations / box_counts in one pass
     over the list, in C when the helper is built.  The helper's ego locations are compared bit-for-bit with the
     reference's literal expression on ``check`` probe frames (numpy's vector-matrix product uses fused
@@ -137,14 +154,17 @@ def extract_slice(infos, lo=0, hi=None, check: int = 64):
         try:
             want = _location_loop([infos[i]["car_from_global"] for i in probe]).view(np.uint64)
             for fused in (True, False):
-                loc_b, box_b, names = ext.extract(infos, lo, hi, fused)
+                loc_b, box_b, names, chg_b = ext.extract(infos, lo, hi, fused)
                 loc = np.frombuffer(loc_b, dtype=np.float64).reshape(-1, 2)
                 if np.array_equal(loc[probe - lo].view(np.uint64), want):
-                    return names, loc, np.frombuffer(box_b, dtype=np.int32)
+                    out = (names, loc, np.frombuffer(box_b, dtype=np.int32))
+                    return out + (np.frombuffer(chg_b, dtype=np.uint8).astype(bool),) if with_change else out
         except (TypeError, KeyError, ValueError):
             pass
     part = infos[lo:hi]
-    return logfile_names(part), ego_locations(part, check), box_counts(part)
+    names = logfile_names(part)
+    out = (names, ego_locations(part, check), box_counts(part))
+    return out + (_change_flags(names),) if with_change else out
 
 
 def extract_spatial_temporal(infos, known_logfiles=None):
@@ -162,24 +182,21 @@ def extract_spatial_temporal(infos, known_logfiles=None):
     rank, world = get_dist_info()
     n = len(infos)
     if world <= 1 or n < 4 * world:
-        names, loc, boxes = extract_slice(infos)
+        names, loc, boxes, change = extract_slice(infos, with_change=True)
         if known_logfiles is not None:
-            for nm in names:
-                if nm not in known_logfiles:
-                    raise KeyError(nm)
-        run_id, max_td = consecutive_runs(names)
+            for i in np.flatnonzero(change):            # every distinct consecutive name, in order (KeyError like :80)
+                if names[i] not in known_logfiles:
+                    raise KeyError(names[i])
+        run_id, max_td = runs_from_change(change)
         return loc, run_id, max_td, boxes
     import time
     import torch.distributed as dist
     t0 = time.perf_counter()
     lo, hi = rank * n // world, (rank + 1) * n // world
-    names, loc_mine, boxes_mine = extract_slice(infos, lo, hi)
-    missing = None
+    names, loc_mine, boxes_mine, change = extract_slice(infos, lo, hi, with_change=True)
+    missing = None                                      # change[0] is fixed up against the previous slice's last name
     if known_logfiles is not None:
-        missing = next((nm for nm in names if nm not in known_logfiles), None)
-    arr = np.asarray(names, dtype=object)
-    change = np.ones(len(names), dtype=bool)            # change[0] is fixed up against the previous slice's last name
-    change[1:] = arr[1:] != arr[:-1]
+        missing = next((names[i] for i in np.flatnonzero(change) if names[i] not in known_logfiles), None)
     mine = {"lo": lo, "missing": missing, "first": names[0], "last": names[-1], "change": np.packbits(change),
             "n": len(names), "loc": loc_mine, "boxes": boxes_mine}
     t1 = time.perf_counter()
