@@ -112,16 +112,70 @@ static PyObject *extract(PyObject *self, PyObject *args) {
     PyObject *last_name = NULL; /* names[i-1], borrowed from the list */
     PyObject *prev_name = NULL, *prev_path = NULL;
     Py_ssize_t prev_prefix = 0; /* length of "<dir>/<name>__" in prev_path */
-    for (Py_ssize_t i = 0; i < m; ++i) {
+    /* The infos of a freshly unpickled pool are cold: a frame costs ~8 dependent cache misses (dict, its key table,
+     * the three value objects, the matrix data, the shape/stride blocks).  The loop is therefore software-pipelined
+     * with prefetches: the dict of frame i+12, the key table of frame i+8, the value objects of frame i+4 (their
+     * lookups are done then and kept in a small ring), the matrix data and shape blocks of frame i+2. */
+    enum { RING = 16, D_DICT = 12, D_KEYS = 8, D_VALS = 4, D_DATA = 2 };
+    PyObject *r_cal[RING], *r_path[RING], *r_gt[RING];
+    for (Py_ssize_t s = -D_DICT; s < m; ++s) {
+        if (s + D_DICT < m) __builtin_prefetch(PyList_GET_ITEM(infos, lo + s + D_DICT));
+        if (s + D_KEYS >= 0 && s + D_KEYS < m) {
+            PyObject *d = PyList_GET_ITEM(infos, lo + s + D_KEYS);
+            if (PyDict_Check(d)) {
+                const char *keys = (const char *)((PyDictObject *)d)->ma_keys;
+                __builtin_prefetch(keys);
+                __builtin_prefetch(keys + 64);
+                __builtin_prefetch(keys + 128);
+                __builtin_prefetch(keys + 192);
+                __builtin_prefetch(keys + 256);
+            }
+        }
+        if (s + D_VALS >= 0 && s + D_VALS < m) {
+            const Py_ssize_t q = s + D_VALS;
+            PyObject *d = PyList_GET_ITEM(infos, lo + q);
+            PyObject *vc = NULL, *vp = NULL, *vg = NULL;
+            if (PyDict_Check(d)) {
+                vc = PyDict_GetItemWithError(d, k_cal);
+                vp = PyDict_GetItemWithError(d, k_path);
+                vg = PyDict_GetItemWithError(d, k_gt);
+                if (PyErr_Occurred()) goto fail;
+                if (vc) {
+                    __builtin_prefetch(vc);
+                    __builtin_prefetch((const char *)vc + 64);
+                }
+                if (vp) {
+                    __builtin_prefetch(vp);
+                    __builtin_prefetch((const char *)vp + 64);
+                }
+                if (vg) __builtin_prefetch(vg);
+            }
+            r_cal[q % RING] = vc;
+            r_path[q % RING] = vp;
+            r_gt[q % RING] = vg;
+        }
+#ifdef ADSEL_HAVE_NUMPY_HEADERS
+        if (g_fast == 1 && s + D_DATA >= 0 && s + D_DATA < m) {
+            PyObject *vc = r_cal[(s + D_DATA) % RING], *vg = r_gt[(s + D_DATA) % RING];
+            if (vc && is_exact_ndarray(vc)) {
+                const PyArrayObject_fields *a = (const PyArrayObject_fields *)vc;
+                __builtin_prefetch(a->data);
+                __builtin_prefetch(a->data + 64);
+                __builtin_prefetch(a->dimensions);
+            }
+            if (vg && is_exact_ndarray(vg)) __builtin_prefetch(((const PyArrayObject_fields *)vg)->dimensions);
+        }
+#endif
+        if (s < 0) continue;
+        const Py_ssize_t i = s;
         PyObject *info = PyList_GET_ITEM(infos, lo + i);
         if (!PyDict_Check(info)) {
             PyErr_SetString(PyExc_TypeError, "infos entries must be dicts");
             goto fail;
         }
-        PyObject *cal = PyDict_GetItemWithError(info, k_cal), *path = PyDict_GetItemWithError(info, k_path),
-                 *gt = PyDict_GetItemWithError(info, k_gt);
+        PyObject *cal = r_cal[i % RING], *path = r_path[i % RING], *gt = r_gt[i % RING];
         if (!cal || !path || !gt) {
-            if (!PyErr_Occurred()) PyErr_SetObject(PyExc_KeyError, !cal ? k_cal : !path ? k_path : k_gt);
+            PyErr_SetObject(PyExc_KeyError, !cal ? k_cal : !path ? k_path : k_gt);
             goto fail;
         }
         double c[4][4];
