@@ -114,9 +114,9 @@ static PyObject *extract(PyObject *self, PyObject *args) {
     Py_ssize_t prev_prefix = 0; /* length of "<dir>/<name>__" in prev_path */
     /* The infos of a freshly unpickled pool are cold: a frame costs ~8 dependent cache misses (dict, its key table,
      * the three value objects, the matrix data, the shape/stride blocks).  The loop is therefore software-pipelined
-     * with prefetches: the dict of frame i+12, the key table of frame i+8, the value objects of frame i+4 (their
-     * lookups are done then and kept in a small ring), the matrix data and shape blocks of frame i+2. */
-    enum { RING = 16, D_DICT = 12, D_KEYS = 8, D_VALS = 4, D_DATA = 2 };
+     * with prefetches: the dict of frame i+24, the key table of frame i+16, the value objects of frame i+8 (their
+     * lookups are done then and kept in a small ring), the matrix data and shape blocks of frame i+4. */
+    enum { RING = 32, D_DICT = 24, D_KEYS = 16, D_VALS = 8, D_DATA = 4 };
     PyObject *r_cal[RING], *r_path[RING], *r_gt[RING];
     for (Py_ssize_t s = -D_DICT; s < m; ++s) {
         if (s + D_DICT < m) __builtin_prefetch(PyList_GET_ITEM(infos, lo + s + D_DICT));
