@@ -218,3 +218,19 @@ def test_c_host_helper_equals_the_python_extraction(pools, monkeypatch):
     _, loc32, _ = P.extract_slice(adv32)
     assert np.array_equal(loc32.astype(np.float64), np.stack([(-(a["car_from_global"][:3, 3].T @ a["car_from_global"][:3, :3]))[:2]
                                                                for a in adv32]).astype(np.float64))
+
+
+def test_runs_from_change_equals_consecutive_runs():
+    """pool.runs_from_change (used with the C helper's boundary flags) == pool.consecutive_runs on random name lists,
+    including a single run, all-distinct names and a trailing one-frame run (max_td ignores the LAST run, :127-129)."""
+    from adsel_b200 import pool as P
+    rng = np.random.default_rng(4)
+    cases = [["a"] * 7, list("abcdef"), ["a", "a", "b"], ["a"], ["x", "y", "y", "y", "x", "x"]]
+    for _ in range(20):
+        cases.append([f"L{int(v)}" for v in np.repeat(rng.integers(0, 5, size=12), rng.integers(1, 6, size=12))])
+    for names in cases:
+        want_id, want_td = P.consecutive_runs(names)
+        got_id, got_td = P.runs_from_change(P._change_flags(names))
+        assert np.array_equal(got_id, want_id) and got_td == want_td, names
+        oracle_id, oracle_td = R.consecutive_runs([{"cam_front_path": f"d/{nm}__x"} for nm in names])
+        assert np.array_equal(got_id, oracle_id) and got_td == oracle_td
