@@ -8,6 +8,7 @@ from typing import Optional
 
 from ..dist import master_only
 from ..fileio import dump, load
+from . import budget_buffer as bb
 from .registry import SELECTORS
 
 
@@ -23,24 +24,32 @@ class BaseSelector(object):
                  infos_origin="", detector=None, dataloader=None, logger: Optional[logging.Logger] = None,
                  pred: bool = False, cost_b: float = 0.04, cost_f: float = 0.12) -> None:
         super().__init__()
-        self.budget = budget
+        # files: the buffer is re-written in place unless a separate dump name is given (:33)
         self.buffer_file = buffer_file
         self.dump_file_name = buffer_file if dump_file_name is None else dump_file_name
-        self.buffer = load(buffer_file)                 # {"0": [], "<cumulative budget>": [idx, ...]}
-        self.detector = detector
-        self.dataloader = dataloader
-        self.selected_index = {}
         self.infos_file = infos_origin
-        self.infos_origin = load(infos_origin)          # list[dict], whole pool in RAM (base_selector.py:39)
-        self.current_budget = str(self.budget + int(self.get_max_key()))
+        self.buffer = load(buffer_file)                 # {"0": [], "<cumulative budget>": [idx, ...]}
+        self.infos_origin = load(infos_origin)          # list[dict], whole pool in RAM (:39)
+        # budget: ``budget`` more cost units on top of the latest round (:40)
+        self.budget = budget
+        self.cost_b, self.cost_f = cost_b, cost_f
+        self.current_budget = bb.next_key(self.buffer, budget)
+        self.selected_index = {}
+        # carried for the caller, untouched by the data-only selectors
+        self.detector, self.dataloader, self.pred = detector, dataloader, pred
         self.logger = logger if logger is not None else logging.getLogger(__file__)
-        self.pred = pred
-        self.cost_b = cost_b
-        self.cost_f = cost_f
         self.last_stats = {}
 
+    # -- reference API ------------------------------------------------------------------------
     def get_max_key(self):
-        return str(max(int(key) for key in self.buffer.keys()))
+        return bb.latest_key(self.buffer)
+
+    def get_selected_samples(self):
+        return self.selected_index
+
+    def get_cost_amount(self):
+        """Annotation cost of the frames already in the buffer (:78-86)."""
+        return bb.annotation_cost(self.infos_origin, self.buffer[self.get_max_key()], self.cost_f, self.cost_b)
 
     def select_samples(self, **kwargs) -> None:
         return
@@ -51,23 +60,10 @@ class BaseSelector(object):
         self.buffer.update(self.selected_index)
         dump(self.buffer, self.dump_file_name)
         self.logger.info(f"update the buffer, and save as {self.dump_file_name}")
-        ext = os.path.splitext(self.infos_file)[-1]
-        replace_path = self.infos_file.replace(ext, f"_{self.current_budget}{ext}")
-        infos_sampled = [self.infos_origin[i] for i in self.buffer[str(self.current_budget)]]
-        dump(infos_sampled, replace_path)
-        self.logger.info(f"sample the {self.current_budget} infos and save as {replace_path}")
-
-    def get_selected_samples(self):
-        return self.selected_index
-
-    def get_cost_amount(self):
-        """Annotation cost of the frames already in the buffer, accumulated in the reference's order (:78-86)."""
-        cost = 0
-        sampled_frames = [self.infos_origin[i] for i in self.buffer[self.get_max_key()]]
-        cost += self.cost_f * len(sampled_frames)
-        for anno in sampled_frames:
-            cost += anno["gt_names"].shape[0] * self.cost_b
-        return cost
+        key = str(self.current_budget)
+        out_path = bb.subset_path(self.infos_file, key)
+        dump([self.infos_origin[i] for i in self.buffer[key]], out_path)
+        self.logger.info(f"sample the {key} infos and save as {out_path}")
 
     # -- shared by the diversity selectors ---------------------------------------------------
     @staticmethod

@@ -234,3 +234,21 @@ def test_runs_from_change_equals_consecutive_runs():
         assert np.array_equal(got_id, want_id) and got_td == want_td, names
         oracle_id, oracle_td = R.consecutive_runs([{"cam_front_path": f"d/{nm}__x"} for nm in names])
         assert np.array_equal(got_id, oracle_id) and got_td == oracle_td
+
+
+def test_budget_buffer_helpers():
+    """Pure bookkeeping helpers behind BaseSelector (base_selector.py:40,47-49,69-70,78-86)."""
+    from adsel_b200.selectors import budget_buffer as bb
+    buf = {"0": [], "600": [3, 1], "1200": [3, 1, 7]}
+    assert bb.latest_key(buf) == "1200"                 # numeric, not lexicographic ("600" > "1200" as strings)
+    assert bb.next_key(buf, 4800) == "6000"
+    assert bb.next_key({"0": []}, 2400) == "2400"
+    assert bb.subset_path("/d/infos_train.pkl", "600") == "/d/infos_train_600.pkl"
+    assert bb.subset_path("/d/a.pkl/b.pkl", "5") == "/d/a_5.pkl/b_5.pkl"       # str.replace rule of the reference
+    infos = [{"gt_names": np.empty(n, dtype="<U3")} for n in (4, 0, 9, 2)]
+    want = 0
+    want += 0.12 * 3
+    for n in (2, 4, 9):
+        want += n * 0.04
+    assert bb.annotation_cost(infos, [3, 0, 2], 0.12, 0.04) == want
+    assert bb.annotation_cost(infos, [], 0.12, 0.04) == 0
