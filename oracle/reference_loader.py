@@ -72,12 +72,14 @@ def load_reference_selectors():
     from det3d.selectors.spatial_selector import SpatialSelector
     from det3d.selectors.temporal_selector import TemporalSelector
     from det3d.selectors.euclidean_spatial_selector import EuSpatialSelector
+    from det3d.selectors.random_selector import RandomSelector
 
     out = {
         "SpatialTemporalSelector": SpatialTemporalSelector,
         "SpatialSelector": SpatialSelector,
         "TemporalSelector": TemporalSelector,
         "EuSpatialSelector": EuSpatialSelector,
+        "RandomSelector": RandomSelector,
     }
     try:
         # feature_selector.py imports ``example_to_device`` from det3d.torchie.apis.train, which pulls in the whole

@@ -252,3 +252,30 @@ def test_budget_buffer_helpers():
         want += n * 0.04
     assert bb.annotation_cost(infos, [3, 0, 2], 0.12, 0.04) == want
     assert bb.annotation_cost(infos, [], 0.12, 0.04) == 0
+
+
+def test_random_selector_equals_the_reference(pools, tmp_path):
+    """RandomSelector consumes python's RNG exactly like the reference (random_selector.py:40-66): golden made by
+    oracle/make_goldens.py --pool P2K --only random from the unmodified class."""
+    import random
+    from conftest import load_golden
+    g = load_golden("P2K_random.json")
+    pl = pools("P2K")
+    for cid, case in g["cases"].items():
+        buf = str(tmp_path / f"{cid}.json")
+        fileio.dump({"0": []}, buf, indent=4)
+        got = {}
+        for budget in case["rounds"]:
+            random.seed(3407)
+            sel = build_selector(dict(type="RandomSelector", budget=budget, buffer_file=buf,
+                                      infos_origin=pl["paths"]["infos"], **case["kwargs"]))
+            sel.select_samples(local_rank=0)
+            got.update(sel.get_selected_samples())
+            sel.dump_file()
+        assert got == case["selected_index"], cid
+    # an exhausted pool ends in the same IndexError random.choice raises in the reference
+    buf = str(tmp_path / "exhaust.json")
+    fileio.dump({"0": []}, buf)
+    sel = build_selector(dict(type="RandomSelector", budget=10 ** 7, buffer_file=buf, infos_origin=pl["paths"]["infos"]))
+    with pytest.raises(IndexError):
+        sel.select_samples()
