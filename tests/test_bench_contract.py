@@ -32,3 +32,22 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_profiled_traffic_table_names_kernels_of_this_library():
+    """profiles/traffic.json (ncu dram bytes per launch) feeds roofline.traffic: every entry must name a kernel that
+    exists in csrc/ and carry a byte count and the capture it came from."""
+    import glob
+    sys.path.insert(0, ROOT)
+    import bench
+    table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    src = "".join(open(p).read() for p in glob.glob(os.path.join(ROOT, "exploring*", "csrc", "*.cu")))
+    lookup = bench.profiled_traffic()
+    for kernel, entry in table.items():
+        if kernel.startswith("_"):
+            continue
+        assert kernel in src or kernel.replace("_kernel", "_tma_kernel") in src, kernel
+        got = lookup(kernel)
+        assert got["traffic"] == entry["bytes"] > 0 and got["traffic_launch"].split(":")[0].endswith(".csv")
+        assert os.path.exists(os.path.join(ROOT, "profiles", got["traffic_launch"].split(":")[0]))
+    assert lookup("no_such_kernel") == {"traffic": None}
