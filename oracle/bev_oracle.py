@@ -1,10 +1,12 @@
 """oracle/bev_oracle.py -- TEST INFRASTRUCTURE ONLY.
 
-CPU restatement of the BEV density descriptor (north_star kernel 1).  PARITY UNPINNED BY THE
-REFERENCE: no selector of the reference computes a LiDAR descriptor.  The
-binning follows the reference's numba BEV map, det3d/ops/point_cloud/bev_ops.py:27-53, whose
-semantics are restated here on the numba-free numpy path and checked against a literal pure-Python
-transcription of that loop on small inputs (tests/test_oracle_bev.py):
+CPU restatement of the BEV density descriptor (north_star kernel 1).  No selector of the reference computes a
+LiDAR descriptor, so the DESCRIPTOR (density levels, distances, what gets selected from
+them) is PARITY UNPINNED BY THE REFERENCE.  The BINNING is pinned: it follows the reference's numba BEV map,
+det3d/ops/point_cloud/bev_ops.py:27-53, and ``bev_counts`` is checked cell for cell against the count channel
+``bev_map[-1]`` of the unmodified ``points_to_bev`` run in this container (tests/golden/bev_counts.json, made by
+oracle/make_golden_bev.py) and against a literal pure-Python transcription of that loop on small inputs
+(tests/test_oracle_bev.py):
 
   grid = round((hi - lo) / voxel)                     (:27-30, float32)
   c_j  = floor((p_j - lo_j) / voxel_j), j = x,y,z     (:37, float32 subtract and TRUE division)

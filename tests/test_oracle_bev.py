@@ -36,3 +36,31 @@ def test_sq_distance_matrix_is_exact_integer():
     d = B.sq_distance_matrix(a, a)
     assert np.array_equal(d, ((a[:, None, :] - a[None, :, :]) ** 2).sum(-1))
     assert np.all(np.diag(d) == 0)
+
+
+def golden_frames():
+    """(case id, voxel, frame number, points float32 [m,4], golden count vector) for every frame of
+    tests/golden/bev_counts.json -- the reference's own ``points_to_bev`` count channel (oracle/make_golden_bev.py)."""
+    from conftest import load_golden
+    import make_golden_bev as G
+    g = load_golden("bev_counts.json")
+    assert tuple(g["range"]) == B.NUSC_RANGE
+    for case, rec in g["cases"].items():
+        for f, fr in enumerate(rec["frames"]):
+            pts = G.case_points(case, f, rec["n_points"])
+            assert len(pts) == fr["n_points"]
+            want = np.zeros(fr["shape"][0] * fr["shape"][1], dtype=np.int32)
+            want[np.asarray(fr["cells"], dtype=np.int64)] = fr["counts"]
+            assert want.sum() == fr["inside"]
+            yield case, tuple(rec["voxel"]), f, pts, want
+
+
+def test_counts_equal_the_reference_bev_map():
+    """Pins the binning (float32 subtract / divide / floor, half-open bounds, y-major cells, sum over z slices)
+    to det3d/ops/point_cloud/bev_ops.py:27-53 as run by numba in this container."""
+    seen = 0
+    for case, voxel, f, pts, want in golden_frames():
+        got = B.bev_counts(pts, np.array([0, len(pts)]), B.NUSC_RANGE, voxel)[0]
+        assert np.array_equal(got, want), (case, f)
+        seen += 1
+    assert seen == 7
