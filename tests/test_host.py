@@ -279,3 +279,24 @@ def test_random_selector_equals_the_reference(pools, tmp_path):
     sel = build_selector(dict(type="RandomSelector", budget=10 ** 7, buffer_file=buf, infos_origin=pl["paths"]["infos"]))
     with pytest.raises(IndexError):
         sel.select_samples()
+
+
+def test_multisweep_lidar_loader_equals_the_reference_loading_code(tmp_path):
+    """``load_multisweep_points`` against the reference's own read_file / remove_close / read_sweep and nuScenes
+    branch (loading.py:17-63,98-126) -- golden made by oracle/make_golden_lidar.py; row order is immaterial for a
+    histogram, so rows are compared as a sorted multiset of float32 bit patterns."""
+    import make_golden_lidar as G
+    from conftest import load_golden
+    from adsel_b200.selectors.bev_spatial_selector import load_multisweep_points
+    g = load_golden("lidar_multisweep.json")
+    assert g["spec"] == G.SPEC
+    infos = G.write_case(str(tmp_path))
+    assert len(infos) == len(g["frames"])
+    for info, want in zip(infos, g["frames"]):
+        pts = load_multisweep_points(info, "", nsweeps=G.SPEC["file_sweeps"])
+        assert pts.dtype == np.float32 and pts.shape[1] == 5
+        assert G.rows_digest(pts) == (want["points"], want["sha256"])
+        assert G.rows_digest(load_multisweep_points(info, "", nsweeps=1)) == (want["key_frame_points"], want["key_frame_sha256"])
+        assert want["points"] < G.SPEC["file_sweeps"] * G.SPEC["n_points"]       # remove_close dropped sweep returns
+    with pytest.raises(AssertionError):
+        load_multisweep_points(infos[0], "", nsweeps=G.SPEC["file_sweeps"] + 1)   # loading.py:109-113
