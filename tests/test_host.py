@@ -300,3 +300,23 @@ def test_multisweep_lidar_loader_equals_the_reference_loading_code(tmp_path):
         assert want["points"] < G.SPEC["file_sweeps"] * G.SPEC["n_points"]       # remove_close dropped sweep returns
     with pytest.raises(AssertionError):
         load_multisweep_points(infos[0], "", nsweeps=G.SPEC["file_sweeps"] + 1)   # loading.py:109-113
+
+
+def test_registry_and_fileio_behave_like_the_reference_modules(tmp_path):
+    """The scenario table of oracle/host_api_cases.py, recorded on the unmodified det3d.utils.registry and
+    det3d.torchie.fileio (oracle/make_golden_host_api.py), replayed on this package: same values, same bytes on
+    disk, same exception types and messages."""
+    import host_api_cases
+    from conftest import load_golden
+    g = load_golden("host_api.json")
+    api = {"Registry": Registry, "build_from_cfg": build_from_cfg, "load": fileio.load, "dump": fileio.dump}
+    got = host_api_cases.run_all(api, str(tmp_path))
+    want = g["outcomes"]
+    if np.__version__ != g["numpy"]:                 # ndarray pickles name numpy-internal modules
+        for grp in (got, want):
+            grp["fileio"].pop("pkl_infos_bytes")
+    assert set(got) == set(want)
+    for group in want:
+        assert set(got[group]) == set(want[group])
+        for case in want[group]:
+            assert json.loads(json.dumps(got[group][case])) == want[group][case], (group, case)
