@@ -114,3 +114,37 @@ def fileio_cases(api, workdir):
 
 def run_all(api, workdir):
     return {"registry": registry_cases(api), "fileio": fileio_cases(api, workdir)}
+
+
+CLI_ARGV = {   # scenario id -> argv after the program name (tools/active_select.py:22-63)
+    "defaults": ["--config", "c.py"],
+    "budget_and_workdir": ["--config", "c.py", "--budget", "600", "--work_dir", "/w"],
+    "pred_flag": ["--config", "c.py", "--pred"],
+    "launcher_none": ["--config", "c.py", "--launcher", "none"],
+    "launcher_bogus": ["--config", "c.py", "--launcher", "ssh"],
+    "local_rank": ["--config", "c.py", "--local_rank", "3", "--gpus", "8"],
+    "budget_not_int": ["--config", "c.py", "--budget", "many"],
+    "txt_result": ["--config", "c.py", "--txt_result", "1", "--checkpoint", "x.pth"],
+    "unknown_flag": ["--config", "c.py", "--resume"],
+}
+CLI_KEYS = ("config", "work_dir", "txt_result", "gpus", "budget", "pred", "launcher", "local_rank")
+
+
+def cli_cases(parse_argv):
+    """``parse_argv(argv) -> namespace``; outcome = the shared keys of the namespace and the LOCAL_RANK the parser
+    exports when the launcher has not set one (:60-61), or the ``SystemExit`` code of argparse."""
+    import contextlib
+    out = {}
+    for name, argv in CLI_ARGV.items():
+        saved = os.environ.pop("LOCAL_RANK", None)
+        try:
+            with contextlib.redirect_stderr(io.StringIO()):
+                ns = vars(parse_argv(list(argv)))
+            out[name] = {"ok": {k: ns[k] for k in CLI_KEYS}, "LOCAL_RANK": os.environ.get("LOCAL_RANK")}
+        except SystemExit as e:
+            out[name] = {"raises": "SystemExit", "args": [str(e.code)]}
+        finally:
+            os.environ.pop("LOCAL_RANK", None)
+            if saved is not None:
+                os.environ["LOCAL_RANK"] = saved
+    return out

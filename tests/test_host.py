@@ -1,5 +1,6 @@
 """CPU: host logic -- registry/builder API, file formats, buffer bookkeeping, C-ABI exports."""
 import ctypes
+import importlib.util
 import json
 import os
 import pickle
@@ -311,6 +312,10 @@ def test_registry_and_fileio_behave_like_the_reference_modules(tmp_path):
     g = load_golden("host_api.json")
     api = {"Registry": Registry, "build_from_cfg": build_from_cfg, "load": fileio.load, "dump": fileio.dump}
     got = host_api_cases.run_all(api, str(tmp_path))
+    spec = importlib.util.spec_from_file_location("adsel_cli", os.path.join(ROOT, "tools", "active_select.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    got["cli"] = host_api_cases.cli_cases(cli.parse_args)       # flags / defaults / exit codes of tools/active_select.py
     want = g["outcomes"]
     if np.__version__ != g["numpy"]:                 # ndarray pickles name numpy-internal modules
         for grp in (got, want):

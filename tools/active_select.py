@@ -32,13 +32,18 @@ def parse_args(argv=None):
     p = argparse.ArgumentParser(description="Active selection (data-only selectors, B200)")
     p.add_argument("--config", required=True, help="config file with a `selector` dict")
     p.add_argument("--work_dir", help="logged only; the buffer lives at cfg.selector.buffer_file")
-    p.add_argument("--checkpoint", default=None, help="accepted for compatibility, unused")
-    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--checkpoint", default=None, help="accepted for compatibility, unused (no detector is built)")
+    p.add_argument("--txt_result", type=bool, default=False, help="accepted for compatibility, unused")
+    p.add_argument("--gpus", type=int, default=2, help="accepted for compatibility; ranks come from the launcher")
     p.add_argument("--budget", type=int, default=2400, help="annotation-cost budget of this round (reference default)")
     p.add_argument("--pred", action="store_true")
     p.add_argument("--launcher", choices=["none", "pytorch", "slurm", "mpi"], default="pytorch")
+    # torch.distributed.launch passes --local_rank (the reference's default is 0); torchrun only sets LOCAL_RANK
     p.add_argument("--local_rank", type=int, default=int(os.environ.get("LOCAL_RANK", 0)))
-    return p.parse_args(argv)
+    args = p.parse_args(argv)
+    if "LOCAL_RANK" not in os.environ:                  # :60-61
+        os.environ["LOCAL_RANK"] = str(args.local_rank)
+    return args
 
 
 def load_selector_cfg(path):
