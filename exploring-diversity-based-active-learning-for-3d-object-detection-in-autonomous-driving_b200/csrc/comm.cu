@@ -3,12 +3,15 @@
 // barrier.  SURVEY.md §8e; the reference has no counterpart (every rank recomputes everything,
 // det3d/selectors/base_selector.py:57).
 //
-// Each rank allocates ONE arena with a fixed layout that is identical on every rank:
+// Each rank allocates ONE arena with a fixed layout that is identical on every rank (arena_layout below):
 //     [0, 4 KB)   mailbox: greedy exchange slots, barrier counters, error flag   (comm.cuh)
-//     kNN index table   int32 [n, k+1]     every rank writes its rows into every rank's copy
-//     kNN distance table f64  [n, k+1]     (the all-gather is fused into the kNN kernel's stores)
-//     descriptor levels  bf16 [n, dim]     each rank's BEV descriptors, pushed to every peer
+//     kNN index table    int32 [n, k+1]    every rank writes its rows into every rank's copy
+//     kNN distance table f64   [n, k+1]    (the all-gather is fused into the kNN kernel's stores)
+//     descriptor levels  bf16  [n, dim]    each rank's BEV descriptors, pushed to every peer
 //     descriptor norms   int32 [n]
+//     neighbour lists    cursor | off int64 [n] | len int32 [n] | idx int32 [list_cap] | val f64 [list_cap]
+//                        entries whose COLUMN this rank owns; every rank's list build scatters into them
+//     d2 column slice    int32 [rows_pad, per]   dense path, world > 1: peers store the mirror images of their tiles here
 // and maps every peer's arena into its own address space.  Kernels then address peer memory directly
 // over NVLink; the only synchronisation primitives are the mailbox exchange and comm_barrier_kernel.
 #include "comm.cuh"

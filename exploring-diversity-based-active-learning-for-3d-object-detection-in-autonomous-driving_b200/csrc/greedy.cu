@@ -200,7 +200,7 @@ __device__ __forceinline__ void apply_row(const GreedyArgs &a, GreedyShared &sh,
     }
 }
 
-// Second half: re-read the dirtied 256-frame blocks, fold in the pulled group values of the row being
+// Second half: re-read the dirtied BLK-frame blocks, fold in the pulled group values of the row being
 // applied (`pull`), and recompute the block maxima.  One warp per block.
 template <int NT>
 __device__ __forceinline__ void refresh_blocks(const GreedyArgs &a, GreedyShared &sh, const double *tl, int tl_n,
