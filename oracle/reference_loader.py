@@ -99,6 +99,10 @@ def load_reference_selectors():
             sys.modules["det3d.torchie.apis.train"] = train
         from det3d.selectors.feature_selector import FeatureSelector
         out["FeatureSelector"] = FeatureSelector
+        from det3d.selectors.spatial_feature_selector import SpatialFeatureSelector
+        from det3d.selectors.spatial_temporal_feature_selector import SpatialTemporalFeatureSelector
+        out["SpatialFeatureSelector"] = SpatialFeatureSelector
+        out["SpatialTemporalFeatureSelector"] = SpatialTemporalFeatureSelector
     except Exception:   # pragma: no cover - torch missing etc.; the other selectors stay usable
         pass
     return out

@@ -333,3 +333,89 @@ def feature_select(feats, n_boxes, buffer, budget, p=2, cost_b=0.04, cost_f=0.12
             break
         selected.append(nxt)
     return current_budget, selected + sampled
+
+
+# --------------------------------------------------------------------------------------------
+# feature term fused with the spatial (/temporal) terms: det3d/selectors/spatial_feature_selector.py:113-236 and
+# spatial_temporal_feature_selector.py:113-261, rows computed lazily
+# --------------------------------------------------------------------------------------------
+class FusedFeatureRows:
+    """``distance_map[i]`` (and, for the spatial+feature selector, ``spatial_distance_map[i]`` after normalisation)
+    of the two fused selectors.
+
+    Types follow the reference: the geodesic and temporal maps are float64 and go through ``1 - np.exp(-x)`` in
+    float64; the feature map comes out of torch as FLOAT32 (``get_feature_distance_map(...).cpu().numpy()``), so
+    ``1 - np.exp(-feature)`` is numpy's float32 ``exp`` and a float32 result, promoted to float64 only when it is
+    added to / stacked with the other terms.
+    """
+
+    def __init__(self, kind, infos, feats, p=2, k=8, aggregate="sum", lambda_t=1, lambda_f=1):
+        assert kind in ("spatial_feature", "spatial_temporal_feature") and p in (1, 2)
+        self.kind, self.p, self.aggregate, self.lambda_t, self.lambda_f = kind, p, aggregate, lambda_t, lambda_f
+        self.n = len(infos)
+        self.feats = np.ascontiguousarray(feats, dtype=np.float32)
+        self.csr = knn_graph_csr(ego_locations(infos), k)
+        if kind == "spatial_temporal_feature":
+            self.group, _ = consecutive_runs(infos)                  # :183-207 (same run bookkeeping as :110-134 of ST)
+        self._cache = {}
+
+    def spatial(self, i: int) -> np.ndarray:
+        return 1 - np.exp(-geodesic_rows(self.csr, [i])[0])          # spatial_feature_selector.py:189
+
+    def feature(self, i: int) -> np.ndarray:
+        return 1 - np.exp(-feature_row(self.feats, i, self.p))       # :190, float32 in, float32 out
+
+    def row(self, i: int) -> np.ndarray:
+        if i not in self._cache:
+            s, f = self.spatial(i), self.feature(i)
+            assert s.dtype == np.float64 and f.dtype == np.float32
+            if self.kind == "spatial_feature":
+                if self.aggregate == "sum":                          # :192-193
+                    r = s + f
+                elif self.aggregate == "min":                        # :194-195
+                    r = np.stack([s, f]).min(0)
+                else:                                                # :196-197
+                    r = np.stack([s, f]).max(0)
+            else:                                                    # spatial_temporal_feature_selector.py:212-219
+                t = 1 - np.exp(-temporal_row(self.group, i))
+                r = s + self.lambda_t * t + self.lambda_f * f
+            self._cache[i] = r
+        return self._cache[i]
+
+
+def fused_feature_select(kind, infos, feats, buffer, budget, first_index, cost_b=0.04, cost_f=0.12, **kw):
+    """One ``select_samples()`` round of SpatialFeatureSelector / SpatialTemporalFeatureSelector:
+    ``(current_budget_key, sampled + selected)``.
+
+    Quirk kept from the reference: the spatial+feature selector SEEDS the min-distance vector from the normalised
+    SPATIAL rows only (spatial_feature_selector.py:201-209) and uses the aggregated map from the first update on
+    (:217); it also asserts against the buffer (:222).  The spatial+temporal+feature selector seeds from the
+    aggregated map (spatial_temporal_feature_selector.py:225-234) and only asserts against the new picks (:245).
+    """
+    max_key = str(max(int(k) for k in buffer))
+    current_budget = str(budget + int(max_key))
+    sampled = list(buffer[max_key])
+    rows = FusedFeatureRows(kind, infos, feats, **kw)
+    seed_row = rows.spatial if kind == "spatial_feature" else rows.row
+    n_boxes = np.array([info["gt_names"].shape[0] for info in infos], dtype=np.int64)
+    if len(sampled) > 0:
+        fps = np.stack([seed_row(i) for i in sampled]).min(0)
+        selected = [int(np.argmax(fps))]
+    else:
+        selected = [int(first_index)]
+        fps = seed_row(selected[-1])
+    cost = cost_of_sampled(n_boxes, sampled, cost_b, cost_f)
+    cost += cost_f
+    cost += int(n_boxes[selected[-1]]) * cost_b
+    while True:
+        fps = np.stack([fps, rows.row(selected[-1])]).min(0)
+        nxt = int(np.argmax(fps))
+        if kind == "spatial_feature":
+            assert nxt not in sampled, f"id: {nxt} not in the left index list"
+        assert nxt not in selected, f"id: {nxt} has been selected"
+        cost += cost_f
+        cost += int(n_boxes[nxt]) * cost_b
+        if cost > int(current_budget):
+            break
+        selected.append(nxt)
+    return current_budget, sampled + selected
