@@ -85,3 +85,56 @@ void oracle_exp_normalize_array(const double *d, double *out, long n)
 {
     for (long i = 0; i < n; ++i) out[i] = 1.0 - oracle_npexp(-d[i]);
 }
+
+/*
+ * float32 `exp` of numpy 2.3.5 on AVX512F / AVX2+FMA3 hosts: numpy's own SIMD kernel (simd_exp_FLOAT in
+ * loops_exponent_log.dispatch.c.src; float32 does not go through SVML).  The reference reaches it through
+ * `1 - np.exp(-feature_distance_map)` on the float32 map torch hands over
+ * (det3d/selectors/spatial_feature_selector.py:190, spatial_temporal_feature_selector.py:214).
+ *
+ *   q   = rint(x * log2e)                      (add/subtract 1.5*2^23)
+ *   r   = fma(q, -ln2_hi, x); r = fma(q, -ln2_lo, r)          Cody-Waite, ln2_hi = 6.93145752e-1f
+ *   num = ((((p5 r + p4) r + p3) r + p2) r + p1) r + p0        all fma
+ *   den = (q2 r + q1) r + q0
+ *   exp = scalef(num / den, q)                 x > 88.7228... -> inf, x < -103.972... -> 0, NaN -> NaN
+ *
+ * Pinned bit for bit against np.exp on ALL 2^32 float32 inputs in the build container (NaN payloads
+ * aside; tests/test_oracle_npexp.py re-checks a sample and the edges, ADSEL_EXHAUSTIVE=1 the whole range).
+ */
+float oracle_npexpf(float x)
+{
+    const float xmax = 88.72283935546875f, xmin = -103.97208404541015625f;
+    const float log2e = 1.44269504088896341f;
+    const float c1 = -6.93145752e-1f, c2 = -1.42860677e-6f;
+    const float p0 = 9.999999999980870924916e-01f, p1 = 7.257664613233124478488e-01f,
+                p2 = 2.473615434895520810817e-01f, p3 = 5.114512081637298353406e-02f,
+                p4 = 6.757896990527504603057e-03f, p5 = 5.082762527590693718096e-04f;
+    const float q0 = 1.0f, q1 = -2.742335390411667452936e-01f, q2 = 2.159509375685829852307e-02f;
+    const float magic = 0x1.8p+23f;
+    if (x != x) return x;
+    if (x > xmax) return INFINITY;
+    if (x < xmin) return 0.0f;
+    float q = x * log2e;
+    q = (q + magic) - magic;
+    float r = fmaf(q, c1, x);
+    r = fmaf(q, c2, r);
+    float num = fmaf(p5, r, p4);
+    num = fmaf(num, r, p3);
+    num = fmaf(num, r, p2);
+    num = fmaf(num, r, p1);
+    num = fmaf(num, r, p0);
+    float den = fmaf(q2, r, q1);
+    den = fmaf(den, r, q0);
+    return ldexpf(num / den, (int)q);            /* vscalefps: one rounding, denormal results included */
+}
+
+void oracle_npexpf_array(const float *x, float *out, long n)
+{
+    for (long i = 0; i < n; ++i) out[i] = oracle_npexpf(x[i]);
+}
+
+/* 1 - exp(-d) in float32: the feature term's normalisation. */
+void oracle_exp_normalize_f32_array(const float *d, float *out, long n)
+{
+    for (long i = 0; i < n; ++i) out[i] = 1.0f - oracle_npexpf(-d[i]);
+}

@@ -43,7 +43,8 @@ def _lib():
     global _LIB
     if _LIB is None:
         _LIB = ctypes.CDLL(build_c_oracle())
-        for name in ("oracle_npexp_array", "oracle_exp_normalize_array"):
+        for name in ("oracle_npexp_array", "oracle_exp_normalize_array", "oracle_npexpf_array",
+                     "oracle_exp_normalize_f32_array"):
             getattr(_LIB, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long]
             getattr(_LIB, name).restype = None
     return _LIB
@@ -54,6 +55,22 @@ def npexp(x: np.ndarray) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(x)
     _lib().oracle_npexp_array(x.ctypes.data, out.ctypes.data, x.size)
+    return out
+
+
+def npexp_f32(x: np.ndarray) -> np.ndarray:
+    """numpy's float32 exp (its own AVX512F / AVX2 kernel), bit for bit (oracle/npexp.c)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    _lib().oracle_npexpf_array(x.ctypes.data, out.ctypes.data, x.size)
+    return out
+
+
+def exp_normalize_f32(d: np.ndarray) -> np.ndarray:
+    """``1 - np.exp(-d)`` on a float32 array: float32 exp, float32 result (spatial_feature_selector.py:190)."""
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    out = np.empty_like(d)
+    _lib().oracle_exp_normalize_f32_array(d.ctypes.data, out.ctypes.data, d.size)
     return out
 
 
@@ -360,10 +377,10 @@ class FusedFeatureRows:
         self._cache = {}
 
     def spatial(self, i: int) -> np.ndarray:
-        return 1 - np.exp(-geodesic_rows(self.csr, [i])[0])          # spatial_feature_selector.py:189
+        return exp_normalize(geodesic_rows(self.csr, [i])[0])        # spatial_feature_selector.py:189
 
     def feature(self, i: int) -> np.ndarray:
-        return 1 - np.exp(-feature_row(self.feats, i, self.p))       # :190, float32 in, float32 out
+        return exp_normalize_f32(feature_row(self.feats, i, self.p))  # :190, float32 in, float32 out
 
     def row(self, i: int) -> np.ndarray:
         if i not in self._cache:
@@ -377,7 +394,7 @@ class FusedFeatureRows:
                 else:                                                # :196-197
                     r = np.stack([s, f]).max(0)
             else:                                                    # spatial_temporal_feature_selector.py:212-219
-                t = 1 - np.exp(-temporal_row(self.group, i))
+                t = exp_normalize(temporal_row(self.group, i))
                 r = s + self.lambda_t * t + self.lambda_f * f
             self._cache[i] = r
         return self._cache[i]
