@@ -64,6 +64,11 @@ __global__ void exp_f64_kernel(const double *__restrict__ x, long long n, double
         out[i] = np_exp_f64(x[i]);
 }
 
+__global__ void exp_f32_kernel(const float *__restrict__ x, long long n, float *__restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = np_exp_f32(x[i]);
+}
+
 }  // namespace adsel
 
 using namespace adsel;
@@ -419,6 +424,26 @@ int adsel_exp_f64(adsel_handle *h, const double *x, int64_t n, double *out) {
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     ADSEL_CUDA(cudaMemcpyAsync(out, dy, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(dx);
+    cudaFree(dy);
+    return ADSEL_OK;
+}
+
+int adsel_exp_f32(adsel_handle *h, const float *x, int64_t n, float *out) {
+    ADSEL_REQUIRE(h && x && out && n > 0, "adsel_exp_f32: null/empty argument");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    float *dx = nullptr, *dy = nullptr;
+    ADSEL_CUDA(cudaMalloc(&dx, sizeof(float) * n));
+    if (cudaMalloc(&dy, sizeof(float) * n) != cudaSuccess) {
+        cudaFree(dx);
+        ADSEL_CUDA(cudaErrorMemoryAllocation);
+    }
+    ADSEL_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    exp_f32_kernel<<<h->num_sms * 8, 256, 0, h->stream>>>(dx, n, dy);
+    h->launches += 1;
+    ADSEL_CUDA(cudaGetLastError());
+    ADSEL_CUDA(cudaMemcpyAsync(out, dy, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
     ADSEL_CUDA(cudaStreamSynchronize(h->stream));
     cudaFree(dx);
     cudaFree(dy);

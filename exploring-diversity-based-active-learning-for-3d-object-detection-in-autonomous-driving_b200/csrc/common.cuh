@@ -233,6 +233,42 @@ __device__ __forceinline__ double np_exp_f64(double x) {
     return ldexp(y, (int)floor(N));
 }
 
+// numpy's float32 exp (its own SIMD kernel, simd_exp_FLOAT: float32 does not go through SVML), bit for bit on every
+// float32 input: the normalisation of the float32 feature-distance map in the fused feature selectors
+// (det3d/selectors/spatial_feature_selector.py:190).  Restated and pinned in oracle/npexp.c::oracle_npexpf.
+__device__ __forceinline__ float np_exp_f32(float x) {
+    const float xmax = 88.72283935546875f, xmin = -103.97208404541015625f;
+    const float log2e = 1.44269504088896341f, magic = 0x1.8p+23f;
+    const float c1 = -6.93145752e-1f, c2 = -1.42860677e-6f;
+    const float p0 = 9.999999999980870924916e-01f, p1 = 7.257664613233124478488e-01f, p2 = 2.473615434895520810817e-01f,
+                p3 = 5.114512081637298353406e-02f, p4 = 6.757896990527504603057e-03f, p5 = 5.082762527590693718096e-04f;
+    const float q0 = 1.0f, q1 = -2.742335390411667452936e-01f, q2 = 2.159509375685829852307e-02f;
+    if (x != x) return x;
+    if (x > xmax) return __int_as_float(0x7f800000);
+    if (x < xmin) return 0.0f;
+    float q = __fmul_rn(x, log2e);
+    q = __fsub_rn(__fadd_rn(q, magic), magic);          // rint, ties to even
+    float r = __fmaf_rn(q, c1, x);
+    r = __fmaf_rn(q, c2, r);
+    float num = __fmaf_rn(p5, r, p4);
+    num = __fmaf_rn(num, r, p3);
+    num = __fmaf_rn(num, r, p2);
+    num = __fmaf_rn(num, r, p1);
+    num = __fmaf_rn(num, r, p0);
+    float den = __fmaf_rn(q2, r, q1);
+    den = __fmaf_rn(den, r, q0);
+    const float y = __fdiv_rn(num, den);                 // in (0.5, 2)
+    // scalef(y, q), rounded once: powers of two are built from their exponent bits; a result below 2^-126 is
+    // reached through an exact intermediate so that only the final multiplication rounds
+    const int e = (int)q;                                // -150 .. 128
+    if (e >= -126) {
+        float v = __fmul_rn(y, __int_as_float((min(e, 127) + 127) << 23));
+        if (e > 127) v = __fmul_rn(v, 2.0f);
+        return v;
+    }
+    return __fmul_rn(__fmul_rn(y, __int_as_float((e + 64 + 127) << 23)), 0x1p-64f);
+}
+
 // Normalisation of one raw distance d >= 0 (spatial_temporal_selector.py:138-146).
 __device__ __forceinline__ double normalize_value(double d, int mode, double divisor) {
     if (mode == ADSEL_NORM_EXP) return __dsub_rn(1.0, np_exp_f64(-d));

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "adsel_get_stage_ms": (ctypes.c_int, [_P, _P]),
     "adsel_get_counters": (ctypes.c_int, [_P, _P]),
     "adsel_exp_f64": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P]),
+    "adsel_exp_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P]),
     "adsel_pairdist_set_descriptors": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
     "adsel_pairdist_build": (ctypes.c_int, [_P]),
     "adsel_pairdist_get_rows": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, _P]),
@@ -487,6 +488,12 @@ class Handle:
 
     def synchronize(self):
         _check(load().adsel_synchronize(self._h))
+
+    def exp_f32(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(x)
+        _check(load().adsel_exp_f32(self._h, _ptr(x), x.size, _ptr(out)))
+        return out
 
     def exp_f64(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

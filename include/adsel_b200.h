@@ -221,6 +221,10 @@ int adsel_select_dense_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t ou
 /* out[i] = exp(x[i]) with the arithmetic of numpy's AVX512_SKX float64 exp (np.exp in
  * spatial_temporal_selector.py:142-143); host buffers, computed on the device. */
 int adsel_exp_f64(adsel_handle *h, const double *x, int64_t n, double *out);
+/* out[i] = exp(x[i]) with the arithmetic of numpy's float32 exp (its own AVX512F / AVX2 kernel): the
+ * normalisation `1 - np.exp(-feature_distance_map)` of the float32 feature map in
+ * det3d/selectors/spatial_feature_selector.py:190 and spatial_temporal_feature_selector.py:214. */
+int adsel_exp_f32(adsel_handle *h, const float *x, int64_t n, float *out);
 
 #ifdef __cplusplus
 }
