@@ -58,13 +58,16 @@ class BevSpatialSelector(BaseSelector):
                  data_root: str = "", nsweeps: int = 10,
                  point_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0),     # cbgs_spatial_temporal.py:280
                  voxel_size=(0.8, 0.8, 8.0), batch_frames: int = 1024,
-                 points_fn: Optional[Callable] = None, cost_b: float = 0.04, cost_f: float = 0.12) -> None:
+                 points_fn: Optional[Callable] = None, cost_b: float = 0.04, cost_f: float = 0.12,
+                 io_threads: int = 8) -> None:
         super().__init__(budget, buffer_file, dump_file_name, infos_origin=infos_origin, detector=detector,
                          dataloader=dataloader, logger=logger, pred=pred, cost_b=cost_b, cost_f=cost_f)
         self.data_root, self.nsweeps = data_root, nsweeps
         self.point_range, self.voxel_size = tuple(point_range), tuple(voxel_size)
         self.batch_frames = int(batch_frames)
         self.points_fn = points_fn
+        self.io_threads = max(1, int(io_threads))
+        self._io_pool = None
 
     def _points(self, index):
         info = self.infos_origin[index]
@@ -72,15 +75,28 @@ class BevSpatialSelector(BaseSelector):
             return np.ascontiguousarray(self.points_fn(info, index), dtype=np.float32)
         return load_multisweep_points(info, self.data_root, self.nsweeps)
 
+    def load_frames(self, lo, hi):
+        """``(points float32 [P,5], frame_off int64 [hi-lo+1])`` of frames [lo, hi), in frame order.  Frames read
+        from files are loaded by ``io_threads`` threads (np.fromfile and the sweep transforms release the GIL); a
+        user ``points_fn`` is called sequentially, it need not be thread-safe.  An exception of any frame propagates."""
+        if self.points_fn is None and self.io_threads > 1 and hi - lo > 1:
+            if self._io_pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._io_pool = ThreadPoolExecutor(max_workers=self.io_threads, thread_name_prefix="adsel-lidar")
+            frames = list(self._io_pool.map(self._points, range(lo, hi)))
+        else:
+            frames = [self._points(i) for i in range(lo, hi)]
+        off = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.int64)
+        points = np.concatenate(frames, axis=0) if frames else np.empty((0, 5), dtype=np.float32)
+        return points, off
+
     def select_samples(self, **kwargs) -> None:
         import random
         n = len(self.infos_origin)
         handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's slice of the frames
 
         def load_batch(h, lo, hi):                                 # stream the pool through HBM
-            frames = [self._points(i) for i in range(lo, hi)]
-            off = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.int64)
-            h.bev_set_points(np.concatenate(frames, axis=0), off)
+            h.bev_set_points(*self.load_frames(lo, hi))
 
         try:
             handle.dense_build(n, self.batch_frames, load_batch, self.point_range, self.voxel_size)
@@ -94,3 +110,6 @@ class BevSpatialSelector(BaseSelector):
             self.selected_index[self.current_budget] = sampled + selected
         finally:
             handle.close()
+            if self._io_pool is not None:
+                self._io_pool.shutdown(wait=False)
+                self._io_pool = None

@@ -325,3 +325,36 @@ def test_registry_and_fileio_behave_like_the_reference_modules(tmp_path):
         assert set(got[group]) == set(want[group])
         for case in want[group]:
             assert json.loads(json.dumps(got[group][case])) == want[group][case], (group, case)
+
+
+def test_bev_selector_threaded_frame_loading_equals_sequential(pools, tmp_path):
+    """BevSpatialSelector.load_frames: the thread pool returns the same points and offsets, in frame order, as the
+    sequential loop; a user points_fn stays sequential; a failing frame raises."""
+    import threading
+    from adsel_b200 import synthetic
+    from adsel_b200.selectors import BevSpatialSelector
+    infos = [dict(i) for i in pools("P300")["infos"][:40]]
+    synthetic.write_lidar_files(infos, str(tmp_path), n_points=700, nsweeps=3)
+    for i, info in enumerate(infos):                       # ragged frames: a different number of points everywhere
+        pts = np.fromfile(str(tmp_path / info["lidar_path"]), dtype=np.float32).reshape(-1, 5)
+        pts[: 700 - 7 * i].tofile(str(tmp_path / info["lidar_path"]))
+    infos_file, buf = str(tmp_path / "infos.pkl"), str(tmp_path / "buffer.json")
+    pickle.dump(infos, open(infos_file, "wb"), protocol=2)
+    json.dump({"0": []}, open(buf, "w"))
+    kw = dict(budget=10, buffer_file=buf, infos_origin=infos_file, data_root=str(tmp_path), nsweeps=3)
+    seq, par = BevSpatialSelector(io_threads=1, **kw), BevSpatialSelector(io_threads=6, **kw)
+    for lo, hi in ((0, 40), (3, 4), (17, 29), (5, 5)):
+        p1, o1 = seq.load_frames(lo, hi)
+        p2, o2 = par.load_frames(lo, hi)
+        assert p1.dtype == np.float32 and p1.shape[1] == 5 and o1.dtype == np.int64
+        assert np.array_equal(o1, o2) and np.array_equal(p1.view(np.uint32), p2.view(np.uint32))
+        assert len(o1) == hi - lo + 1 and o1[-1] == len(p1)
+    assert len(set(np.diff(seq.load_frames(0, 40)[1]).tolist())) > 30
+    seen = []
+    custom = BevSpatialSelector(points_fn=lambda info, i: (seen.append(threading.current_thread().name), np.zeros((i + 1, 5)))[1],
+                                io_threads=6, **kw)
+    p, o = custom.load_frames(0, 5)
+    assert o.tolist() == [0, 1, 3, 6, 10, 15] and set(seen) == {threading.current_thread().name}
+    os.remove(str(tmp_path / infos[9]["lidar_path"]))
+    with pytest.raises(FileNotFoundError):
+        par.load_frames(0, 40)
