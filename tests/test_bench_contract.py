@@ -51,3 +51,55 @@ def test_profiled_traffic_table_names_kernels_of_this_library():
         assert got["traffic"] == entry["bytes"] > 0 and got["traffic_launch"].split(":")[0].endswith(".csv")
         assert os.path.exists(os.path.join(ROOT, "profiles", got["traffic_launch"].split(":")[0]))
     assert lookup("no_such_kernel") == {"traffic": None}
+
+
+def test_bev_extras_bookkeeping_with_a_stub_engine():
+    """bench.bev_extras on a stub of native.Handle (no GPU): the roofline objects carry bound / achieved / peak / frac /
+    traffic, and the flop / byte accounting follows the formulas stated in DESIGN.md."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class Handle:
+        def __init__(self, device):
+            self.calls = []
+
+        def bev_generate(self, off, **kw):
+            self.calls.append(("gen", len(off) - 1, kw["first_frame"]))
+
+        def bev_build(self, **kw):
+            self.calls.append(("build", kw["frame_base"], kw["total_frames"]))
+
+        def stage_ms(self):
+            return {"bev_histogram": 1.0, "pairdist": 2.0, "dense_greedy": 3.0}
+
+        def pairdist_build(self):
+            pass
+
+        def select_dense(self, n_boxes, **kw):
+            assert kw["budget"] == 1200 and kw["first_index"] == 3
+            return list(range(10)), 5.0
+
+        def close(self):
+            pass
+
+    class Native:
+        pass
+    Native.Handle = Handle
+    n = 5000
+    out = bench.bev_extras(Native, 0, n, np.ones(n, np.int32), 3, {"hbm": 6441.0, "bf16": 1675.9, "bf16_source": "x"},
+                           reps=1, batch=2048)
+    hist, tiles = out["bev_descriptor_build"], out["pairdist_tiles"]
+    sizes = 300_000 + (np.arange(n, dtype=np.int64) * 977) % 4001 - 2000
+    assert hist["points"] == int(sizes.sum()) and hist["ms"] == 3.0            # three batches of <= 2,048 frames, 1 ms each
+    want_gbs = (20.0 * sizes.sum() + n * (16384 * 6 + 4)) / 3e-3 / 1e9
+    r = hist["roofline"]
+    assert r["bound"] == "hbm" and abs(r["achieved"] - want_gbs) < 1e-6 * want_gbs and r["frac"] == r["achieved"] / r["peak"]
+    assert r["traffic"] > 0 and "768 frames" in r["traffic_launch"]
+    bm, bn = -(-n // 128), -(-n // 256)
+    done = sum(max(0, bn - m // 2) for m in range(bm))
+    assert tiles["tiles_computed"] == done and tiles["tiles_full_matrix"] == bm * bn
+    assert abs(tiles["roofline"]["achieved"] - 2.0 * done * 128 * 256 * 16384 / 2e-3 / 1e12) < 1e-9
+    assert tiles["roofline"]["bound"] == "tensor" and tiles["roofline"]["traffic"] > 0
+    sel = out["bev_selection_budget1200"]
+    assert sel["selected_frames"] == 10 and sel["ms_total"] == 3.0 + 2.0 + 3.0
