@@ -209,6 +209,23 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # BEV-descriptor configuration (BASELINE.json configs[1]/[2]: north_star kernels 1 and 3)
 # ------------------------------------------------------------------------------------------------
+def greedy_latency_floor(greedy_ms, steps, clock_info):
+    """What bounds the greedy loop is the LENGTH of its dependency chain, not bandwidth: per step four
+    dependent L2 hits (frame record, list entries, min-distance entries, block re-read; 262 cycles each on the far die)
+    and three CTA barriers (~34 cycles) -- /opt/skills/guides/B300_MICROARCH.md, L2 and barrier rows.  Reported next to
+    the achieved time per step so that the headroom of the loop is a number; it is a model, not a measurement."""
+    try:
+        sm_mhz = float((clock_info or {}).get("sm_mhz") or 1965.0)
+    except (TypeError, ValueError, AttributeError):
+        sm_mhz = 1965.0
+    cycles = 4 * 262 + 3 * 34
+    floor_us = cycles / sm_mhz
+    achieved_us = greedy_ms * 1e3 / max(int(steps), 1)
+    return {"model": "4 dependent L2 hits x 262 cycles + 3 CTA barriers x 34 cycles per step", "cycles_per_step": cycles,
+            "floor_us_per_step": floor_us, "achieved_us_per_step": achieved_us,
+            "frac": floor_us / achieved_us if achieved_us > 0 else None}
+
+
 def profiled_traffic():
     """kernel name -> {"traffic": DRAM bytes of the profiled launch, "traffic_launch": what that launch was} from the
     committed ncu --set full captures (profiles/traffic.json); the profiled launches of the BEV kernels are smaller
@@ -574,6 +591,7 @@ def run_b200_arm(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "latency-bound dependency chain (one CTA, %d sequential steps, %.2f us/step); see DESIGN.md §6"
                         % (steps_per_sel, stages["greedy"] * 1e3 / max(steps_per_sel, 1))}
+    roofline["latency_floor"] = greedy_latency_floor(stages["greedy"], steps_per_sel, clock_info)
 
     if rank == 0:
         line = {
