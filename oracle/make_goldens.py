@@ -81,7 +81,7 @@ def run_case(classes, sel_name, paths, kwargs, rounds, workdir, keep_store=None)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pool", default="P2K")
-    ap.add_argument("--only", default="all", help="all | st (SpatialTemporal exp/sum only) | temporal (TemporalSelector only) | random")
+    ap.add_argument("--only", default="all", help="all | st (SpatialTemporal exp/sum only) | temporal (TemporalSelector only) | random | spatial (SpatialSelector at budget 1200)")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
     ap.add_argument("--budget", type=int, default=600, help="base budget B; chained cases use B/2,B/2,B")
     args = ap.parse_args()
@@ -102,6 +102,8 @@ def main():
         if args.only == "temporal":     # BASELINE.json config 4: temporal-only selector, 850 scenes, budget 1200
             cases += [("temporal_1200", "TemporalSelector", {}, [1200]),
                       ("temporal_rounds", "TemporalSelector", {}, [600, 600])]
+        elif args.only == "spatial":    # BASELINE config 2's engine at full size: SpatialSelector, budget 1200 (~6 min at P28K)
+            cases += [("spatial_1200", "SpatialSelector", {}, [1200])]
         elif args.only == "random":     # the random baseline every experiment of the paper is compared with
             cases += [("random", "RandomSelector", {}, [B]),
                       ("random_rounds", "RandomSelector", {}, [H, H, B]),

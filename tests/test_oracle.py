@@ -72,3 +72,13 @@ def test_restatement_reproduces_the_p850_temporal_golden(pools):
     case = golden["cases"]["temporal_1200"]
     key, sel = R.select("temporal", pl["infos"], pl["logs"], {"0": []}, 1200, first_index_for(len(pl["infos"])))
     assert sel == case["selected_index"][key]
+
+
+def test_restatement_reproduces_the_p28k_spatial_golden(pools):
+    """BASELINE.json config 2's engine at full size: the unmodified SpatialSelector on the 28,130-frame pool at budget
+    1200 (oracle/make_goldens.py --pool P28K --only spatial) vs the streaming restatement."""
+    golden = load_golden("P28K_spatial.json")
+    pl = pools("P28K")
+    case = golden["cases"]["spatial_1200"]
+    key, sel = R.select("spatial", pl["infos"], pl["logs"], {"0": []}, 1200, first_index_for(len(pl["infos"])))
+    assert key == "1200" and sel == case["selected_index"][key]
