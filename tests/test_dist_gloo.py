@@ -117,3 +117,70 @@ def test_two_ranks_select_like_the_reference_and_only_rank0_writes(pools, tmp_pa
         assert r["retry_list_cap"] == int(1010 * 1.1) + 1024                  # ... sized for the largest need over the ranks
     assert json.load(open(os.path.join(out_dir, "buffer.json"))) == {"0": [], "50": want["50"], "100": want["100"]}
     assert os.path.exists(pl["paths"]["infos"].replace(".pkl", "_100.pkl"))
+
+
+def _extract_worker(rank, world, init_file, pool_dir, out_dir):
+    try:
+        for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        import adsel_b200  # noqa: F401
+        from adsel_b200 import fileio, pool
+        dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+        infos = fileio.load(os.path.join(pool_dir, "infos_train_10sweeps_withvelo.pkl"))
+        known = {l["logfile"] for l in fileio.load(os.path.join(pool_dir, "log.json"))}
+        out = {}
+        # 1. whole pool, slices cut wherever n*r//world falls (inside runs and, after the edit below, exactly on one)
+        loc, run_id, max_td, boxes = pool.extract_spatial_temporal(infos, known)
+        out["a"] = [loc.view(np.uint64).tolist(), run_id.tolist(), int(max_td), boxes.tolist()]
+        # 2. a prefix whose length puts slice boundaries exactly on run boundaries: runs of P2K start every ~40 frames
+        names = pool.logfile_names(infos)
+        starts = [i for i in range(1, len(names)) if names[i] != names[i - 1]]
+        cut = starts[2] * world                         # n*r//world == r*starts[2]: rank 1's slice begins a new run
+        sub = infos[:cut]
+        loc, run_id, max_td, boxes = pool.extract_spatial_temporal(sub, known)
+        out["b"] = [loc.view(np.uint64).tolist(), run_id.tolist(), int(max_td), boxes.tolist(), cut]
+        # 3. a logfile unknown to logs_file, seen by the LAST rank's slice only: KeyError on every rank (:80)
+        bad = [dict(i) for i in infos]
+        bad[-3]["cam_front_path"] = bad[-3]["cam_front_path"].replace(names[-3], "n999-unknown-log")
+        try:
+            pool.extract_spatial_temporal(bad, known)
+            out["c"] = "no error"
+        except KeyError as e:
+            out["c"] = e.args[0]
+        # 4. fewer than 4 frames per rank: every rank parses everything itself (no collective)
+        loc, run_id, max_td, boxes = pool.extract_spatial_temporal(infos[: 4 * world - 1], known)
+        out["d"] = [len(loc), run_id.tolist()]
+        json.dump(out, open(os.path.join(out_dir, f"rank{rank}.json"), "w"))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        open(os.path.join(out_dir, f"rank{rank}.err"), "w").write(traceback.format_exc())
+        raise
+
+
+def test_three_ranks_assemble_the_same_pool_arrays_as_one_process(pools, tmp_path):
+    """pool.extract_spatial_temporal under a world of 3 (uneven slices): every rank ends with exactly the arrays a
+    single process extracts -- bit-equal ego locations, run ids merged across slice boundaries (inside a run and exactly
+    on a run boundary), the reference's max_temporal_distance, box counts -- and a logfile missing from logs_file
+    raises KeyError on every rank, whichever rank's slice holds the frame."""
+    from adsel_b200 import pool
+    pl = pools("P2K")
+    out_dir = str(tmp_path)
+    mp.spawn(_extract_worker, args=(3, os.path.join(out_dir, "rendezvous"), pl["dir"], out_dir), nprocs=3, join=True)
+    errs = [f for f in os.listdir(out_dir) if f.endswith(".err")]
+    assert not errs, open(os.path.join(out_dir, errs[0])).read()
+    infos = pl["infos"]
+    known = {l["logfile"] for l in pl["logs"]}
+    res = [json.load(open(os.path.join(out_dir, f"rank{r}.json"))) for r in range(3)]
+    loc, run_id, max_td, boxes = pool.extract_spatial_temporal(infos, known)          # this process: world 1
+    want_a = [loc.view(np.uint64).tolist(), run_id.tolist(), int(max_td), boxes.tolist()]
+    cut = res[0]["b"][4]
+    loc, run_id, max_td, boxes = pool.extract_spatial_temporal(infos[:cut], known)
+    want_b = [loc.view(np.uint64).tolist(), run_id.tolist(), int(max_td), boxes.tolist(), cut]
+    names = pool.logfile_names(infos)
+    assert names[cut // 3] != names[cut // 3 - 1]                                      # the boundary case is really hit
+    for r in res:
+        assert r["a"] == want_a and r["b"] == want_b
+        assert r["c"] == "n999-unknown-log"
+        assert r["d"] == [11, pool.consecutive_runs(names[:11])[0].tolist()]
