@@ -358,3 +358,92 @@ def test_bev_selector_threaded_frame_loading_equals_sequential(pools, tmp_path):
     os.remove(str(tmp_path / infos[9]["lidar_path"]))
     with pytest.raises(FileNotFoundError):
         par.load_frames(0, 40)
+
+
+class _FakeDist:
+    """all_gather over a list of pre-recorded per-rank byte tensors (the packing under test is rank-local)."""
+
+    def __init__(self, recorded=None):
+        self.recorded, self.sent = recorded, None
+
+    def get_backend(self):
+        return "gloo"
+
+    def all_gather(self, outs, t):
+        self.sent = t.clone()
+        for r, o in enumerate(outs):
+            o.copy_(self.recorded[r] if self.recorded is not None else t)
+
+
+def test_slice_records_survive_the_byte_tensor_all_gather():
+    """pool._all_gather_slices packs (lo, n, three optional strings, loc, boxes, packed change bits) into one
+    fixed-size byte tensor per rank: whatever the ranks put in comes out, for ragged slices, empty strings,
+    non-ASCII names and absent (None) fields."""
+    from hypothesis import given, settings, strategies as st
+    from adsel_b200 import pool as P
+
+    name = st.one_of(st.none(), st.text(max_size=40))
+
+    @st.composite
+    def worlds(draw):
+        world = draw(st.integers(1, 4))
+        cap = draw(st.integers(1, 70))
+        recs = []
+        for r in range(world):
+            k = draw(st.integers(1, cap))
+            seed = draw(st.integers(0, 2 ** 31))
+            rng = np.random.default_rng(seed)
+            change = rng.random(k) < 0.3
+            recs.append({"lo": draw(st.integers(0, 10 ** 6)), "n": k, "missing": draw(name), "first": draw(st.text(max_size=40)),
+                         "last": draw(st.text(max_size=40)), "loc": rng.normal(0, 1e3, size=(k, 2)),
+                         "boxes": rng.integers(0, 200, size=k).astype(np.int32), "change": np.packbits(change), "_bits": change})
+        return world, cap, recs
+
+    @settings(max_examples=60, deadline=None)
+    @given(worlds())
+    def check(case):
+        world, cap, recs = case
+        sent = []
+        for rec in recs:                                    # what every rank would contribute
+            d = _FakeDist()
+            P._all_gather_slices(d, world, rec, cap)
+            sent.append(d.sent)
+        assert len({int(t.numel()) for t in sent}) == 1     # fixed size: one collective, no size exchange
+        parts = P._all_gather_slices(_FakeDist(sent), world, recs[0], cap)
+        assert len(parts) == world
+        for got, want in zip(parts, recs):
+            assert (got["lo"], got["n"], got["missing"], got["first"], got["last"]) == \
+                   (want["lo"], want["n"], want["missing"], want["first"], want["last"])
+            assert np.array_equal(got["loc"].view(np.uint64), want["loc"].view(np.uint64))
+            assert np.array_equal(got["boxes"], want["boxes"])
+            assert np.array_equal(np.unpackbits(got["change"])[: want["n"]].astype(bool), want["_bits"])
+
+    check()
+    with pytest.raises(ValueError):                         # a name that does not fit the fixed header is refused, not cut
+        P._all_gather_slices(_FakeDist(), 1, {"lo": 0, "n": 1, "missing": None, "first": "x" * 300, "last": "y",
+                                              "loc": np.zeros((1, 2)), "boxes": np.zeros(1, np.int32),
+                                              "change": np.packbits([True])}, 4)
+
+
+def test_logfile_name_parsers_equal_the_reference_expression_on_arbitrary_paths():
+    """``path.split("/")[-1].split("__")[0]`` (spatial_temporal_selector.py:79) vs the prefix fast path of
+    pool.logfile_names and the C helper, on generated paths: separators anywhere, repeated prefixes, empty parts,
+    non-ASCII characters, and consecutive frames that share / almost share their prefix."""
+    from hypothesis import given, settings, strategies as st
+    from adsel_b200 import pool as P
+    piece = st.lists(st.sampled_from(list("ab_/-.0") + ["__", "é", "日"]), max_size=12).map("".join)
+    path = st.builds(lambda d, n, t: d + n + t, piece, piece, piece)
+    ext = P._hostext()
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.one_of(path, st.sampled_from(["x/L1__C__1.jpg", "x/L1__C__2.jpg", "x/L1_/C__3.jpg", "y/L1__C__4.jpg",
+                                                     "x/L1__C/5__z.jpg", "L1__C__6.jpg", "", "__", "/"])), min_size=1, max_size=30))
+    def check(paths):
+        infos = [{"cam_front_path": p, "car_from_global": np.eye(4), "gt_names": np.zeros(1, dtype="<U1")} for p in paths]
+        want = [p.split("/")[-1].split("__")[0] for p in paths]
+        assert P.logfile_names(infos) == want
+        if ext:
+            names = ext.extract(infos, 0, len(infos), True)[2]
+            assert list(names) == want
+
+    check()
