@@ -379,7 +379,7 @@ def test_slice_records_survive_the_byte_tensor_all_gather():
     """pool._all_gather_slices packs (lo, n, three optional strings, loc, boxes, packed change bits) into one
     fixed-size byte tensor per rank: whatever the ranks put in comes out, for ragged slices, empty strings,
     non-ASCII names and absent (None) fields."""
-    from hypothesis import given, settings, strategies as st
+    from hypothesis import HealthCheck, given, settings, strategies as st
     from adsel_b200 import pool as P
 
     name = st.one_of(st.none(), st.text(max_size=40))
@@ -399,7 +399,7 @@ def test_slice_records_survive_the_byte_tensor_all_gather():
                          "boxes": rng.integers(0, 200, size=k).astype(np.int32), "change": np.packbits(change), "_bits": change})
         return world, cap, recs
 
-    @settings(max_examples=60, deadline=None)
+    @settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck), database=None)
     @given(worlds())
     def check(case):
         world, cap, recs = case
@@ -429,13 +429,13 @@ def test_logfile_name_parsers_equal_the_reference_expression_on_arbitrary_paths(
     """``path.split("/")[-1].split("__")[0]`` (spatial_temporal_selector.py:79) vs the prefix fast path of
     pool.logfile_names and the C helper, on generated paths: separators anywhere, repeated prefixes, empty parts,
     non-ASCII characters, and consecutive frames that share / almost share their prefix."""
-    from hypothesis import given, settings, strategies as st
+    from hypothesis import HealthCheck, given, settings, strategies as st
     from adsel_b200 import pool as P
     piece = st.lists(st.sampled_from(list("ab_/-.0") + ["__", "é", "日"]), max_size=12).map("".join)
     path = st.builds(lambda d, n, t: d + n + t, piece, piece, piece)
     ext = P._hostext()
 
-    @settings(max_examples=150, deadline=None)
+    @settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck), database=None)
     @given(st.lists(st.one_of(path, st.sampled_from(["x/L1__C__1.jpg", "x/L1__C__2.jpg", "x/L1_/C__3.jpg", "y/L1__C__4.jpg",
                                                      "x/L1__C/5__z.jpg", "L1__C__6.jpg", "", "__", "/"])), min_size=1, max_size=30))
     def check(paths):
