@@ -33,7 +33,8 @@ static int g_fast = -1; /* -1 not validated yet, 0 disabled, 1 enabled */
 static int is_exact_ndarray(PyObject *o) { return strcmp(Py_TYPE(o)->tp_name, "numpy.ndarray") == 0; }
 static int read_cal_fields(PyObject *cal, double m[4][4]) {
     const PyArrayObject_fields *a = (const PyArrayObject_fields *)cal;
-    if (a->nd != 2 || a->dimensions[0] < 3 || a->dimensions[1] < 4) return -1;
+    if (a->nd != 2 || a->dimensions[0] != 4 || a->dimensions[1] != 4) return -1;
+    if (a->strides[0] != 32 || a->strides[1] != 8) return -1;   /* C order only, see read_cal */
     const PyArray_Descr *d = a->descr;
     if (d->type_num != NPY_DOUBLE || d->byteorder == '>') return -1;
     const char *base = a->data;
@@ -46,7 +47,12 @@ static int read_cal_fields(PyObject *cal, double m[4][4]) {
 static int read_cal(PyObject *cal, double m[4][4]) {
     Py_buffer view;
     if (PyObject_GetBuffer(cal, &view, PyBUF_STRIDES | PyBUF_FORMAT) != 0) return -1;
-    int ok = view.ndim == 2 && view.shape[0] >= 3 && view.shape[1] >= 4 && view.itemsize == 8 && view.format &&
+    /* Only the one layout real pools have -- a C-ordered 4x4 float64 matrix -- is accepted: numpy's vector-matrix
+     * product takes a different BLAS kernel (different rounding order) for Fortran-ordered or strided operands, and a
+     * probe of a few dozen frames could not vouch for a pool that mixes layouts.  Anything else raises TypeError and
+     * pool.py evaluates the reference's literal expression instead. */
+    int ok = view.ndim == 2 && view.shape[0] == 4 && view.shape[1] == 4 && view.itemsize == 8 && view.format &&
+             view.strides[0] == 32 && view.strides[1] == 8 &&
              (strcmp(view.format, "d") == 0 || strcmp(view.format, "<d") == 0 || strcmp(view.format, "=d") == 0);
     if (ok) {
         const char *base = (const char *)view.buf;
@@ -55,7 +61,7 @@ static int read_cal(PyObject *cal, double m[4][4]) {
     }
     PyBuffer_Release(&view);
     if (!ok) {
-        PyErr_SetString(PyExc_TypeError, "car_from_global is not a float64 matrix");
+        PyErr_SetString(PyExc_TypeError, "car_from_global is not a C-ordered 4x4 float64 matrix");
         return -1;
     }
     return 0;

@@ -50,6 +50,12 @@ def ego_locations(infos, check: int = 64) -> np.ndarray:
     literal expression and must match bit-for-bit, otherwise the literal loop is used for all.
     """
     cals = [info["car_from_global"] for info in infos]
+    # numpy's vector-matrix product rounds differently for Fortran-ordered / strided operands (another BLAS kernel), so
+    # the batched product below stands for the per-frame one only when every matrix has the layout of the stacked copy
+    uniform = all(isinstance(c, np.ndarray) and c.shape == (4, 4) and c.dtype == np.float64 and c.flags.c_contiguous
+                  for c in cals)
+    if not uniform:
+        return _location_loop(cals)
     try:
         stack = np.concatenate(cals).reshape(-1, 4, 4).astype(np.float64, copy=False)   # [N,4,4]; 3x faster than np.stack
     except ValueError:

@@ -447,3 +447,53 @@ def test_logfile_name_parsers_equal_the_reference_expression_on_arbitrary_paths(
             assert list(names) == want
 
     check()
+
+
+def test_extraction_on_unusual_pose_arrays_and_missing_keys():
+    """Whatever memory layout the 4x4 pose has (Fortran order, a transposed view, a slice of a larger array, a read-only
+    array) the extracted ego location is the reference expression bit for bit -- through the C helper when it accepts
+    the array, through the python path otherwise; a frame without the keys the reference reads raises KeyError."""
+    from adsel_b200 import pool as P
+    rng = np.random.default_rng(8)
+    base = [rng.normal(size=(4, 4)) * 10.0 ** rng.integers(-3, 4) for _ in range(40)]
+    big = rng.normal(size=(40, 6, 6))
+    ro = rng.normal(size=(4, 4))
+    ro.setflags(write=False)
+    variants = {
+        "fortran": [np.asfortranarray(m) for m in base],
+        "transposed_view": [m.T for m in base],
+        "slice_of_larger": [big[i, 1:5, 2:6] for i in range(40)],
+        "readonly": [ro] * 3,
+        "mixed": [np.asfortranarray(m) if i % 2 else m for i, m in enumerate(base)],
+    }
+    for name, mats in variants.items():
+        infos = [{"cam_front_path": f"d/L{i // 7}__C__{i}.jpg", "car_from_global": m, "gt_names": np.zeros(i % 4, dtype="<U3")}
+                 for i, m in enumerate(mats)]
+        want = np.stack([(-(m[:3, 3].T @ m[:3, :3]))[:2] for m in mats])
+        names, loc, boxes = P.extract_slice(infos)
+        assert np.array_equal(loc.view(np.uint64), want.view(np.uint64)), name
+        assert names == [f"L{i // 7}" for i in range(len(mats))] and boxes.tolist() == [i % 4 for i in range(len(mats))]
+    # the case a probe cannot see: 1,000 C-ordered poses and ONE Fortran-ordered pose at an index that is not probed
+    # (numpy rounds f[:3,3].T @ f[:3,:3] differently for that layout in ~40 % of random matrices)
+    n = 1000
+    probes = set(np.unique(np.linspace(0, n - 1, num=64).astype(np.int64)).tolist())
+    odd = next(i for i in range(400, n) if i not in probes)
+    for seed in range(40):                                   # find values whose result really depends on the layout
+        m = np.random.default_rng(seed).normal(size=(4, 4))
+        f = np.asfortranarray(m)
+        if not np.array_equal((m[:3, 3].T @ m[:3, :3])[:2].view(np.uint64), (f[:3, 3].T @ f[:3, :3])[:2].view(np.uint64)):
+            break
+    else:
+        pytest.skip("this numpy build rounds both layouts alike")
+    mats = [rng.normal(size=(4, 4)) for _ in range(n)]
+    mats[odd] = f
+    infos = [{"cam_front_path": f"d/L{i // 50}__C__{i}.jpg", "car_from_global": mm, "gt_names": np.zeros(1)} for i, mm in enumerate(mats)]
+    want = np.stack([(-(mm[:3, 3].T @ mm[:3, :3]))[:2] for mm in mats])
+    assert np.array_equal(P.extract_slice(infos)[1].view(np.uint64), want.view(np.uint64))
+    assert np.array_equal(P.ego_locations(infos).view(np.uint64), want.view(np.uint64))
+    good = [{"cam_front_path": "d/L__1", "car_from_global": np.eye(4), "gt_names": np.zeros(1)} for _ in range(5)]
+    for key in ("cam_front_path", "car_from_global", "gt_names"):
+        bad = [dict(g) for g in good]
+        del bad[3][key]
+        with pytest.raises(KeyError):
+            P.extract_slice(bad)
