@@ -497,3 +497,43 @@ def test_extraction_on_unusual_pose_arrays_and_missing_keys():
         del bad[3][key]
         with pytest.raises(KeyError):
             P.extract_slice(bad)
+
+
+def test_cli_loads_reference_style_configs_without_the_detector_stack(tmp_path):
+    """The reference's config files import detector-stack helpers at module level (examples/active/cbgs_*.py:4-5,166,189).
+    tools/active_select.py executes them with placeholders when ``det3d`` is not importable, reads ``selector`` only,
+    and leaves no fake modules behind; other import errors still surface."""
+    import sys
+    spec = importlib.util.spec_from_file_location("adsel_cli_cfg", os.path.join(ROOT, "tools", "active_select.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    cfg = tmp_path / "cbgs_like.py"
+    cfg.write_text(
+        "import itertools\nimport logging\n\n"
+        "from det3d.builder import build_box_coder\nfrom det3d.utils.config_tool import get_downsample_factor\n\n"
+        "tasks = [dict(num_class=1, class_names=['car'])]\n"
+        "class_names = list(itertools.chain(*[t['class_names'] for t in tasks]))\n"
+        "box_coder = dict(type='ground_box3d_coder', n_dim=9)\n"
+        "model = dict(neck=dict(ds_layer_strides=[2, 2]), backbone=dict(ds_factor=8))\n"
+        "assigner = dict(box_coder=build_box_coder(box_coder), out_size_factor=get_downsample_factor(model),\n"
+        "                logger=logging.getLogger('RPN'))\n"
+        "train_anno = '/data/infos_train_10sweeps_withvelo.pkl'\n"
+        "selector = dict(type='SpatialTemporalSelector', budget=4800, buffer_file='/data/b.json', infos_origin=train_anno,\n"
+        "                logs_file='/data/log.json')\n")
+    assert "det3d" not in sys.modules
+    got = cli.load_selector_cfg(str(cfg))
+    assert got == dict(type="SpatialTemporalSelector", budget=4800, buffer_file="/data/b.json",
+                       infos_origin="/data/infos_train_10sweeps_withvelo.pkl", logs_file="/data/log.json")
+    assert not [m for m in sys.modules if m == "det3d" or m.startswith("det3d.")]
+    bad = tmp_path / "bad.py"
+    bad.write_text("import module_that_does_not_exist_anywhere\nselector = dict()\n")
+    with pytest.raises(ModuleNotFoundError):
+        cli.load_selector_cfg(str(bad))
+    none = tmp_path / "none.py"
+    none.write_text("x = 1\n")
+    with pytest.raises(KeyError):
+        cli.load_selector_cfg(str(none))
+    ref_cfg = "/root/reference/examples/active/cbgs_spatial_temporal.py"
+    if os.path.exists(ref_cfg):                      # the unmodified file, where the reference tree is present
+        sel = cli.load_selector_cfg(ref_cfg)
+        assert sel["type"] == "SpatialTemporalSelector" and sel["budget"] == 4800 and sel["infos_origin"].endswith(".pkl")

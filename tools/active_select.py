@@ -8,16 +8,20 @@ selector from ``cfg.selector``, call ``select_samples(local_rank=...)`` and ``du
 the data-only selectors (:119-148); that part is skipped.  Seeds as in :76-80.
 
 The config is a python file that defines ``selector = dict(type=..., budget=..., buffer_file=...,
-infos_origin=..., logs_file=...)`` (the selector block of examples/active/cbgs_spatial_temporal.py:361-367;
-the reference's full configs cannot be imported without the detector stack), or a .json/.yaml file
-with a top-level ``selector`` mapping.
+infos_origin=..., logs_file=...)`` -- the reference's own config files work unmodified
+(examples/active/cbgs_spatial_temporal.py:361-367 is such a block; the two detector-stack helpers those files
+import are replaced by placeholders when ``det3d`` is not installed, see ``run_config_file``) -- or a
+.json/.yaml file with a top-level ``selector`` mapping.
 """
 import argparse
+import importlib.abc
+import importlib.machinery
 import logging
 import os
 import random
 import runpy
 import sys
+import types
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
@@ -46,9 +50,55 @@ def parse_args(argv=None):
     return args
 
 
+class _PlaceholderModule(types.ModuleType):
+    """Stands in for ``det3d`` and its sub-modules while a reference config file is executed outside the reference
+    tree: every attribute is a function that returns its first argument (``build_box_coder(cfg) -> cfg``,
+    ``get_downsample_factor(model) -> model``), which is all the detector half of such a config needs to evaluate."""
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return lambda *a, **k: a[0] if a else None
+
+
+class _PlaceholderFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname == "det3d" or fullname.startswith("det3d."):
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _PlaceholderModule(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+def run_config_file(path):
+    """Execute a python config like ``Config.fromfile`` does (det3d/torchie/utils/config.py).  The reference's own
+    configs (examples/active/cbgs_*.py) import two helpers of the detector stack at module level
+    (``det3d.builder.build_box_coder``, ``det3d.utils.config_tool.get_downsample_factor``); when ``det3d`` is not
+    importable they are replaced by placeholders for the duration of the execution -- only ``selector`` is read."""
+    try:
+        return runpy.run_path(path)
+    except ModuleNotFoundError as e:
+        if not (e.name or "").split(".")[0] == "det3d":
+            raise
+    finder = _PlaceholderFinder()
+    sys.meta_path.insert(0, finder)
+    try:
+        return runpy.run_path(path)
+    finally:
+        sys.meta_path.remove(finder)
+        for name in [m for m in sys.modules if m == "det3d" or m.startswith("det3d.")]:
+            if isinstance(sys.modules[name], _PlaceholderModule):
+                del sys.modules[name]
+
+
 def load_selector_cfg(path):
     if path.endswith(".py"):
-        cfg = runpy.run_path(path)
+        cfg = run_config_file(path)
     else:
         cfg = fileio.load(path)
     if "selector" not in cfg:
