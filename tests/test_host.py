@@ -537,3 +537,46 @@ def test_cli_loads_reference_style_configs_without_the_detector_stack(tmp_path):
     if os.path.exists(ref_cfg):                      # the unmodified file, where the reference tree is present
         sel = cli.load_selector_cfg(ref_cfg)
         assert sel["type"] == "SpatialTemporalSelector" and sel["budget"] == 4800 and sel["infos_origin"].endswith(".pkl")
+
+
+def test_reference_registry_builds_the_drop_in_selector(pools, tmp_path):
+    """INTEGRATION.md §1, executed: the re-registration stub placed in the reference's
+    det3d/selectors/spatial_temporal_selector.py registers this package's class in the REFERENCE's own ``SELECTORS``
+    registry, and the reference's own ``build_selector`` (det3d/selectors/builder.py:8-9 -> det3d/utils/registry.py:49-80)
+    constructs it from the config block of examples/active/cbgs_spatial_temporal.py:361-367.  Needs the reference tree
+    (this container only)."""
+    import re
+    import sys
+    import reference_loader
+    if not reference_loader.reference_available():
+        pytest.skip("reference tree not present")
+    saved = {k: v for k, v in sys.modules.items() if k == "det3d" or k.startswith("det3d.")}
+    saved_path = list(sys.path)
+    try:
+        reference_loader.load_reference_selectors()                     # shims + the empty det3d.selectors package object
+        md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+        stub = re.search(r"```python\n(# det3d/selectors/spatial_temporal_selector.py  \(replacement body\)\n.*?)```", md, re.S).group(1)
+        stub = stub.replace('sys.path.insert(0, "/path/to/this/repo")', f"sys.path.insert(0, {ROOT!r})")
+        # the stub replaces the module the reference_loader imported: a fresh registry entry is needed for the same name
+        from det3d.selectors.registry import SELECTORS as REF_SELECTORS
+        REF_SELECTORS.module_dict.pop("SpatialTemporalSelector", None)
+        mod = type(sys)("det3d.selectors.spatial_temporal_selector")
+        mod.__package__ = "det3d.selectors"
+        exec(compile(stub, "INTEGRATION.md#stub", "exec"), mod.__dict__)
+        from det3d.selectors.builder import build_selector as ref_build_selector
+        pl = pools("P300")
+        buf = str(tmp_path / "buffer.json")
+        fileio.dump({"0": []}, buf, indent=4)
+        sel = ref_build_selector(dict(type="SpatialTemporalSelector", budget=600, buffer_file=buf,
+                                      infos_origin=pl["paths"]["infos"], logs_file=pl["paths"]["logs"]))
+        assert isinstance(sel, SpatialTemporalSelector) and type(sel).__module__ == "det3d.selectors.spatial_temporal_selector"
+        assert REF_SELECTORS.get("SpatialTemporalSelector") is type(sel)
+        assert sel.current_budget == "600" and sel.normalize == "exp" and sel.k == 8 and sel.cost_b == 0.04
+        with pytest.raises(TypeError):
+            ref_build_selector(dict(type="SpatialTemporalSelector", budget=1, buffer_file=buf, infos_origin=pl["paths"]["infos"],
+                                    no_such_kwarg=1))
+    finally:
+        for k in [k for k in sys.modules if k == "det3d" or k.startswith("det3d.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        sys.path[:] = saved_path
