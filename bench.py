@@ -126,8 +126,21 @@ def cpu_port_once(infos, logs, budget):
     return time.perf_counter() - t0, sel
 
 
-def cpu_reference_once(paths, budget, tmp):
-    """The unmodified reference selector (only where /root/reference exists)."""
+REF_SAMPLE_FRAMES = 4000        # frames of the bounded reference sample (the first ones of the pool)
+
+
+def bench_config(world, n):
+    """The ``config`` object of BOTH arms (the reference arm runs on this arm's config, bounded per step)."""
+    return {"workload": workload_name(world), "pool_frames": n, "budget": BUDGET,
+            "l2": "flushed between timed iterations (256 MiB write)",
+            "parallelism": ("1 process per GPU; kNN rows and neighbour lists built by the rank that owns the source frames "
+                            "and stored into every rank's arena over NVLink, greedy loop resident in one GPU's shared memory "
+                            "(replicated on every rank)") if world > 1 else "single GPU"}
+
+
+def cpu_reference_once(paths, budget, tmp, store=None):
+    """The unmodified reference selector (/root/reference, or its byte-for-byte copy oracle/_ref on the GPU box).
+    ``store``: path of the reference's own distance cache -- a second call with the same path is its WARM run."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import contextlib
     import io
@@ -136,7 +149,8 @@ def cpu_reference_once(paths, budget, tmp):
     cls = load_reference_selectors()["SpatialTemporalSelector"]
     buf = os.path.join(tmp, f"ref_buffer_{time.time_ns()}.json")
     json.dump({"0": []}, open(buf, "w"))
-    store = os.path.join(tmp, f"ref_store_{time.time_ns()}.npy")
+    keep = store is not None
+    store = store or os.path.join(tmp, f"ref_store_{time.time_ns()}.npy")
     random.seed(3407)
     sel = cls(budget=budget, buffer_file=buf, infos_origin=paths["infos"], logs_file=paths["logs"],
               distance_store_file=store, logger=logging.getLogger("ref"))
@@ -144,9 +158,58 @@ def cpu_reference_once(paths, budget, tmp):
     with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
         sel.select_samples(local_rank=0)
     dt = time.perf_counter() - t0
-    if os.path.exists(store):
+    if os.path.exists(store) and not keep:
         os.remove(store)
     return dt, sel.get_selected_samples()[sel.current_budget]
+
+
+def reference_sample(paths, infos, tmp, frames):
+    """Bounded sample of the workload for the CPU arms: the first ``frames`` frames of the same pool (same logs file),
+    budget scaled by the same factor, through the same selector.  The reference's geodesic APSP is superlinear in the
+    pool size (82 % of its time at 28,130 frames), so frames/s measured on the sample OVERSTATES the
+    reference's throughput on the full pool: ratios against it are conservative."""
+    from adsel_b200 import fileio
+    m = min(int(frames), len(infos))
+    sub = os.path.join(tmp, f"ref_sample_{m}.pkl")
+    if not os.path.exists(sub):
+        fileio.dump(infos[:m], sub)
+    return {"infos": sub, "logs": paths["logs"]}, m, max(60, int(round(BUDGET * m / len(infos))))
+
+
+def reference_full_workload(which, timeout_s):
+    """One FULL-size selection of the unmodified reference (28,130 frames, budget 4800) in a child process: cold
+    (no distance cache: kNN, dense APSP, maps, loop) and warm (cached geodesic map), SURVEY.md §8d.  Bounded by a
+    timeout; needs ~32 GB of host RAM.  Returns seconds or a reason string."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--full-once", which]
+    try:
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return f"no result within {timeout_s} s"
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    return f"child exited {out.returncode}"
+
+
+def run_full_once(which):
+    """Child of reference_full_workload(): prints {"cold_s": ..} and, for ``both``, {"warm_s": ..} as well."""
+    import adsel_b200  # noqa: F401
+    res = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        _, paths = make_pool(tmp, 1)
+        store = os.path.join(tmp, "dijkstra_distance_map.npy")
+        t, sel = cpu_reference_once(paths, BUDGET, tmp, store=store)
+        res["cold_s"], res["selected_frames"] = t, len(sel)
+        gpath = os.path.join(ROOT, "tests", "golden", "P28K_st.json")
+        if os.path.exists(gpath):
+            res["identical_to_committed_golden"] = sel == json.load(open(gpath))["cases"]["st_exp_sum_4800"]["selected_index"][str(BUDGET)]
+        print(json.dumps(res), flush=True)
+        if which == "both":
+            t, sel2 = cpu_reference_once(paths, BUDGET, tmp, store=store)
+            res["warm_s"] = t
+            res["warm_identical"] = sel2 == sel
+            print(json.dumps(res), flush=True)
+    return 0
 
 
 def run_reference_arm(args):
@@ -161,47 +224,48 @@ def run_reference_arm(args):
     with tempfile.TemporaryDirectory() as tmp:
         spec, paths = make_pool(tmp, world)
         infos, logs = fileio.load(paths["infos"]), fileio.load(paths["logs"])
-        use_ref = reference_available() and not args.port and world == 1   # the dense reference needs 4 x N^2 x 8 B
+        n = spec.n_frames
+        use_ref = reference_available() and not args.port
         kind = "reference" if use_ref else "port"
-
-        # N > 1 (pool of N x 28,130 frames): a full-budget selection of the port can take many minutes, so the timed
-        # sample is the largest budget prefix of the same selection (same graph build, first greedy steps) that a
-        # budget-300 probe predicts to finish within ~150 s.  With a prefix the reported frames/s is an UPPER bound
-        # of the CPU implementation's throughput on this workload.
-        sample_budget = BUDGET
-        if world > 1:
-            t_probe = cpu_port_once(infos, logs, 300)[0]
-            sample_budget = next((b for b in (4800, 2400, 1200, 600) if t_probe * b / 300.0 <= 150.0), 600)
+        # Each step is a BOUNDED sample of the workload: the first m frames of the pool through the same selector, m
+        # chosen from a probe so that warm-up + steps end within ~4 minutes (the reference needs minutes per selection
+        # of the full pool and cannot allocate its N x N maps beyond ~60 k frames).
+        runs = args.warmup + args.steps
+        probe_paths, m0, b0 = reference_sample(paths, infos, tmp, 2000)
+        t0 = cpu_reference_once(probe_paths, b0, tmp)[0] if use_ref else cpu_port_once(infos[:m0], logs, b0)[0]
+        m = int(min(REF_SAMPLE_FRAMES, max(1000.0, m0 * (240.0 / max(runs * t0, 1e-3)) ** (1 / 2.2))))
+        sample_paths, m, sample_budget = reference_sample(paths, infos, tmp, m)
 
         def once():
             if use_ref:
-                return cpu_reference_once(paths, sample_budget, tmp)[0]
-            return cpu_port_once(infos, logs, sample_budget)[0]
+                return cpu_reference_once(sample_paths, sample_budget, tmp)[0]
+            return cpu_port_once(infos[:m], logs, sample_budget)[0]
 
-        # bounded: the whole run stays within a few minutes whatever K/W the driver passes
-        t_first = once() if (args.warmup > 0 and world == 1) else None
-        est = t_first if t_first is not None else (150.0 if use_ref else 15.0 * world)
-        steps = max(1, min(args.steps, int(240.0 / max(est, 1e-3))))
-        warm_done = 1 if t_first is not None else 0
-        for _ in range(min(args.warmup, 1 if use_ref else 2) - warm_done if world == 1 else 0):
+        for _ in range(args.warmup):
             once()
-            warm_done += 1
-        times = [once() for _ in range(steps)]
+        times = [once() for _ in range(args.steps)]
+        full = None
+        if use_ref and world == 1 and not args.no_full_reference:
+            full = reference_full_workload("both", 900)
     sec = sum(times) / len(times)
-    value = spec.n_frames / sec
+    value = m / sec
+    sample = (f"each step = the {'unmodified reference' if use_ref else 'oracle port of the'} SpatialTemporalSelector on the first {m} of the "
+              f"{n} frames of the pool, budget {sample_budget} (= {BUDGET} x {m}/{n}), cold, {sec:.2f} s per step; frames/s on "
+              f"this sub-pool OVERSTATES the reference on the full pool (its all-pairs Dijkstra is superlinear); "
+              f"single-threaded numpy/scipy; host has {os.cpu_count()} cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm_done, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(world), "pool_frames": spec.n_frames, "budget": BUDGET},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": kind,
-                         "sample": (f"full workload, {steps} timed selection(s)" if world == 1 else
-                                    (f"full workload on the {spec.n_frames}-frame pool, {steps} run(s)" if sample_budget == BUDGET else
-                                     f"budget-{sample_budget} prefix of the budget-{BUDGET} selection on the {spec.n_frames}-frame pool, "
-                                     f"{steps} run(s): an upper bound of the CPU throughput")) +
-                                   f"; single-threaded numpy/scipy; host has {os.cpu_count()} cores"},
+        "config": bench_config(world, n),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": kind, "sample": sample,
+                         "full_workload": full},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if isinstance(full, dict) and full.get("cold_s"):
+        line["cpu_baseline"]["full_workload_frames_per_s_cold"] = n / full["cold_s"]
+        if full.get("warm_s"):
+            line["cpu_baseline"]["full_workload_frames_per_s_warm"] = n / full["warm_s"]
     print(json.dumps(line), flush=True)
     return 0
 
@@ -624,6 +688,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--port", action="store_true", help="--impl reference: force the oracle port even if /root/reference exists")
+    ap.add_argument("--full-once", default=None, choices=["cold", "both"], help=argparse.SUPPRESS)
+    ap.add_argument("--no-full-reference", action="store_true",
+                    help="--impl reference: skip the one full-size cold + warm selection of the unmodified reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bev", action="store_true", help="skip the BEV-descriptor extras (histogram / tcgen05 tiles)")
     ap.add_argument("--bev-scale", type=int, default=1, help="N > 1 only: also run the dense BEV path on a pool of "
@@ -631,6 +698,8 @@ def main():
     args = ap.parse_args()
     logging.basicConfig(level=logging.WARNING)
     if args.impl == "reference":
+        if args.full_once:
+            return run_full_once(args.full_once)
         return run_reference_arm(args)
     return run_b200_arm(args)
 

@@ -42,19 +42,42 @@ class _BuildLock:
         self._f.close()
 
 
+def _headers():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(os.path.dirname(CSRC), "..", "include", "adsel_b200.h"))
+    return [d for d in deps if os.path.exists(d)]
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu for sm_100a into one shared library; returns its path.  The library is written to a
-    temporary name and renamed into place, under a lock, so concurrent ranks never see a partial file."""
+    """Compile every .cu for sm_100a (one nvcc per source, in parallel, objects cached under csrc/build/ and
+    redone only when the source or a header is newer) and link them into one shared library; returns its path.
+    The library is written to a temporary name and renamed into place, under a lock, so concurrent ranks never
+    see a partial file."""
     if not force and not needs_build():
         return LIB
     with _BuildLock():
         if not force and not needs_build():          # another process built it while this one waited
             return LIB
+        from concurrent.futures import ThreadPoolExecutor
         nvcc = os.environ.get("NVCC", "nvcc")
+        objdir = os.path.join(CSRC, "build")
+        os.makedirs(objdir, exist_ok=True)
+        hdr_time = max(os.path.getmtime(d) for d in _headers())
+        compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+        def compile_one(src):
+            obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+            if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
+                    and os.path.getmtime(obj) > hdr_time):
+                return obj
+            subprocess.check_call([nvcc] + compile_flags + ["-c", "-o", obj, src], cwd=CSRC)
+            return obj
+
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+            objs = list(ex.map(compile_one, _sources()))
         tmp = f"{LIB}.tmp{os.getpid()}"
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources() + ["-lcuda"]
         try:
-            subprocess.check_call(cmd, cwd=CSRC)
+            subprocess.check_call([nvcc, "-shared", "-o", tmp] + objs + ["-lcuda"], cwd=CSRC)
             os.replace(tmp, LIB)
         finally:
             if os.path.exists(tmp):

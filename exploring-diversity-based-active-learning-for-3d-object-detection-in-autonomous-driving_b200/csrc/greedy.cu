@@ -44,7 +44,7 @@ constexpr int MAX_BLKS = 9800;        // 20 B of shared memory per block + 32 KB
 
 struct GreedyArgs {
     int n, nblk, lo, hi, blk_lo, blk_hi, tl_n, sel_words;
-    int csize, cta_cols;   // cluster variant: CTAs per cluster, columns per CTA (multiple of 256)
+    int csize, cta_cols, r_nblk;   // resident variant: CTAs per cluster, columns and blocks per CTA
     int spatial, temporal, aggregate, groups_contiguous, pull;
     double lambda_t, s_far, t_far;
     double cost_b, cost_f, cost_start, budget;
@@ -462,276 +462,468 @@ __global__ void __launch_bounds__(NT, 1) greedy_select_kernel(const GreedyArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cluster variant: fps lives in SHARED memory, split over the CTAs of one thread-block cluster.
+// Resident variant (the default whenever the columns fit): fps lives in SHARED memory.
 //
-// In the single-CTA kernel above the min-distance vector lives in L2 and every step pays an
-// atomicMin (RED) round trip followed by a re-read of the dirtied blocks -- the longest link of the
-// dependency chain.  Here the rank's columns are cut into `csize` contiguous pieces, one per CTA of a
-// cluster (csize = 2 for the 28,130-frame pool: 110 KB of shared memory each), so that
-//   * a row update is a plain shared-memory min (every touched column is written by exactly one thread:
-//     list entries are unique per list, the group is applied in a second phase),
-//   * the arg-max is a scan of the CTA's own shared-memory slice (no dirty tracking, no block maxima),
-//   * the CTAs exchange their local maxima through distributed shared memory with the mailbox protocol of
-//     comm.cuh (tagged self-validating 8-byte words, st.shared::cluster + poll; no cluster barrier in the
-//     loop, so L1 -- which holds the prefetched frame records and the lists -- is never flushed),
-//   * every CTA does the cost bookkeeping redundantly; cluster rank 0 writes the results and, when the
-//     pool is sharded over GPUs, posts the rank's record to the other ranks while every CTA polls the
-//     rank's mailbox.
+// In the kernel above the min-distance vector lives in L2, so a step pays four dependent L2 round
+// trips (frame record, list entries, RED, re-read of the dirtied blocks) and three CTA barriers behind
+// which one warp does the serial work.  Here the columns are held in shared memory -- by one CTA when
+// they fit (28,130 frames * 8 B = 225 KB of the 227 KB a CTA may use, 256-frame blocks), else split over
+// the CTAs of a thread-block cluster (up to 16: 440 k frames) -- and a step is organised so that its
+// dependent chain is ONE L2 round trip (the winner's list entries) plus shared-memory work:
+//   * every thread keeps the bookkeeping state (cost, count, current frame) in registers and every warp
+//     does the final arg-max over the block maxima redundantly, so the winner needs no broadcast and no
+//     barrier of its own: two CTA barriers per step plus one that hides under the list load;
+//   * a row update is a plain shared-memory min.  Group (temporal) entries are written while the list
+//     loads are in flight, list entries after a barrier (list values of same-group frames are <= the
+//     group values, so the order makes the plain writes exact); with the "exp" normalisation the group
+//     phase only visits |j - src| < 38, the part of the temporal LUT that differs from the far value;
+//   * a block's maximum can only change when the entry that IS its maximum is lowered (entries only
+//     decrease), so only those blocks are re-reduced: 1-2 per step instead of every touched block;
+//   * the record of every block's best frame (list range, group range, box count) is cached in shared
+//     memory when the block is refreshed -- fetched asynchronously and stored one phase later, validated
+//     by the frame index -- so the winner's record is a shared-memory read, not an L2 round trip;
+//   * cluster: warp 0 of every CTA posts its local maximum to every CTA through distributed shared
+//     memory (tagged self-validating words, comm.cuh's protocol) and every warp polls its own CTA's
+//     slots; every CTA does the bookkeeping redundantly, CTA 0 writes the results.
 // ---------------------------------------------------------------------------------------------
 namespace cg = cooperative_groups;
 
-constexpr int CLUSTER_MAX = 8;                  // portable cluster size
+constexpr int CLUSTER_MAX = 16;                 // non-portable cluster size (opt-in), 8 is the portable limit
 constexpr int XSLOT_WORDS = 4;
+constexpr int RES_NT = 256;                     // threads of a resident CTA
+
+struct BlkRec {           // cached FrameRec of a block's best frame (shared memory, 28 B)
+    unsigned idx;         // frame the record belongs to (0xffffffff: none)
+    int list_len;
+    unsigned off_lo, off_hi;
+    int e0, e1, n_boxes;
+};
 
 __device__ __forceinline__ unsigned long long ld_volatile_shared(const unsigned long long *p) {
     return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
 
-// Warp-level exchange of the CTAs' local maxima through distributed shared memory.  xslot: this CTA's
-// [2][CLUSTER_MAX][XSLOT_WORDS] slots; remote[r]: the same array in CTA r's shared memory.
+// Issues the two 16-byte loads of a frame record without consuming them (the caller stores them a phase later).
+__device__ __forceinline__ void ldg_rec_async(const FrameRec *p, uint4 &lo, uint4 &hi) {
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "l"(p));
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(reinterpret_cast<const char *>(p) + 16));
+}
+
+// Exchange of the CTAs' local maxima through distributed shared memory.  xslot: this CTA's
+// [2][CLUSTER_MAX][XSLOT_WORDS] slots; remote[r]: the same array in CTA r's shared memory.  Warp 0 posts,
+// EVERY warp polls the own slots and reduces, so all threads of all CTAs hold the winner without a barrier.
 __device__ __forceinline__ Best cluster_exchange(unsigned long long *xslot, unsigned long long *const *remote, int crank,
-                                                 int csize, unsigned tag, Best local) {
+                                                 int csize, unsigned tag, Best local, bool poster) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int peer = lane / 3, word = lane - 3 * peer;
     const size_t parity_off = (size_t)(tag & 1u) * CLUSTER_MAX * XSLOT_WORDS;
-    const bool active = lane < 3 * csize;
-    if (active) {
-        const unsigned long long payload = word == 0 ? (local.v >> 32) : word == 1 ? (local.v & 0xffffffffull)
-                                                                                  : (unsigned long long)(unsigned)local.i;
-        remote[peer][parity_off + (size_t)crank * XSLOT_WORDS + word] = (payload << 32) | tag;   // st.shared::cluster
-    }
-    unsigned long long got = 0;
-    if (active) {
-        const unsigned long long *p = xslot + parity_off + (size_t)peer * XSLOT_WORDS + word;
-        while (true) {
-            got = ld_volatile_shared(p);
-            if ((unsigned)got == tag) break;
+    const int nwords = 3 * csize;   // <= 48
+    if (poster) {
+        for (int l = lane; l < nwords; l += 32) {
+            const int peer = l / 3, word = l - 3 * peer;
+            const unsigned long long payload = word == 0 ? (local.v >> 32) : word == 1 ? (local.v & 0xffffffffull)
+                                                                                      : (unsigned long long)(unsigned)local.i;
+            remote[peer][parity_off + (size_t)crank * XSLOT_WORDS + word] = (payload << 32) | tag;   // st.shared::cluster
         }
     }
-    const int src = lane < csize ? 3 * lane : 0;
-    const unsigned long long hi = __shfl_sync(full, got, src) >> 32;
-    const unsigned long long lo = __shfl_sync(full, got, src + 1) >> 32;
-    const unsigned idx = (unsigned)(__shfl_sync(full, got, src + 2) >> 32);
+    unsigned long long got0 = 0, got1 = 0;
+    if (lane < nwords) {
+        const unsigned long long *p = xslot + parity_off + (size_t)(lane / 3) * XSLOT_WORDS + (lane % 3);
+        do got0 = ld_volatile_shared(p);
+        while ((unsigned)got0 != tag);
+    }
+    if (lane + 32 < nwords) {
+        const int l = lane + 32;
+        const unsigned long long *p = xslot + parity_off + (size_t)(l / 3) * XSLOT_WORDS + (l % 3);
+        do got1 = ld_volatile_shared(p);
+        while ((unsigned)got1 != tag);
+    }
+    // lane r < csize assembles CTA r's record from words 3r, 3r+1, 3r+2 (word w sits in lane w & 31, register w >> 5)
+    unsigned part[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int w = lane < csize ? 3 * lane + q : 0;
+        const unsigned long long a0 = __shfl_sync(full, got0, w & 31), a1 = __shfl_sync(full, got1, w & 31);
+        part[q] = (unsigned)((w >> 5 ? a1 : a0) >> 32);
+    }
     Best x{0ull, 0x7fffffff};
     if (lane < csize) {
-        x.v = (hi << 32) | lo;
-        x.i = (int)idx;
+        x.v = ((unsigned long long)part[0] << 32) | part[1];
+        x.i = (int)part[2];
     }
     return warp_best(x);
 }
 
-template <int NT, bool SHARDED>
-__global__ void __launch_bounds__(NT, 1) greedy_cluster_kernel(const GreedyArgs a, const CommView comm) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const int crank = (int)cluster.block_rank(), csize = a.csize;
-    const int c_lo = min(a.lo + crank * a.cta_cols, a.hi), c_hi = min(c_lo + a.cta_cols, a.hi);
-    const int c_len = c_hi - c_lo;
+#define RPROF_MARK(slot)                                  \
+    if (PROFILE && threadIdx.x == 0) {                     \
+        const int dep = *(volatile int *)&sh.err;    /* consume shared memory: a deferred barrier blocks here */ \
+        long long now;                                    \
+        asm volatile("{\n.reg .b32 t;\nmov.b32 t, %1;\nmov.u64 %0, %%clock64;\n}" : "=l"(now) : "r"(dep) : "memory"); \
+        prof_acc[slot] += (unsigned long long)(now - prof_t); \
+        prof_t = now;                                     \
+    }
+
+struct ResidentShared {
+    int ndirty[2];
+    int err, err_frame, sat;
+};
+
+template <int RB, bool CLUSTER, bool PROFILE>
+__global__ void __launch_bounds__(RES_NT, 1) greedy_resident_kernel(const GreedyArgs a) {
+    constexpr int NT = RES_NT, NW = NT / 32;
+    unsigned long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = PROFILE ? clock64() : 0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int crank = 0;
+    if (CLUSTER) crank = (int)cg::this_cluster().block_rank();
+    const int csize = CLUSTER ? a.csize : 1;
+    const int c_lo = min(a.lo + crank * a.cta_cols, a.hi), c_hi = min(c_lo + a.cta_cols, a.hi), c_len = c_hi - c_lo;
+    const int nblk = a.r_nblk;   // blocks of a CTA's slice (cta_cols / RB); those at or beyond c_len are empty
+    const bool writer = crank == 0 && tid == 0;
+
     extern __shared__ unsigned long long greedy_smem[];
-    unsigned long long *fps_s = greedy_smem;                                       // [cta_cols]
-    double *tl = reinterpret_cast<double *>(fps_s + a.cta_cols);                   // [tl_n]
-    unsigned long long *xslot = reinterpret_cast<unsigned long long *>(tl + a.tl_n);   // [2][CLUSTER_MAX][XSLOT_WORDS]
-    unsigned *selbits = reinterpret_cast<unsigned *>(xslot + 2 * CLUSTER_MAX * XSLOT_WORDS);   // [sel_words]
-    __shared__ GreedyShared sh;
-    __shared__ Best wres[NT / 32];
-    __shared__ unsigned long long *remote[CLUSTER_MAX];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int NWARPS = NT / 32;
+    unsigned long long *fps_s = greedy_smem;                                         // [cta_cols]
+    unsigned long long *blk_val = fps_s + a.cta_cols;                                // [nblk]
+    unsigned long long *xslot = blk_val + nblk;                                      // CLUSTER: [2][CLUSTER_MAX][XSLOT_WORDS]
+    unsigned long long **remote = reinterpret_cast<unsigned long long **>(xslot + (CLUSTER ? 2 * CLUSTER_MAX * XSLOT_WORDS : 0));
+    double *tl = reinterpret_cast<double *>(remote + (CLUSTER ? CLUSTER_MAX : 0));   // [tl_n] head of the temporal LUT
+    int *blk_idx = reinterpret_cast<int *>(tl + a.tl_n);                             // [nblk]
+    int *dirty = blk_idx + nblk;                                                     // [nblk]
+    int *dirty_list = dirty + nblk;                                                  // [nblk]
+    BlkRec *blk_rec = reinterpret_cast<BlkRec *>(dirty_list + nblk);                 // [nblk]
+    unsigned *selbits = reinterpret_cast<unsigned *>(blk_rec + nblk);                // [sel_words] (0 words: private global bytes)
+    unsigned char *sel_bytes = a.is_selected + (size_t)crank * a.n;                  // this CTA's private copy of the flags
+    __shared__ ResidentShared sh;
+
     const int tl_n = a.tl_n;
-    ExchangeLane xlane;
-    if (SHARDED) xlane = make_exchange_lane(comm);
-
     const unsigned long long far_bits = a.far_bits;
-    for (int i = threadIdx.x; i < a.cta_cols; i += NT) fps_s[i] = far_bits;
-    for (int d = threadIdx.x; d < tl_n; d += NT) tl[d] = a.tlut[d];
-    for (int wd = threadIdx.x; wd < a.sel_words; wd += NT) selbits[wd] = 0u;
-    for (int i = threadIdx.x; i < 2 * CLUSTER_MAX * XSLOT_WORDS; i += NT) xslot[i] = 0ull;
-    if (threadIdx.x < CLUSTER_MAX)
-        remote[threadIdx.x] = threadIdx.x < csize ? cluster.map_shared_rank(xslot, threadIdx.x) : nullptr;
+    for (int i = tid; i < a.cta_cols; i += NT) fps_s[i] = far_bits;
+    for (int d = tid; d < tl_n; d += NT) tl[d] = a.tlut[d];
+    for (int wd = tid; wd < a.sel_words; wd += NT) selbits[wd] = 0u;
+    if (CLUSTER) {
+        for (int i = tid; i < 2 * CLUSTER_MAX * XSLOT_WORDS; i += NT) xslot[i] = 0ull;
+        if (tid < CLUSTER_MAX) remote[tid] = tid < csize ? cg::this_cluster().map_shared_rank(xslot, tid) : nullptr;
+    }
+    // every fps entry starts at `far`, so a block's best is its first frame: no initial refresh
+    for (int lb = tid; lb < nblk; lb += NT) {
+        const bool nonempty = lb * RB < c_len;
+        const int first = c_lo + lb * RB;
+        blk_val[lb] = nonempty ? far_bits : 0ull;
+        blk_idx[lb] = nonempty ? first : 0x7fffffff;
+        dirty[lb] = 0;
+        BlkRec br;
+        br.idx = 0xffffffffu;
+        br.list_len = br.e0 = br.e1 = br.n_boxes = 0;
+        br.off_lo = br.off_hi = 0u;
+        if (nonempty) {
+            const FrameRec r = a.rec[first];
+            br.idx = (unsigned)first;
+            br.list_len = r.list_len;
+            br.off_lo = (unsigned)r.list_off;
+            br.off_hi = (unsigned)((unsigned long long)r.list_off >> 32);
+            br.e0 = r.e0;
+            br.e1 = r.e1;
+            br.n_boxes = r.n_boxes;
+        }
+        blk_rec[lb] = br;
+    }
+    if (tid == 0) {
+        sh.ndirty[0] = sh.ndirty[1] = 0;
+        sh.err = 0;
+        sh.err_frame = -1;
+        sh.sat = 0;
+    }
     __syncthreads();
-    bool local_abort = false;
-    if (threadIdx.x == 0) {
-        sh.stop = 0;
-        sh.m = 0;
-        sh.cur = -1;
-        sh.cost = a.cost_start;
-        const unsigned long long needed = a.list_cursor ? *a.list_cursor : 0ull;
-        if (crank == 0) a.result[5] = (double)needed;
-        if ((long long)needed > a.list_capacity) {   // neighbour-list pool too small: the host grows it and reruns
-            local_abort = true;
-            if (crank == 0) {
-                a.result[1] = (double)ADSEL_ERR_CAPACITY;
-                a.result[4] = -1.0;
-            }
-            sh.stop = SHARDED ? 3 : 1;
-        } else if (a.n_sampled == 0) {
-            const int first = a.first_index;
-            if (crank == 0) a.out[0] = first;
-            sh.m = 1;
-            set_selected(a, selbits, first);
-            sh.cost = __dadd_rn(sh.cost, a.cost_f);
-            fetch_frame(a, sh, first);
-            sh.cost = __dadd_rn(sh.cost, sh.rec.box_cost);
-        }
-    }
-    cluster.sync();   // every CTA's slots are zeroed and mapped before anyone posts
-    if (!SHARDED && sh.stop) {
-        cluster.sync();
-        return;
-    }
-    if (a.forbid_sampled)
-        for (int t = threadIdx.x; t < a.n_sampled; t += NT) set_selected(a, selbits, a.sampled[t]);
-
-    // one row update on this CTA's slice: list entries, barrier, group members
-    auto apply = [&]() {
-        const int src = sh.cur;
-        const long long off = sh.rec.list_off;
-        const int len = a.spatial == ADSEL_SPATIAL_GEODESIC ? sh.rec.list_len : 0;
-        for (int t = threadIdx.x; t < len; t += NT) {
-            const int j = a.list_idx[off + t];
-            const unsigned long long v = (unsigned long long)__double_as_longlong(a.list_val[off + t]);   // same round trip
-            if (j >= c_lo && j < c_hi && v < fps_s[j - c_lo]) fps_s[j - c_lo] = v;
-        }
+    // Saturation of the temporal LUT: for d >= sat, tlut[d] equals the far value bit for bit (exp: 38), so group
+    // members further away than that keep the row's far value and need not be visited.
+    int tl_sat = 0x7fffffff;
+    if (a.temporal && a.groups_contiguous && a.spatial != ADSEL_SPATIAL_EUCLID) {
+        const int lim = min(a.n, 4096);
+        const unsigned long long tfar = (unsigned long long)__double_as_longlong(a.t_far);
+        int mx = 0;
+        for (int d = tid; d < lim; d += NT)
+            if ((unsigned long long)__double_as_longlong(a.tlut[d]) != tfar) mx = d + 1;
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0 && mx > 0) atomicMax(&sh.sat, mx);
         __syncthreads();
-        int g0 = 0, g1 = 0;
-        if (a.temporal || a.spatial == ADSEL_SPATIAL_EUCLID) {
-            g0 = sh.rec.e0;
-            g1 = sh.rec.e1;
+        tl_sat = sh.sat >= lim ? 0x7fffffff : sh.sat;
+    }
+
+    // ---- state replicated in the registers of every thread (of every CTA) ----
+    double cost = a.cost_start;
+    int m = 0, cur = -1, stop = 0;   // stop: 1 budget reached, 2 error
+    long long l_off = 0;
+    int l_len = 0, e0 = 0, e1 = 0;
+    double2 me = make_double2(0.0, 0.0);
+    int par = 0;                     // parity of the dirty counter in use (the other one is being reset)
+    int to_flag = -1;                // thread 0: frame whose selected flag is checked / set in the next apply
+    bool flag_check = false;         // thread 0: flag_seen holds the frame's flag as loaded when it was picked
+    bool flag_seen = false;
+
+    auto set_flag = [&](int idx) {   // thread 0 only
+        if (a.sel_words) selbits[idx >> 5] |= 1u << (idx & 31);
+        else sel_bytes[idx] = 1;
+    };
+    auto get_flag = [&](int idx) -> bool {   // thread 0 only
+        if (a.sel_words) return (selbits[idx >> 5] >> (idx & 31)) & 1u;
+        return __ldcg(sel_bytes + idx) != 0;
+    };
+    auto load_rec_global = [&](int idx) -> int {   // all threads, same address; returns n_boxes
+        const FrameRec r = a.rec[idx];
+        l_off = r.list_off;
+        l_len = r.list_len;
+        e0 = r.e0;
+        e1 = r.e1;
+        return r.n_boxes;
+    };
+    auto lower = [&](int j, unsigned long long v) {
+        const int lj = j - c_lo;
+        if (v < fps_s[lj]) {
+            fps_s[lj] = v;
+            const int lb = lj / RB;
+            // only the entry that IS the block's maximum can change it by decreasing
+            if (blk_idx[lb] == j && atomicExch(&dirty[lb], 1) == 0) dirty_list[atomicAdd(&sh.ndirty[par], 1)] = lb;
         }
-        if (a.groups_contiguous) {
-            g0 = max(g0, c_lo);
-            g1 = min(g1, c_hi);
-            for (int j = g0 + threadIdx.x; j < g1; j += NT) {
-                const unsigned long long v = (unsigned long long)__double_as_longlong(group_value(a, sh, tl, tl_n, src, j));
-                if (v < fps_s[j - c_lo]) fps_s[j - c_lo] = v;
-            }
-        } else {
-            for (int t = g0 + threadIdx.x; t < g1; t += NT) {
-                const int j = a.group_members[t];
-                if (j >= c_lo && j < c_hi) {
-                    const unsigned long long v = (unsigned long long)__double_as_longlong(group_value(a, sh, tl, tl_n, src, j));
-                    if (v < fps_s[j - c_lo]) fps_s[j - c_lo] = v;
+    };
+    // pending record of a refreshed block's best frame (lane 0 of every warp)
+    int pend_lb = -1, pend_idx = 0;
+    uint4 pend_lo = make_uint4(0, 0, 0, 0), pend_hi = make_uint4(0, 0, 0, 0);
+
+    // fps = min(fps, distance_map[cur]) on this CTA's slice; ends with the list writes (caller barriers)
+    auto apply = [&]() {
+        const int src = cur;
+        const int len = a.spatial == ADSEL_SPATIAL_GEODESIC ? l_len : 0;
+        // 1. list loads in flight (one L2 round trip, the only one of a step)
+        int j0 = -1, j1 = -1;
+        unsigned long long v0 = 0, v1 = 0;
+        if (tid < len) {
+            j0 = a.list_idx[l_off + tid];
+            v0 = (unsigned long long)__double_as_longlong(a.list_val[l_off + tid]);
+        }
+        if (tid + NT < len) {
+            j1 = a.list_idx[l_off + tid + NT];
+            v1 = (unsigned long long)__double_as_longlong(a.list_val[l_off + tid + NT]);
+        }
+        // 2. temporal group (or Euclid city group) while they fly
+        GreedyShared gs;   // group_value() reads sh.me only
+        gs.me = me;
+        if (a.temporal || a.spatial == ADSEL_SPATIAL_EUCLID) {
+            if (a.groups_contiguous) {
+                int g0 = max(e0, c_lo), g1 = min(e1, c_hi);
+                if (tl_sat != 0x7fffffff) {
+                    g0 = max(g0, src - tl_sat + 1);
+                    g1 = min(g1, src + tl_sat);
+                }
+                for (int j = g0 + tid; j < g1; j += NT)
+                    lower(j, (unsigned long long)__double_as_longlong(group_value(a, gs, tl, tl_n, src, j)));
+            } else {
+                for (int t = e0 + tid; t < e1; t += NT) {
+                    const int j = a.group_members[t];
+                    if (j >= c_lo && j < c_hi)
+                        lower(j, (unsigned long long)__double_as_longlong(group_value(a, gs, tl, tl_n, src, j)));
                 }
             }
+        }
+        __syncthreads();   // group writes before list writes (hidden under the list loads)
+        // 3. list entries: unique columns, plain writes
+        if (j0 >= c_lo && j0 < c_hi) lower(j0, v0);
+        if (j1 >= c_lo && j1 < c_hi) lower(j1, v1);
+        for (int t = tid + 2 * NT; t < len; t += NT) {
+            const int j = a.list_idx[l_off + t];
+            if (j >= c_lo && j < c_hi) lower(j, (unsigned long long)__double_as_longlong(a.list_val[l_off + t]));
+        }
+        // 4. deferred work that must not race with the bookkeeping reads before the barrier above
+        if (lane == 0 && pend_lb >= 0) {
+            BlkRec br;
+            br.idx = (unsigned)pend_idx;
+            br.off_lo = pend_lo.x;      // FrameRec: list_off (8), list_len, e0 | e1, n_boxes, box_cost (8)
+            br.off_hi = pend_lo.y;
+            br.list_len = (int)pend_lo.z;
+            br.e0 = (int)pend_lo.w;
+            br.e1 = (int)pend_hi.x;
+            br.n_boxes = (int)pend_hi.y;
+            blk_rec[pend_lb] = br;
+            pend_lb = -1;
+        }
+        if (tid == 0 && to_flag >= 0) {   // :182 assert, evaluated a phase late so that the flag load is off the chain
+            if (flag_check && flag_seen) {
+                sh.err = 1;
+                sh.err_frame = to_flag;
+            } else {
+                set_flag(to_flag);
+            }
+            to_flag = -1;
         }
     };
 
-    if (sh.stop == 0) {
-        for (int t = 0; t < a.n_sampled; ++t) {   // fps = min over the rows of the frames already in the buffer (:160-164)
-            __syncthreads();
-            if (threadIdx.x == 0) fetch_frame(a, sh, a.sampled[t]);
-            __syncthreads();
-            apply();
+    bool local_abort = false;
+    {
+        const unsigned long long needed = a.list_cursor ? *a.list_cursor : 0ull;
+        if (writer) a.result[5] = (double)needed;
+        if ((long long)needed > a.list_capacity) {   // neighbour-list pool too small: the host grows it and reruns
+            local_abort = true;
+            if (writer) {
+                a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                a.result[4] = -1.0;
+            }
         }
     }
+    if (CLUSTER) cg::this_cluster().sync();   // every CTA's slots are zeroed and mapped before anyone posts
     long long steps = 0;
-    bool seeding = a.n_sampled > 0;
-    while (true) {
-        if (!seeding && sh.stop == 0) apply();
-        __syncthreads();
-        // arg-max of this CTA's slice, first index among equal maxima
-        Best acc[4];
+    bool seeding = a.n_sampled > 0;   // first pick = argmax without a preceding update (:165)
+    if (!local_abort) {
+        if (a.forbid_sampled && tid == 0)
+            for (int t = 0; t < a.n_sampled; ++t) set_flag(a.sampled[t]);
+        if (a.n_sampled == 0) {   // empty buffer: the caller's random.choice is taken and costed up front (:168,172-174)
+            cur = a.first_index;
+            const int nb = load_rec_global(cur);
+            if (a.spatial == ADSEL_SPATIAL_EUCLID) me = a.loc[cur];
+            if (writer) a.out[0] = cur;
+            m = 1;
+            to_flag = cur;
+            cost = __dadd_rn(cost, a.cost_f);
+            cost = __dadd_rn(cost, __dmul_rn((double)nb, a.cost_b));
+        } else {
+            for (int t = 0; t < a.n_sampled; ++t) {   // fps = min over the rows of the frames already in the buffer (:160-164)
+                cur = a.sampled[t];
+                load_rec_global(cur);
+                if (a.spatial == ADSEL_SPATIAL_EUCLID) me = a.loc[cur];
+                apply();
+                __syncthreads();
+            }
+        }
+        while (true) {
+            RPROF_MARK(7)
+            if (!seeding) apply();
+            RPROF_MARK(0)
+            __syncthreads();
+            RPROF_MARK(1)
+            {   // re-reduce the blocks whose maximum was lowered, one warp per block
+                const int nd = sh.ndirty[par];
+                for (int q = wid; q < nd; q += NW) {
+                    const int lb = dirty_list[q];
+                    Best e[RB / 32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] = Best{0ull, 0x7fffffff};
-        for (int i0 = threadIdx.x; i0 < c_len; i0 += 4 * NT) {
+                    for (int i = 0; i < RB / 32; ++i) {
+                        const int lj = lb * RB + lane + 32 * i;
+                        e[i] = lj < c_len ? Best{fps_s[lj], c_lo + lj} : Best{0ull, 0x7fffffff};
+                    }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = i0 + q * NT;
-                if (i < c_len) {
-                    const unsigned long long v = fps_s[i];
-                    if (v > acc[q].v || acc[q].i == 0x7fffffff) {   // ascending i per accumulator: strict '>' keeps the first
-                        acc[q].v = v;
-                        acc[q].i = c_lo + i;
+                    for (int w = 1; w < RB / 32; w <<= 1)
+#pragma unroll
+                        for (int i = 0; i + w < RB / 32; i += 2 * w) e[i] = better(e[i], e[i + w]);
+                    const Best x = warp_best(e[0]);
+                    if (lane == 0) {
+                        blk_val[lb] = x.v;
+                        blk_idx[lb] = x.i;
+                        dirty[lb] = 0;
+                        if (x.i != 0x7fffffff) {   // its record: in flight now, stored into blk_rec during the next apply
+                            pend_lb = lb;
+                            pend_idx = x.i;
+                            ldg_rec_async(a.rec + x.i, pend_lo, pend_hi);
+                        }
                     }
                 }
             }
-        }
-        Best x = better(better(acc[0], acc[1]), better(acc[2], acc[3]));
-        x = warp_best(x);
-        if (lane == 0) wres[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            Best y = lane < NWARPS ? wres[lane] : Best{0ull, 0x7fffffff};
+            RPROF_MARK(2)
+            __syncthreads();
+            RPROF_MARK(3)
+            if (tid == 0) sh.ndirty[par] = 0;   // the next apply counts in the other word (zeroed a step ago)
+            par ^= 1;
+            // arg-reduce over this CTA's block maxima, by every warp
+            Best y{0ull, 0x7fffffff};
+            for (int b0 = lane; b0 < nblk; b0 += 4 * 32) {
+                Best e[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int b = b0 + 32 * q;
+                    e[q] = b < nblk ? Best{blk_val[b], blk_idx[b]} : Best{0ull, 0x7fffffff};
+                }
+                y = better(y, better(better(e[0], e[1]), better(e[2], e[3])));
+            }
             y = warp_best(y);
-            if (y.i != 0x7fffffff && lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rec + y.i));
-            const unsigned tag = 1u + (unsigned)steps;
-            if (csize > 1) y = cluster_exchange(xslot, remote, crank, csize, tag, y);
-            int comm_status = 0;
-            if (SHARDED) {
-                const bool abort_now = __shfl_sync(0xffffffffu, local_abort ? 1 : 0, 0) != 0;
-                const ExchangeResult r = exchange_best(comm, xlane, comm.seq_base + tag, y.v,
-                                                       abort_now ? COMM_ABORT_INDEX : (unsigned)y.i, crank == 0);
-                y.v = r.key;
-                y.i = r.index;
-                comm_status = r.status;
+            if (CLUSTER) y = cluster_exchange(xslot, remote, crank, csize, 1u + (unsigned)steps, y, wid == 0);
+            RPROF_MARK(4)
+            ++steps;
+            if (sh.err) {   // :182 assert -- the frame applied in this step had been selected before
+                stop = 2;
+                break;
             }
-            if (lane == 0) {
-                const int nxt = y.i;
-                if (comm_status != 0) {
-                    if (crank == 0 && a.result[1] == 0.0)
-                        a.result[1] = (double)(comm_status == 2 ? ADSEL_ERR_COMM : ADSEL_ERR_PEER_ABORT);
-                    sh.stop = 2;
-                } else if (nxt < 0 || nxt >= a.n) {
-                    if (crank == 0) a.result[1] = (double)ADSEL_ERR_INVALID;
-                    sh.stop = 2;
-                } else {
-                    const FrameRec rec = a.rec[nxt];
-                    const bool was_selected = get_selected(a, selbits, nxt);
-                    const double2 me = a.spatial == ADSEL_SPATIAL_EUCLID ? a.loc[nxt] : make_double2(0.0, 0.0);
-                    if (seeding) {
-                        if (crank == 0) a.out[0] = nxt;
-                        sh.m = 1;
-                        set_selected(a, selbits, nxt);
-                        sh.cost = __dadd_rn(sh.cost, a.cost_f);
-                        sh.cost = __dadd_rn(sh.cost, rec.box_cost);
-                        sh.rec = rec;
-                        sh.me = me;
-                        sh.cur = nxt;
-                    } else if (was_selected) {   // :182 assert
-                        if (crank == 0) {
-                            a.result[1] = (double)ADSEL_ERR_RESELECTED;
-                            a.result[4] = (double)nxt;
-                        }
-                        sh.stop = 1;
-                    } else {
-                        sh.cost = __dadd_rn(sh.cost, a.cost_f);          // :184
-                        sh.cost = __dadd_rn(sh.cost, rec.box_cost);      // :185
-                        if (sh.cost > a.budget) {                        // :186
-                            sh.stop = 1;
-                        } else if (sh.m >= a.out_cap) {
-                            if (crank == 0) {
-                                a.result[1] = (double)ADSEL_ERR_CAPACITY;
-                                a.result[4] = -2.0;
-                            }
-                            sh.stop = 1;
-                        } else {
-                            if (crank == 0) a.out[sh.m] = nxt;
-                            sh.m += 1;
-                            set_selected(a, selbits, nxt);
-                            sh.rec = rec;
-                            sh.me = me;
-                            sh.cur = nxt;
-                        }
-                    }
+            const int nxt = y.i;
+            if (nxt < 0 || nxt >= a.n) {   // empty pool: cannot happen with n > 0
+                if (writer) a.result[1] = (double)ADSEL_ERR_INVALID;
+                stop = 2;
+                break;
+            }
+            // the winner's record: cached with its block's maximum, else one global round trip
+            int nb = 0;
+            bool have = false;
+            if (nxt >= c_lo && nxt < c_hi) {
+                const BlkRec br = blk_rec[(nxt - c_lo) / RB];
+                if (br.idx == (unsigned)nxt) {
+                    have = true;
+                    l_off = (long long)(((unsigned long long)br.off_hi << 32) | br.off_lo);
+                    l_len = br.list_len;
+                    e0 = br.e0;
+                    e1 = br.e1;
+                    nb = br.n_boxes;
                 }
             }
+            if (!have) nb = load_rec_global(nxt);
+            if (a.spatial == ADSEL_SPATIAL_EUCLID) me = a.loc[nxt];
+            const double box_cost = __dmul_rn((double)nb, a.cost_b);   // n_boxes * cost_b, one rounded product (base_selector.py:85)
+            if (seeding) {   // :165,172-174 -- always taken, no budget check
+                seeding = false;
+                if (writer) a.out[0] = nxt;
+                m = 1;
+                cost = __dadd_rn(cost, a.cost_f);
+                cost = __dadd_rn(cost, box_cost);
+                cur = nxt;
+                to_flag = nxt;
+                continue;
+            }
+            if (tid == 0) flag_seen = get_flag(nxt);   // consumed in the next apply, or below when the loop ends here
+            cost = __dadd_rn(cost, a.cost_f);      // :184
+            cost = __dadd_rn(cost, box_cost);      // :185
+            const bool over = cost > a.budget;     // :186
+            const bool full = !over && m >= a.out_cap;
+            if (over || full) {
+                if (writer) {
+                    if (flag_seen) {               // :182 comes before the cost test
+                        a.result[1] = (double)ADSEL_ERR_RESELECTED;
+                        a.result[4] = (double)nxt;
+                    } else if (full) {
+                        a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                        a.result[4] = -2.0;
+                    }
+                }
+                stop = over ? 1 : 2;
+                break;
+            }
+            if (writer) a.out[m] = nxt;
+            m += 1;
+            cur = nxt;
+            to_flag = nxt;
+            flag_check = true;
+            RPROF_MARK(5)
         }
-        __syncthreads();
-        ++steps;
-        if (sh.stop == 2) break;
-        if (seeding) {
-            seeding = false;
-            continue;
-        }
-        if (sh.stop) break;
     }
-    for (int i = threadIdx.x; i < c_len; i += NT) a.fps[c_lo + i] = fps_s[i];   // adsel_get_fps
-    if (threadIdx.x == 0 && crank == 0) {
-        a.result[0] = sh.cost;
-        a.result[2] = (double)sh.m;
+    __syncthreads();
+    if (stop == 2 && sh.err && writer) {
+        a.result[1] = (double)ADSEL_ERR_RESELECTED;
+        a.result[4] = (double)sh.err_frame;
+    }
+    for (int i = tid; i < c_len; i += NT) a.fps[c_lo + i] = fps_s[i];   // adsel_get_fps
+    if (writer) {
+        a.result[0] = cost;
+        a.result[2] = (double)m;
         a.result[3] = (double)steps;
+        if (PROFILE)
+            for (int i = 0; i < 12; ++i) a.prof[i] = prof_acc[i];
     }
-    cluster.sync();   // no CTA leaves while a peer may still store into its slots
+    if (CLUSTER) cg::this_cluster().sync();   // no CTA leaves while a peer may still store into its slots
 }
 
 __global__ void temporal_lut_kernel(double *tlut, int n, int norm_mode, double divisor) {
@@ -783,45 +975,424 @@ static int greedy_threads() {
     return (t == 256 || t == 512 || t == 1024) ? t : 512;
 }
 
-// Cluster size for the shared-memory-resident variant, 0 when it is not used.
-// MEASURED SLOWER than the single-CTA kernel on B200 (P28K, budget 4800: 16.2 / 15.3 / 13.6 ms with 2 / 4 / 8 CTAs
-// against 10.4 ms): what the shared-memory fps saves (the RED -> ld.cg round trip) is spent again on the scan of the
-// whole slice, the two-level arg-max, the DSMEM exchange (~215 cycles one way) and the frame-record fetch that now
-// misses L1 in every CTA but the winner's.  It is therefore OFF unless ADSEL_GREEDY_CLUSTER=1/2/4/8 asks for it
-// (negative or unset: off); it passes the same parity tests and is kept as the measured alternative of DESIGN.md §5.
-static int pick_cluster(const GreedyArgs &a, int nt, size_t *smem_out, int *cta_cols_out, int *sel_words_out) {
-    const char *e = getenv("ADSEL_GREEDY_CLUSTER");
-    const int forced = e ? atoi(e) : 0;
-    if (forced <= 0) return 0;
-    const long long cols = a.hi - a.lo;
-    const size_t budget = 220 * 1024;   // of the 227 KB opt-in maximum: room for the static shared variables
-    for (int c = 1; c <= CLUSTER_MAX; c *= 2) {
-        if (forced > 0 && c != forced) continue;
-        long long per = (cols + c - 1) / c;
-        per = (per + 255) / 256 * 256;
-        if (per < 256) per = 256;
-        const size_t base = (size_t)per * 8 + (size_t)a.tl_n * 8 + 2 * CLUSTER_MAX * XSLOT_WORDS * 8 + 64;
-        if (base > budget) continue;
-        // the selected-frame bitmap goes to shared memory when it still fits, else global bytes are used
-        const size_t bitmap = (size_t)((a.n + 31) / 32) * 4;
-        const int sel_words = (a.n <= 524288 && base + bitmap <= budget) ? (a.n + 31) / 32 : 0;
-        // default: the smallest cluster that fits, but no more than 16 slice entries per thread
-        if (forced <= 0 && c < CLUSTER_MAX && per > 16LL * nt && ((cols + 2 * c - 1) / (2 * c)) >= 256) continue;
-        *smem_out = base + (size_t)sel_words * 4;
-        *cta_cols_out = (int)per;
-        *sel_words_out = sel_words;
-        return c;
-    }
-    return 0;
+// ---------------------------------------------------------------------------------------------
+// Fast variant of the resident kernel: ONE CTA, the configuration of the headline workload family
+// (no Euclid term, temporal groups that are contiguous index ranges), written for the LENGTH OF THE
+// INSTRUCTION CHAIN of a step.  ncu on the generic resident kernel (profiles/r02_resident_v1_hotspots.txt):
+// 2,464 warp-instructions per step, IPC per warp 0.08 -- the step is a serial chain of constant-bank reloads
+// (LDC/LDCU 226 per step), mode tests and 64-bit compare/select trees, not of memory round trips.  Here
+//   * everything a step needs from the kernel arguments is pinned in registers (no LDC in the loop) and
+//     no mode is tested in the loop: the group value is a shared-memory table gval[|j - src|] that already
+//     holds aggregate(s_far, normalize(|j - src|)) -- any normalisation and any aggregate cost one LDS;
+//   * block refresh and final arg-max are three 32-bit REDUX operations each (max high word, max low word
+//     among the lanes that hold it, min frame index among those that hold both) around VIMNMX trees: no
+//     64-bit compare/select, no branches;
+//   * the selected frame's record (list range, group range, box cost) comes from the shared-memory cache of
+//     its block's best frame (two LDS.128), its list loads are issued before anything else, the cost
+//     bookkeeping and the group phase run in their shadow, the re-selection flag is checked a phase late.
+// Chain of a step: LDS record -> LDG list (the one L2 round trip) -> LDS/STS min -> BAR -> refresh of the
+// 1-2 blocks whose best was lowered -> BAR -> arg-max over the block maxima by every warp.
+// ---------------------------------------------------------------------------------------------
+#define ADSEL_PIN32(x) asm volatile("" : "+r"(x))
+#define ADSEL_PIN64(x) asm volatile("" : "+l"(x))
+#define ADSEL_PINF64(x) asm volatile("" : "+d"(x))
+
+struct FastShared {
+    int ndirty[2];
+    int err, err_frame, sat;
+};
+
+struct Win {
+    unsigned hi, lo;
+    int idx;
+};
+
+// Warp-wide arg-max over CNT (hi, lo, idx) candidates per lane: largest 64-bit key, lowest idx among equal keys.
+template <int CNT>
+__device__ __forceinline__ Win warp_argmax(const unsigned (&hi)[CNT], const unsigned (&lo)[CNT], const int (&idx)[CNT]) {
+    const unsigned full = 0xffffffffu;
+    unsigned h = hi[0];
+#pragma unroll
+    for (int i = 1; i < CNT; ++i) h = max(h, hi[i]);
+    const unsigned mhi = __reduce_max_sync(full, h);
+    unsigned l = 0u;
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) l = max(l, hi[i] == mhi ? lo[i] : 0u);
+    const unsigned mlo = __reduce_max_sync(full, l);
+    int c = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) c = min(c, (hi[i] == mhi && lo[i] == mlo) ? idx[i] : 0x7fffffff);
+    Win w;
+    w.hi = mhi;
+    w.lo = mlo;
+    w.idx = __reduce_min_sync(full, c);
+    return w;
 }
 
-template <int NT, bool SHARDED>
-static cudaError_t launch_cluster_nt(adsel_handle *h, const GreedyArgs &a, const CommView &view, size_t smem) {
-    cudaFuncSetAttribute(greedy_cluster_kernel<NT, SHARDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+__device__ __forceinline__ int atom_inc_shared(int *p) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return old;
+}
+
+template <int RB, bool PROFILE>
+__global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs a) {
+    constexpr int NT = RES_NT, NW = NT / 32, PER = RB / 32;
+    constexpr int SHIFT = RB == 256 ? 8 : 7;
+    static_assert(RB == 128 || RB == 256, "block size");
+    unsigned long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = PROFILE ? clock64() : 0;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    // ---- hot arguments, pinned in registers ----
+    int n = a.n, cols = a.cta_cols, nblk = a.r_nblk, G = a.tl_n, out_cap = a.out_cap;
+    const int32_t *lidx = a.list_idx;
+    const double *lval = a.list_val;
+    const FrameRec *recs = a.rec;
+    int32_t *out = a.out;
+    unsigned char *sel_bytes = a.is_selected;
+    double budget = a.budget, cost_f = a.cost_f;
+    const bool has_list = a.spatial == ADSEL_SPATIAL_GEODESIC, has_group = a.temporal != 0;
+    ADSEL_PIN32(n);
+    ADSEL_PIN32(nblk);
+    ADSEL_PIN32(G);
+    ADSEL_PIN32(out_cap);
+    ADSEL_PIN64(lidx);
+    ADSEL_PIN64(lval);
+    ADSEL_PIN64(recs);
+    ADSEL_PIN64(out);
+    ADSEL_PIN64(sel_bytes);
+    ADSEL_PINF64(budget);
+    ADSEL_PINF64(cost_f);
+
+    extern __shared__ unsigned long long greedy_smem[];
+    unsigned long long *fps_s = greedy_smem;                              // [cols]
+    unsigned long long *blk_val = fps_s + cols;                           // [nblk]
+    unsigned long long *gval = blk_val + nblk;                            // [G] row value of a group member at index gap d
+    uint4 *blk_rec = reinterpret_cast<uint4 *>(gval + G);                 // [nblk][2] FrameRec of the block's best frame, n_boxes := frame
+    int *blk_idx = reinterpret_cast<int *>(blk_rec + 2 * (size_t)nblk);   // [nblk]
+    int *dirty_list = blk_idx + nblk;                                     // [2 * nblk]
+    __shared__ FastShared sh;
+
+    const unsigned long long far_bits = a.far_bits;
+    for (int i = tid; i < cols; i += NT) fps_s[i] = i < n ? far_bits : 0ull;
+    for (int d = tid; d < G; d += NT)
+        gval[d] = (unsigned long long)__double_as_longlong(combine(a.spatial, a.temporal, a.aggregate, a.lambda_t, a.s_far, a.tlut[d]));
+    // every fps entry starts at `far`, so a block's best is its first frame: no initial refresh
+    for (int lb = tid; lb < nblk; lb += NT) {
+        const int first = lb << SHIFT;
+        const bool nonempty = first < n;
+        blk_val[lb] = nonempty ? far_bits : 0ull;
+        blk_idx[lb] = nonempty ? first : 0x7fffffff;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0xffffffffu, 0, 0);
+        if (nonempty) {
+            ldg_rec_async(recs + first, lo, hi);
+            hi.y = (unsigned)first;
+        }
+        blk_rec[2 * lb] = lo;
+        blk_rec[2 * lb + 1] = hi;
+    }
+    if (tid == 0) {
+        sh.ndirty[0] = sh.ndirty[1] = 0;
+        sh.err = 0;
+        sh.err_frame = -1;
+        sh.sat = 0;
+    }
+    __syncthreads();
+    // Saturation of the temporal LUT: for d >= sat, tlut[d] equals the far value bit for bit (exp: 38), so group
+    // members further away than that keep the row's far value and are not visited.
+    int sat = 0x3fffffff;
+    if (has_group) {
+        const int lim = min(n, 4096);
+        const unsigned long long tfar = (unsigned long long)__double_as_longlong(a.t_far);
+        int mx = 0;
+        for (int d = tid; d < lim; d += NT)
+            if ((unsigned long long)__double_as_longlong(a.tlut[d]) != tfar) mx = d + 1;
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0 && mx > 0) atomicMax(&sh.sat, mx);
+        __syncthreads();
+        sat = sh.sat >= lim ? 0x3fffffff : sh.sat;
+    }
+
+    // ---- state replicated in the registers of every thread ----
+    double cost = a.cost_start;
+    int m = 0, cur = -1, stop = 0, par = 0;
+    long long l_off = 0;
+    int l_len = 0, e0 = 0, e1 = 0;
+    int to_flag = -1;                // thread 0: frame whose selected flag is checked / set in the next apply
+    bool flag_check = false;
+    unsigned flag_seen = 0;
+    int pend_lb = -1, pend_idx = 0;  // lane 0 of every warp: record in flight for a refreshed block's best frame
+    uint4 pend_lo = make_uint4(0, 0, 0, 0), pend_hi = make_uint4(0, 0, 0, 0);
+
+    bool marking = true;             // false while the rows of the buffer are applied (all blocks are re-reduced afterwards)
+    auto lower = [&](int j, unsigned long long v) {
+        if (v < fps_s[j]) {
+            fps_s[j] = v;
+            const int lb = j >> SHIFT;
+            // only the entry that IS the block's maximum can change it by decreasing; a block can be listed twice
+            // per step (group phase, list phase) -- it is then re-reduced twice with the same result
+            if (marking && blk_idx[lb] == j) dirty_list[atom_inc_shared(&sh.ndirty[par])] = lb;
+        }
+    };
+    auto take_rec = [&](const uint4 &lo, const uint4 &hi) -> double {   // FrameRec words -> row state; returns box_cost
+        l_off = (long long)(((unsigned long long)lo.y << 32) | lo.x);
+        l_len = has_list ? (int)lo.z : 0;
+        e0 = (int)lo.w;
+        e1 = (int)hi.x;
+        return __longlong_as_double((long long)(((unsigned long long)hi.w << 32) | hi.z));
+    };
+    auto apply = [&]() {
+        // 1. list loads in flight (the one L2 round trip of a step)
+        int j0 = -1, j1 = -1;
+        unsigned long long v0 = 0, v1 = 0;
+        if (tid < l_len) {
+            j0 = lidx[l_off + tid];
+            v0 = (unsigned long long)__double_as_longlong(lval[l_off + tid]);
+        }
+        if (tid + NT < l_len) {
+            j1 = lidx[l_off + tid + NT];
+            v1 = (unsigned long long)__double_as_longlong(lval[l_off + tid + NT]);
+        }
+        // 2. temporal group in their shadow: frames [e0, e1) within the LUT's unsaturated reach of cur
+        if (has_group) {
+            const int g0 = max(e0, cur - sat + 1), g1 = min(e1, cur + sat);
+            for (int j = g0 + tid; j < g1; j += NT) {
+                const int d = abs(j - cur);
+                const unsigned long long v = d < G ? gval[d]
+                    : (unsigned long long)__double_as_longlong(combine(a.spatial, a.temporal, a.aggregate, a.lambda_t, a.s_far, a.tlut[d]));
+                lower(j, v);
+            }
+        }
+        __syncthreads();   // group writes before list writes (list values of same-group frames are <= the group values); hidden under the list loads
+        // 3. list entries: unique columns, plain writes
+        if (j0 >= 0) lower(j0, v0);
+        if (j1 >= 0) lower(j1, v1);
+        for (int t = tid + 2 * NT; t < l_len; t += NT) lower(lidx[l_off + t], (unsigned long long)__double_as_longlong(lval[l_off + t]));
+        // 4. deferred work that must not race with the reads made before the barrier above
+        if (lane == 0 && pend_lb >= 0) {
+            pend_hi.y = (unsigned)pend_idx;   // n_boxes slot := frame the record belongs to
+            blk_rec[2 * pend_lb] = pend_lo;
+            blk_rec[2 * pend_lb + 1] = pend_hi;
+            pend_lb = -1;
+        }
+        if (tid == 0 && to_flag >= 0) {   // :182 assert, evaluated a phase late so that the flag load is off the chain
+            if (flag_check && flag_seen) {
+                sh.err = 1;
+                sh.err_frame = to_flag;
+            } else {
+                sel_bytes[to_flag] = 1;
+            }
+            to_flag = -1;
+        }
+    };
+
+    // re-reduce the first nd blocks of dirty_list, one warp per block
+    auto refresh = [&](int nd) {
+        for (int q = wid; q < nd; q += NW) {
+            const int lb = dirty_list[q];
+            const int base = (lb << SHIFT) + lane;
+            unsigned hi[PER], lo[PER];
+            int idx[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const unsigned long long v = fps_s[base + 32 * i];
+                hi[i] = (unsigned)(v >> 32);
+                lo[i] = (unsigned)v;
+                idx[i] = base + 32 * i < n ? base + 32 * i : 0x7fffffff;
+            }
+            const Win x = warp_argmax<PER>(hi, lo, idx);
+            if (lane == 0) {
+                blk_val[lb] = ((unsigned long long)x.hi << 32) | x.lo;
+                blk_idx[lb] = x.idx;
+                if (x.idx != 0x7fffffff) {   // its record: in flight now, stored into blk_rec during the next apply
+                    pend_lb = lb;
+                    pend_idx = x.idx;
+                    ldg_rec_async(recs + x.idx, pend_lo, pend_hi);
+                }
+            }
+        }
+    };
+
+    bool local_abort = false;
+    {
+        const unsigned long long needed = a.list_cursor ? *a.list_cursor : 0ull;
+        if (tid == 0) a.result[5] = (double)needed;
+        if ((long long)needed > a.list_capacity) {   // neighbour-list pool too small: the host grows it and reruns
+            local_abort = true;
+            if (tid == 0) {
+                a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                a.result[4] = -1.0;
+            }
+        }
+    }
+    long long steps = 0;
+    bool seeding = a.n_sampled > 0;   // first pick = argmax without a preceding update (:165)
+    if (!local_abort) {
+        if (a.forbid_sampled && tid == 0)
+            for (int t = 0; t < a.n_sampled; ++t) sel_bytes[a.sampled[t]] = 1;
+        if (a.n_sampled == 0) {   // empty buffer: the caller's random.choice is taken and costed up front (:168,172-174)
+            cur = a.first_index;
+            uint4 lo, hi;
+            ldg_rec_async(recs + cur, lo, hi);
+            const double box_cost = take_rec(lo, hi);
+            if (tid == 0) out[0] = cur;
+            m = 1;
+            to_flag = cur;
+            cost = __dadd_rn(cost, cost_f);
+            cost = __dadd_rn(cost, box_cost);
+        } else {
+            marking = false;
+            for (int t = 0; t < a.n_sampled; ++t) {   // fps = min over the rows of the frames already in the buffer (:160-164)
+                cur = a.sampled[t];
+                uint4 lo, hi;
+                ldg_rec_async(recs + cur, lo, hi);
+                take_rec(lo, hi);
+                apply();
+                __syncthreads();
+            }
+            marking = true;
+            // every block maximum and its cached record from scratch
+            for (int lb = tid; lb < nblk; lb += NT) dirty_list[lb] = lb;
+            __syncthreads();
+            refresh(nblk);
+            pend_lb = -1;
+            __syncthreads();
+            for (int lb = tid; lb < nblk; lb += NT) {
+                const int best = blk_idx[lb];
+                if (best != 0x7fffffff) {
+                    uint4 lo, hi;
+                    ldg_rec_async(recs + best, lo, hi);
+                    hi.y = (unsigned)best;
+                    blk_rec[2 * lb] = lo;
+                    blk_rec[2 * lb + 1] = hi;
+                }
+            }
+            __syncthreads();
+        }
+        while (true) {
+            RPROF_MARK(7)
+            if (!seeding) apply();
+            RPROF_MARK(0)
+            __syncthreads();
+            RPROF_MARK(1)
+            refresh(sh.ndirty[par]);
+            RPROF_MARK(2)
+            __syncthreads();
+            RPROF_MARK(3)
+            if (tid == 0) sh.ndirty[par] = 0;   // the next apply counts in the other word (zeroed a step ago)
+            par ^= 1;
+            // arg-max over the block maxima, by every warp (no broadcast, no barrier)
+            Win y;
+            y.hi = y.lo = 0u;
+            y.idx = 0x7fffffff;
+            for (int b0 = 0; b0 < nblk; b0 += 4 * 32) {   // uniform trip count: the REDUX inside need every lane
+                unsigned hi[4], lo[4];
+                int idx[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int b = b0 + lane + 32 * q;
+                    const bool ok = b < nblk;
+                    const unsigned long long v = ok ? blk_val[b] : 0ull;
+                    hi[q] = (unsigned)(v >> 32);
+                    lo[q] = (unsigned)v;
+                    idx[q] = ok ? blk_idx[b] : 0x7fffffff;
+                }
+                const Win w = warp_argmax<4>(hi, lo, idx);
+                const bool take = w.hi > y.hi || (w.hi == y.hi && (w.lo > y.lo || (w.lo == y.lo && w.idx < y.idx)));
+                if (take) y = w;
+            }
+            RPROF_MARK(4)
+            ++steps;
+            if (sh.err) {   // :182 assert -- the frame applied in this step had been selected before
+                stop = 2;
+                break;
+            }
+            const int nxt = y.idx;
+            if (nxt < 0 || nxt >= n) {   // empty pool: cannot happen with n > 0
+                if (tid == 0) a.result[1] = (double)ADSEL_ERR_INVALID;
+                stop = 2;
+                break;
+            }
+            // the winner's record: cached with its block's maximum, else one global round trip
+            uint4 rlo = blk_rec[2 * (nxt >> SHIFT)], rhi = blk_rec[2 * (nxt >> SHIFT) + 1];
+            if (rhi.y != (unsigned)nxt) ldg_rec_async(recs + nxt, rlo, rhi);
+            const double box_cost = take_rec(rlo, rhi);
+            cur = nxt;
+            if (seeding) {   // :165,172-174 -- always taken, no budget check
+                seeding = false;
+                if (tid == 0) out[0] = nxt;
+                m = 1;
+                cost = __dadd_rn(cost, cost_f);
+                cost = __dadd_rn(cost, box_cost);
+                to_flag = nxt;
+                continue;
+            }
+            if (tid == 0) flag_seen = __ldcg(sel_bytes + nxt);   // consumed in the next apply, or below when the loop ends here
+            cost = __dadd_rn(cost, cost_f);        // :184
+            cost = __dadd_rn(cost, box_cost);      // :185 (n_boxes * cost_b, one rounded product)
+            const bool over = cost > budget;       // :186
+            const bool full = !over && m >= out_cap;
+            if (over || full) {
+                if (tid == 0) {
+                    if (flag_seen) {               // :182 comes before the cost test
+                        a.result[1] = (double)ADSEL_ERR_RESELECTED;
+                        a.result[4] = (double)nxt;
+                    } else if (full) {
+                        a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                        a.result[4] = -2.0;
+                    }
+                }
+                stop = over ? 1 : 2;
+                break;
+            }
+            if (tid == 0) out[m] = nxt;
+            m += 1;
+            to_flag = nxt;
+            flag_check = true;
+            RPROF_MARK(5)
+        }
+    }
+    __syncthreads();
+    if (stop == 2 && sh.err && tid == 0) {
+        a.result[1] = (double)ADSEL_ERR_RESELECTED;
+        a.result[4] = (double)sh.err_frame;
+    }
+    for (int i = tid; i < n; i += NT) a.fps[i] = fps_s[i];   // adsel_get_fps
+    if (tid == 0) {
+        a.result[0] = cost;
+        a.result[2] = (double)m;
+        a.result[3] = (double)steps;
+        if (PROFILE)
+            for (int i = 0; i < 12; ++i) a.prof[i] = prof_acc[i];
+    }
+}
+
+// ---- host side of the resident variant -----------------------------------------------------------
+struct ResidentPlan {
+    int csize = 0, rb = 0, cta_cols = 0, nblk = 0, tl_n = 0, sel_words = 0;
+    size_t smem = 0;
+};
+
+static size_t resident_fixed_bytes(long long cta_cols, long long nblk, bool cluster) {
+    size_t b = (size_t)cta_cols * 8 + (size_t)nblk * 8;
+    if (cluster) b += (size_t)(2 * CLUSTER_MAX * XSLOT_WORDS + CLUSTER_MAX) * 8;
+    return b + (size_t)nblk * 12 + (size_t)nblk * sizeof(BlkRec);
+}
+
+template <int RB, bool CLUSTER, bool PROFILE>
+static cudaError_t launch_resident(adsel_handle *h, const GreedyArgs &a, size_t smem, bool dry_run, int *max_clusters) {
+    auto kernel = greedy_resident_kernel<RB, CLUSTER, PROFILE>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (CLUSTER && a.csize > 8) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)a.csize, 1, 1);
-    cfg.blockDim = dim3(NT, 1, 1);
+    cfg.blockDim = dim3(RES_NT, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
@@ -830,8 +1401,112 @@ static cudaError_t launch_cluster_nt(adsel_handle *h, const GreedyArgs &a, const
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, greedy_cluster_kernel<NT, SHARDED>, a, view);
+    cfg.numAttrs = CLUSTER ? 1 : 0;
+    if (dry_run) {   // can a cluster of this size and shared-memory footprint be scheduled at all?
+        *max_clusters = 1;
+        return CLUSTER ? cudaOccupancyMaxActiveClusters(max_clusters, kernel, &cfg) : cudaSuccess;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
+static cudaError_t dispatch_resident(adsel_handle *h, const GreedyArgs &a, const ResidentPlan &pl, bool dry_run, int *max_clusters) {
+    if (pl.csize > 1) return launch_resident<128, true, false>(h, a, pl.smem, dry_run, max_clusters);
+    if (a.prof) return pl.rb == 128 ? launch_resident<128, false, true>(h, a, pl.smem, dry_run, max_clusters)
+                                    : launch_resident<256, false, true>(h, a, pl.smem, dry_run, max_clusters);
+    return pl.rb == 128 ? launch_resident<128, false, false>(h, a, pl.smem, dry_run, max_clusters)
+                        : launch_resident<256, false, false>(h, a, pl.smem, dry_run, max_clusters);
+}
+
+// Cluster size / block size / shared-memory layout of the resident variant; false when the columns do not fit
+// (more than 16 CTAs' worth: the global-memory kernel above takes over) or ADSEL_GREEDY_CLUSTER=0 asks for that.
+// ADSEL_GREEDY_CLUSTER=1/2/4/8/16 forces a cluster size (tests, measurements); unset: the smallest that fits.
+static bool plan_resident(adsel_handle *h, GreedyArgs &a, int tl_want, ResidentPlan *out) {
+    const char *e = getenv("ADSEL_GREEDY_CLUSTER");
+    const int forced = (e && *e) ? atoi(e) : -1;
+    if (forced == 0) return false;
+    if (a.list_capacity >= (1ll << 40)) return false;
+    const size_t budget = 232448 - 512;   // 227 KB opt-in maximum per CTA minus the static shared variables
+    const long long cols = a.hi - a.lo;
+    for (int c = 1; c <= CLUSTER_MAX; c *= 2) {
+        if (forced > 0 && c != forced) continue;
+        if (c > 1 && a.prof) continue;
+        for (int rb = 128; rb <= 256; rb *= 2) {
+            if (c > 1 && rb != 128) continue;
+            long long per = (cols + c - 1) / c;
+            per = (per + rb - 1) / rb * rb;
+            if (per < rb) per = rb;
+            const long long nblk = per / rb;
+            const size_t fixed = resident_fixed_bytes(per, nblk, c > 1);
+            if (fixed > budget) continue;
+            size_t room = budget - fixed;
+            ResidentPlan pl;
+            pl.csize = c;
+            pl.rb = rb;
+            pl.cta_cols = (int)per;
+            pl.nblk = (int)nblk;
+            pl.tl_n = (int)((size_t)tl_want * 8 <= room ? tl_want : room / 8);
+            room -= (size_t)pl.tl_n * 8;
+            const size_t words = (size_t)(a.n + 31) / 32;
+            pl.sel_words = words * 4 <= room ? (int)words : 0;
+            pl.smem = fixed + (size_t)pl.tl_n * 8 + (size_t)pl.sel_words * 4;
+            a.csize = pl.csize;
+            a.cta_cols = pl.cta_cols;
+            a.r_nblk = pl.nblk;
+            a.tl_n = pl.tl_n;
+            a.sel_words = pl.sel_words;
+            int max_clusters = 0;
+            if (dispatch_resident(h, a, pl, true, &max_clusters) != cudaSuccess || max_clusters < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            *out = pl;
+            return true;
+        }
+    }
+    return false;
+}
+
+
+// ---- host side of the fast variant ---------------------------------------------------------------
+struct FastPlan {
+    int rb = 0, cols = 0, nblk = 0, g = 0;
+    size_t smem = 0;
+};
+
+// One resident CTA with the lean step (greedy_fast_kernel): no Euclid term, contiguous temporal groups, the
+// whole pool on this device, columns + block tables within 227 KB.  ADSEL_GREEDY_FAST=0 disables it.
+static bool plan_fast(const adsel_handle *h, const GreedyArgs &a, bool sharded, int g_want, FastPlan *out) {
+    const char *e = getenv("ADSEL_GREEDY_FAST");
+    if (e && atoi(e) == 0) return false;
+    const char *c = getenv("ADSEL_GREEDY_CLUSTER");
+    if (c && *c && atoi(c) != 1) return false;   // an explicit cluster size (or 0: global-memory kernel) was asked for
+    if (sharded || a.spatial == ADSEL_SPATIAL_EUCLID || (a.temporal && !a.groups_contiguous)) return false;
+    if (a.list_capacity >= (1ll << 40)) return false;
+    const size_t budget = 232448 - 128;   // 227 KB opt-in maximum per CTA minus the static shared variables
+    for (int rb = 128; rb <= 256; rb *= 2) {
+        const long long cols = ((long long)a.n + rb - 1) / rb * rb, nblk = cols / rb;
+        const size_t fixed = (size_t)cols * 8 + (size_t)nblk * (8 + 32 + 4 + 8);
+        if (fixed > budget) continue;
+        long long g = (long long)((budget - fixed) / 8);
+        if (g > g_want) g = g_want;
+        if ((nblk + g) & 1) g += ((size_t)(g + 1) * 8 <= budget - fixed) ? 1 : -1;   // cached records are 16-byte aligned
+        if (g < 0) continue;
+        out->rb = rb;
+        out->cols = (int)cols;
+        out->nblk = (int)nblk;
+        out->g = (int)g;
+        out->smem = fixed + (size_t)g * 8;
+        return true;
+    }
+    return false;
+}
+
+template <int RB, bool PROFILE>
+static cudaError_t launch_fast(adsel_handle *h, const GreedyArgs &a, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(greedy_fast_kernel<RB, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    greedy_fast_kernel<RB, PROFILE><<<1, RES_NT, smem, h->stream>>>(a);
+    return cudaGetLastError();
 }
 
 template <bool SHARDED>
@@ -866,12 +1541,11 @@ int greedy_preload() {
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<256, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<512, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<1024, false>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<256, true>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<512, true>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<1024, true>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<256, false>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<512, false>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_cluster_kernel<1024, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<128, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<128, false, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<256, false, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<128, true, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, temporal_lut_kernel));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, fill_u64_kernel2));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, frame_rec_kernel));
@@ -907,7 +1581,7 @@ int greedy_prepare(adsel_handle *h, const adsel_select_params *p, int32_t n_samp
     if (p->spatial == ADSEL_SPATIAL_GEODESIC) ADSEL_TRY(lists_prepare(h, sharded));
     ADSEL_TRY(h->fps.reserve(n));
     ADSEL_TRY(h->frame_rec.reserve(n));
-    ADSEL_TRY(h->is_selected.reserve(n));
+    ADSEL_TRY(h->is_selected.reserve((size_t)n * CLUSTER_MAX));   // one private copy per CTA of a resident cluster
     ADSEL_TRY(h->tlut.reserve(n));
     ADSEL_TRY(h->d_sampled.reserve(n_sampled > 0 ? n_sampled : 1));
     ADSEL_TRY(h->d_out.reserve(out_cap));
@@ -999,31 +1673,37 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
 
     if (n_sampled > 0)
         ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyHostToDevice, h->stream));
-    ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, n, h->stream));
     ADSEL_CUDA(cudaMemsetAsync(h->d_result.p, 0, sizeof(double) * 8, h->stream));
-    fill_u64_kernel2<<<h->num_sms * 2, 256, 0, h->stream>>>(h->fps.p, (size_t)n, far_bits);
-    h->launches += 1;
-    ADSEL_CUDA(cudaGetLastError());
     a.sel_words = n <= 524288 ? (n + 31) / 32 : 0;
     a.far_bits = far_bits;
     CommView view;
     if (sharded) ADSEL_TRY(comm_view(h, &view));
-    size_t csmem = 0;
-    int cta_cols = 0, csel = 0;
-    const int nt = greedy_threads();
-    const int csize = a.prof ? 0 : pick_cluster(a, nt, &csmem, &cta_cols, &csel);
-    if (csize > 0) {   // shared-memory-resident fps, one CTA per slice piece, exchange over distributed shared memory
-        a.csize = csize;
-        a.cta_cols = cta_cols;
-        a.sel_words = csel;
-        cudaError_t e;
-        if (sharded) e = nt == 256 ? launch_cluster_nt<256, true>(h, a, view, csmem) : nt == 1024 ? launch_cluster_nt<1024, true>(h, a, view, csmem)
-                                                                                                  : launch_cluster_nt<512, true>(h, a, view, csmem);
-        else e = nt == 256 ? launch_cluster_nt<256, false>(h, a, view, csmem) : nt == 1024 ? launch_cluster_nt<1024, false>(h, a, view, csmem)
-                                                                                           : launch_cluster_nt<512, false>(h, a, view, csmem);
-        ADSEL_CUDA(e);
-        h->greedy_cluster = csize;
+    ResidentPlan plan;
+    FastPlan fast;
+    const int tl_want = a.temporal ? (p->normalize == ADSEL_NORM_EXP && a.tl_n > 64 ? 64 : a.tl_n) : 0;
+    if (plan_fast(h, a, sharded, tl_want, &fast)) {   // one resident CTA, lean step
+        a.csize = 1;
+        a.cta_cols = fast.cols;
+        a.r_nblk = fast.nblk;
+        a.tl_n = fast.g;
+        a.sel_words = 0;
+        ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n, h->stream));
+        ADSEL_CUDA(a.prof ? (fast.rb == 128 ? launch_fast<128, true>(h, a, fast.smem) : launch_fast<256, true>(h, a, fast.smem))
+                          : (fast.rb == 128 ? launch_fast<128, false>(h, a, fast.smem) : launch_fast<256, false>(h, a, fast.smem)));
+        h->greedy_cluster = 1;
+    } else if (!sharded && plan_resident(h, a, tl_want, &plan)) {   // fps resident in shared memory (one CTA or a cluster)
+        ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n * plan.csize, h->stream));
+        int unused = 0;
+        ADSEL_CUDA(dispatch_resident(h, a, plan, false, &unused));
+        h->greedy_cluster = plan.csize;
     } else {
+        ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, n, h->stream));
+        fill_u64_kernel2<<<h->num_sms * 2, 256, 0, h->stream>>>(h->fps.p, (size_t)n, far_bits);
+        h->launches += 1;
+        ADSEL_CUDA(cudaGetLastError());
+        a.csize = 0;
+        a.tl_n = a.temporal ? (h->max_group < 4096 ? h->max_group : 4096) : 0;
+        a.sel_words = n <= 524288 ? (n + 31) / 32 : 0;
         const size_t smem = (size_t)nblk * 20 + (size_t)a.tl_n * 8 + (size_t)a.sel_words * 4 + 16;
         if (sharded) launch_greedy<true>(h, a, view, smem);
         else launch_greedy<false>(h, a, view, smem);

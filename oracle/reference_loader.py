@@ -12,15 +12,25 @@ stack: pycocotools, spconv, compiled ops), so
 3. the selector modules are then imported normally, e.g.
    ``det3d.selectors.spatial_temporal_selector``.
 
-Nothing here is used at run time on the GPU box (/root/reference does not exist there); it is used
-in this container by oracle/make_goldens.py to produce tests/golden/*.json and by
-``bench.py --impl reference`` only when the reference tree is present.
+Where /root/reference does not exist (the GPU box) the same unmodified files are found under ``oracle/_ref``,
+a byte-for-byte copy made in this container by ``oracle/make_ref.py`` (git-ignored, ships with the tree).
+Used by oracle/make_goldens.py to produce tests/golden/*.json and by ``bench.py --impl reference`` /
+``bench.py``'s ``cpu_baseline`` leg; never by the product path.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("ADSEL_REFERENCE_ROOT", "/root/reference")
+_LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/make_ref.py (git-ignored, ships to the GPU box)
+
+
+def _default_root() -> str:
+    if os.path.isdir("/root/reference/det3d"):
+        return "/root/reference"
+    return _LOCAL_COPY
+
+
+REFERENCE_ROOT = os.environ.get("ADSEL_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available() -> bool:

@@ -230,24 +230,50 @@ def test_grid_knn_equals_bruteforce_on_tie_heavy_and_degenerate_inputs(handle, m
     monkeypatch.delenv("ADSEL_KNN")
 
 
-@pytest.mark.parametrize("cluster", ["1", "2", "8"])
-def test_cluster_variant_of_the_greedy_loop_selects_identically(handle, pools, monkeypatch, cluster):
-    """ADSEL_GREEDY_CLUSTER: fps in shared memory, split over a thread-block cluster, exchange through DSMEM
-    (the measured alternative of DESIGN.md §5; off by default)."""
+@pytest.mark.parametrize("cluster", ["1", "2", "4", "8", "16"])
+def test_resident_variants_of_the_greedy_loop_select_identically(handle, pools, monkeypatch, cluster):
+    """ADSEL_GREEDY_CLUSTER: fps resident in the shared memory of 1 CTA or of a 2..16-CTA thread-block cluster
+    (exchange through DSMEM) against ADSEL_GREEDY_CLUSTER=0, the global-memory kernel."""
     infos = pools("P8K")["infos"]
     loc, run_id, max_td = _set_spatial_pool(handle, infos)
     handle.build_knn_graph(8)
     kw = dict(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0, budget=600, first_index=4242)
+    monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", "0")
     want, want_cost = handle.select(**kw)
     want_fps = handle.get_fps()
+    want2, _ = handle.select(**{**kw, "budget": 900, "sampled": want, "first_index": -1, "cost_start": want_cost})
     monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", cluster)
     got, cost = handle.select(**kw)
     assert got == want and cost == want_cost
     assert np.array_equal(handle.get_fps().view(np.uint64), want_fps.view(np.uint64))
     got2, _ = handle.select(**{**kw, "budget": 900, "sampled": got, "first_index": -1, "cost_start": cost})
-    monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
-    want2, _ = handle.select(**{**kw, "budget": 900, "sampled": want, "first_index": -1, "cost_start": want_cost})
     assert got2 == want2
+    # exhaustion: every frame taken, then the reference's assertion (spatial_temporal_selector.py:182)
+    small = pools("P300")["infos"]
+    _set_spatial_pool(handle, small)
+    handle.build_knn_graph(8)
+    for var in ("0", cluster):
+        monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", var)
+        with pytest.raises(AssertionError, match="has been selected"):
+            handle.select(**{**kw, "budget": 10 ** 6, "first_index": 7})
+    monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
+
+
+@pytest.mark.parametrize("variant", ["0", "2", "generic"])
+def test_every_golden_case_with_the_global_memory_the_cluster_and_the_generic_resident_kernel(pools, tmp_path, monkeypatch, variant):
+    """The default (one resident CTA, fast step where the mode allows) is what the golden tests above run; the same
+    18 cases through the global-memory kernel (pools beyond 16 CTAs' shared memory, the multi-GPU column shards), a
+    2-CTA cluster and the generic one-CTA resident kernel."""
+    if variant == "generic":
+        monkeypatch.setenv("ADSEL_GREEDY_FAST", "0")
+        variant = "1"
+    monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", variant)
+    golden = load_golden("P2K_all.json")
+    pl = pools("P2K")
+    for cid, case in golden["cases"].items():
+        res, _ = _run_case_through_selectors(pl, case, tmp_path)
+        assert res == case["selected_index"], f"{variant}/{cid}"
+    monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
 
 
 def test_p850_temporal_selector_budget_1200_identical_to_reference(pools, tmp_path):

@@ -1,69 +1,46 @@
 #!/usr/bin/env python
-"""Offline reader of an ``ncu --set full --import-source on`` report: per kernel, the SASS instructions with the most
-warp-stall samples and the samples by stall reason, as a small CSV for profiles/.
+"""Per-instruction view of an ``ncu --set full --import-source on`` capture, read offline.
 
-    python tools/ncu_hotspots.py gpurun_out/prof_greedy_r01c.ncu-rep profiles/r01c_greedy_hotspots.csv [--top 30] [--kernel substr]
-
-Needs only the ``ncu`` CLI (no GPU): it shells out to ``ncu -i <rep> --page source --csv``.
+usage: ncu -i X.ncu-rep --page source --csv > src.csv;  python tools/ncu_hotspots.py src.csv [steps] [top]
+Prints the executed warp-instructions per step by opcode, the stall samples by reason and the hottest SASS sites.
 """
-import argparse
 import csv
-import subprocess
 import sys
-
-
-def kernels_of(report):
-    text = subprocess.run(["ncu", "-i", report, "--page", "source", "--csv"], capture_output=True, text=True, check=True).stdout
-    rows = list(csv.reader(text.splitlines()))
-    i = 0
-    while i < len(rows):
-        if rows[i] and rows[i][0] == "Kernel Name":
-            name, hdr, body, j = rows[i][1], rows[i + 1], [], i + 2
-            while j < len(rows) and not (rows[j] and rows[j][0] == "Kernel Name"):
-                if len(rows[j]) == len(hdr):
-                    body.append(rows[j])
-                j += 1
-            yield name, hdr, body
-            i = j
-        else:
-            i += 1
+from collections import Counter
 
 
 def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("report")
-    ap.add_argument("out")
-    ap.add_argument("--top", type=int, default=30)
-    ap.add_argument("--kernel", default="", help="only kernels whose name contains this")
-    ap.add_argument("--note", default="")
-    args = ap.parse_args()
-    seen = set()
-    with open(args.out, "w", newline="") as f:
-        w = csv.writer(f)
-        for name, hdr, body in kernels_of(args.report):
-            if args.kernel not in name or not body or name in seen:      # first launch of every distinct kernel
-                continue
-            seen.add(name)
-            si, src, addr = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Address")
-            stall = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "(Not Issued)" not in h]
-            base, total = int(body[0][addr], 16), sum(int(r[si]) for r in body)
-            w.writerow([f"# {name}: warp-stall samples per SASS instruction (ncu -i {args.report.split('/')[-1]} --page source "
-                        f"--csv); top {args.top} of {len(body)} instructions, {total} samples. {args.note}"])
-            w.writerow(["offset", "sass", "samples", "share_pct", "dominant_stall", "preceding_instruction"])
-            for k in sorted(range(len(body)), key=lambda k: -int(body[k][si]))[: args.top]:
-                r = body[k]
-                dom = max(stall, key=lambda i: int(r[i] or 0))
-                w.writerow([hex(int(r[addr], 16) - base), r[src].strip(), r[si], f"{100 * int(r[si]) / max(total, 1):.1f}",
-                            f"{hdr[dom]}={r[dom]}", body[k - 1][src].strip() if k else ""])
-            w.writerow([])
-            w.writerow(["# all samples by stall reason"])
-            agg = {hdr[i]: sum(int(r[i] or 0) for r in body) for i in stall}
-            for reason, v in sorted(agg.items(), key=lambda kv: -kv[1]):
-                if v:
-                    w.writerow([reason, v, f"{100 * v / max(sum(agg.values()), 1):.1f}"])
-            w.writerow([])
-    return 0
+    path = sys.argv[1]
+    steps = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+    top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    rows = list(csv.reader(open(path)))
+    hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    hdr = rows[hdr_i]
+    col = {name: i for i, name in enumerate(hdr)}
+    body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+    stall_cols = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
+    by_op, by_reason, total_samples, total_inst = Counter(), Counter(), 0, 0
+    sites = []
+    for k, r in enumerate(body):
+        sass = r[col["Source"]].strip()
+        op = sass.split()[0] if not sass.startswith("@") else sass.split()[1]
+        op = op.rstrip(";")
+        ex = int(r[col["Instructions Executed"]] or 0)
+        sm = int(r[col["# Samples"]] or 0)
+        by_op[op.split(".")[0]] += ex
+        total_inst += ex
+        total_samples += sm
+        for n in stall_cols:
+            by_reason[n] += int(r[col[n]] or 0)
+        sites.append((sm, ex, k, sass, {n: int(r[col[n]] or 0) for n in stall_cols if int(r[col[n]] or 0)}))
+    print(f"warp-instructions executed: {total_inst} = {total_inst / steps:.0f} per step; samples {total_samples}")
+    print("by opcode (per step):", ", ".join(f"{o} {c / steps:.0f}" for o, c in by_op.most_common(24)))
+    print("stall samples:", ", ".join(f"{n[6:]} {100 * c / max(total_samples, 1):.1f}%" for n, c in by_reason.most_common(10)))
+    print(f"top {top} sites by samples:")
+    for sm, ex, k, sass, why in sorted(sites, reverse=True)[:top]:
+        w = ", ".join(f"{n[6:]} {c}" for n, c in sorted(why.items(), key=lambda t: -t[1])[:3])
+        print(f"  #{k:5d} {100 * sm / max(total_samples, 1):5.1f}%  exec/step {ex / steps:6.1f}  {sass[:70]:70s} {w}")
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    main()
