@@ -66,12 +66,15 @@ struct DevBuf {
 
 namespace adsel {
 // Everything the greedy kernel needs about the frame it just selected, fetched in one round trip.
+// Two self-tagged 16-byte halves: a copy that is being overwritten asynchronously (cp.async into the greedy
+// kernel's shared-memory cache) is valid exactly when both tags name the frame that is looked up.
 struct __align__(16) FrameRec {
     long long list_off;   // neighbour list of this frame (entries inside this rank's column slice)
     int list_len;
+    unsigned self;        // the frame this record describes
     int e0, e1;           // its temporal group as a range of group_members
-    int n_boxes;
-    double box_cost;      // n_boxes * cost_b, rounded once (the reference's per-frame product)
+    int n_boxes;          // box cost = n_boxes * cost_b, rounded once (the reference's per-frame product)
+    unsigned self2;
 };
 
 // Where one rank's neighbour lists live: its own buffers, or the lists region of its arena (sharded, so that

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(NT, 1) greedy_select_kernel(const GreedyArgs a
             set_selected(a, selbits, first);
             sh.cost = __dadd_rn(sh.cost, a.cost_f);
             fetch_frame(a, sh, first);
-            sh.cost = __dadd_rn(sh.cost, sh.rec.box_cost);
+            sh.cost = __dadd_rn(sh.cost, __dmul_rn((double)sh.rec.n_boxes, a.cost_b));
         }
     }
     __syncthreads();
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(NT, 1) greedy_select_kernel(const GreedyArgs a
                         sh.m = 1;
                         set_selected(a, selbits, nxt);
                         sh.cost = __dadd_rn(sh.cost, a.cost_f);
-                        sh.cost = __dadd_rn(sh.cost, rec.box_cost);
+                        sh.cost = __dadd_rn(sh.cost, __dmul_rn((double)rec.n_boxes, a.cost_b));
                         sh.rec = rec;
                         sh.me = me;
                         sh.cur = nxt;
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(NT, 1) greedy_select_kernel(const GreedyArgs a
                         sh.stop = 1;
                     } else {
                         sh.cost = __dadd_rn(sh.cost, a.cost_f);          // :184
-                        sh.cost = __dadd_rn(sh.cost, rec.box_cost);      // :185 (n_boxes*cost_b, one rounded product)
+                        sh.cost = __dadd_rn(sh.cost, __dmul_rn((double)rec.n_boxes, a.cost_b));      // :185 (n_boxes*cost_b, one rounded product)
                         if (sh.cost > a.budget) {                                                    // :186
                             sh.stop = 1;
                         } else if (sh.m >= a.out_cap) {
@@ -561,6 +561,14 @@ __device__ __forceinline__ Best cluster_exchange(unsigned long long *xslot, unsi
         const int dep = *(volatile int *)&sh.err;    /* consume shared memory: a deferred barrier blocks here */ \
         long long now;                                    \
         asm volatile("{\n.reg .b32 t;\nmov.b32 t, %1;\nmov.u64 %0, %%clock64;\n}" : "=l"(now) : "r"(dep) : "memory"); \
+        prof_acc[slot] += (unsigned long long)(now - prof_t); \
+        prof_t = now;                                     \
+    }
+
+#define FPROF(slot)                                       \
+    if (PROFILE && threadIdx.x == 0) {                     \
+        long long now;                                    \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(now) :: "memory"); \
         prof_acc[slot] += (unsigned long long)(now - prof_t); \
         prof_t = now;                                     \
     }
@@ -738,12 +746,12 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_resident_kernel(const Greedy
         if (lane == 0 && pend_lb >= 0) {
             BlkRec br;
             br.idx = (unsigned)pend_idx;
-            br.off_lo = pend_lo.x;      // FrameRec: list_off (8), list_len, e0 | e1, n_boxes, box_cost (8)
+            br.off_lo = pend_lo.x;      // FrameRec: list_off (8), list_len, self | e0, e1, n_boxes, self2
             br.off_hi = pend_lo.y;
             br.list_len = (int)pend_lo.z;
-            br.e0 = (int)pend_lo.w;
-            br.e1 = (int)pend_hi.x;
-            br.n_boxes = (int)pend_hi.y;
+            br.e0 = (int)pend_hi.x;
+            br.e1 = (int)pend_hi.y;
+            br.n_boxes = (int)pend_hi.z;
             blk_rec[pend_lb] = br;
             pend_lb = -1;
         }
@@ -945,8 +953,8 @@ __global__ void frame_rec_kernel(FrameRec *rec, int n, const int64_t *list_off, 
     const int g = group_id[i];
     r.e0 = group_ptr[g];
     r.e1 = group_ptr[g + 1];
-    r.n_boxes = n_boxes[i];
-    r.box_cost = __dmul_rn((double)r.n_boxes, cost_b);   // anno["gt_names"].shape[0] * cost_b (base_selector.py:85)
+    r.n_boxes = n_boxes[i];   // anno["gt_names"].shape[0]; the kernels form n_boxes * cost_b as one rounded product (base_selector.py:85)
+    r.self = r.self2 = (unsigned)i;
     rec[i] = r;
 }
 
@@ -965,7 +973,7 @@ int comm_view(adsel_handle *h, CommView *view);
 
 static unsigned long long *greedy_prof_ptr() {
     static unsigned long long *buf = nullptr;
-    if (!buf) cudaMalloc(&buf, 12 * sizeof(unsigned long long));
+    if (!buf) cudaMalloc(&buf, 16 * sizeof(unsigned long long));
     return buf;
 }
 
@@ -997,8 +1005,8 @@ static int greedy_threads() {
 #define ADSEL_PIN64(x) asm volatile("" : "+l"(x))
 #define ADSEL_PINF64(x) asm volatile("" : "+d"(x))
 
-struct FastShared {
-    int ndirty[2];
+struct __align__(8) FastShared {
+    int2 nd[2];           // per step parity: x = blocks listed for a re-reduce, y = the step's frame had been selected before
     int err, err_frame, sat;
 };
 
@@ -1035,12 +1043,17 @@ __device__ __forceinline__ int atom_inc_shared(int *p) {
     return old;
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <int RB, bool PROFILE>
 __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs a) {
     constexpr int NT = RES_NT, NW = NT / 32, PER = RB / 32;
     constexpr int SHIFT = RB == 256 ? 8 : 7;
     static_assert(RB == 128 || RB == 256, "block size");
-    unsigned long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_t = PROFILE ? clock64() : 0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
@@ -1051,7 +1064,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     const FrameRec *recs = a.rec;
     int32_t *out = a.out;
     unsigned char *sel_bytes = a.is_selected;
-    double budget = a.budget, cost_f = a.cost_f;
+    double budget = a.budget, cost_f = a.cost_f, cost_b = a.cost_b;
     const bool has_list = a.spatial == ADSEL_SPATIAL_GEODESIC, has_group = a.temporal != 0;
     ADSEL_PIN32(n);
     ADSEL_PIN32(nblk);
@@ -1064,14 +1077,16 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     ADSEL_PIN64(sel_bytes);
     ADSEL_PINF64(budget);
     ADSEL_PINF64(cost_f);
+    ADSEL_PINF64(cost_b);
 
     extern __shared__ unsigned long long greedy_smem[];
     unsigned long long *fps_s = greedy_smem;                              // [cols]
     unsigned long long *blk_val = fps_s + cols;                           // [nblk]
     unsigned long long *gval = blk_val + nblk;                            // [G] row value of a group member at index gap d
-    uint4 *blk_rec = reinterpret_cast<uint4 *>(gval + G);                 // [nblk][2] FrameRec of the block's best frame, n_boxes := frame
+    uint4 *blk_rec = reinterpret_cast<uint4 *>(gval + G);                 // [nblk][2] FrameRec of the block's best frame (self-tagged halves)
     int *blk_idx = reinterpret_cast<int *>(blk_rec + 2 * (size_t)nblk);   // [nblk]
     int *dirty_list = blk_idx + nblk;                                     // [2 * nblk]
+    int *blk_step = dirty_list + 2 * nblk;                                // [nblk] step that last re-reduced the block (its cached record may still be landing)
     __shared__ FastShared sh;
 
     const unsigned long long far_bits = a.far_bits;
@@ -1084,16 +1099,14 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
         const bool nonempty = first < n;
         blk_val[lb] = nonempty ? far_bits : 0ull;
         blk_idx[lb] = nonempty ? first : 0x7fffffff;
-        uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0xffffffffu, 0, 0);
-        if (nonempty) {
-            ldg_rec_async(recs + first, lo, hi);
-            hi.y = (unsigned)first;
-        }
+        blk_step[lb] = -1;
+        uint4 lo = make_uint4(0, 0, 0, 0xffffffffu), hi = make_uint4(0, 0, 0, 0xffffffffu);
+        if (nonempty) ldg_rec_async(recs + first, lo, hi);
         blk_rec[2 * lb] = lo;
         blk_rec[2 * lb + 1] = hi;
     }
     if (tid == 0) {
-        sh.ndirty[0] = sh.ndirty[1] = 0;
+        sh.nd[0] = sh.nd[1] = make_int2(0, 0);
         sh.err = 0;
         sh.err_frame = -1;
         sh.sat = 0;
@@ -1116,43 +1129,44 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
 
     // ---- state replicated in the registers of every thread ----
     double cost = a.cost_start;
-    int m = 0, cur = -1, stop = 0, par = 0;
+    int m = 0, cur = -1, cur_blk = -1, stop = 0, par = 0;
     long long l_off = 0;
     int l_len = 0, e0 = 0, e1 = 0;
     int to_flag = -1;                // thread 0: frame whose selected flag is checked / set in the next apply
     bool flag_check = false;
     unsigned flag_seen = 0;
-    int pend_lb = -1, pend_idx = 0;  // lane 0 of every warp: record in flight for a refreshed block's best frame
-    uint4 pend_lo = make_uint4(0, 0, 0, 0), pend_hi = make_uint4(0, 0, 0, 0);
-
     bool marking = true;             // false while the rows of the buffer are applied (all blocks are re-reduced afterwards)
+
     auto lower = [&](int j, unsigned long long v) {
         if (v < fps_s[j]) {
             fps_s[j] = v;
             const int lb = j >> SHIFT;
-            // only the entry that IS the block's maximum can change it by decreasing; a block can be listed twice
-            // per step (group phase, list phase) -- it is then re-reduced twice with the same result
-            if (marking && blk_idx[lb] == j) dirty_list[atom_inc_shared(&sh.ndirty[par])] = lb;
+            // Only the entry that IS a block's maximum can change it by decreasing.  The block of the row's own
+            // frame is always re-reduced (warp 0), so it is not listed; another block can be listed twice per step
+            // (group phase, list phase) and is then re-reduced twice with the same result.
+            if (lb != cur_blk && marking && blk_idx[lb] == j) dirty_list[atom_inc_shared(&sh.nd[par].x)] = lb;
         }
     };
-    auto take_rec = [&](const uint4 &lo, const uint4 &hi) -> double {   // FrameRec words -> row state; returns box_cost
+    auto take_rec = [&](const uint4 &lo, const uint4 &hi) -> double {   // FrameRec words -> row state; returns the box cost
         l_off = (long long)(((unsigned long long)lo.y << 32) | lo.x);
         l_len = has_list ? (int)lo.z : 0;
-        e0 = (int)lo.w;
-        e1 = (int)hi.x;
-        return __longlong_as_double((long long)(((unsigned long long)hi.w << 32) | hi.z));
+        e0 = (int)hi.x;
+        e1 = (int)hi.y;
+        return __dmul_rn((double)(int)hi.z, cost_b);   // n_boxes * cost_b, one rounded product (base_selector.py:85)
     };
     auto apply = [&]() {
         // 1. list loads in flight (the one L2 round trip of a step)
+        const int32_t *pi = lidx + l_off + tid;
+        const double *pv = lval + l_off + tid;
         int j0 = -1, j1 = -1;
         unsigned long long v0 = 0, v1 = 0;
         if (tid < l_len) {
-            j0 = lidx[l_off + tid];
-            v0 = (unsigned long long)__double_as_longlong(lval[l_off + tid]);
+            j0 = *pi;
+            v0 = (unsigned long long)__double_as_longlong(*pv);
         }
         if (tid + NT < l_len) {
-            j1 = lidx[l_off + tid + NT];
-            v1 = (unsigned long long)__double_as_longlong(lval[l_off + tid + NT]);
+            j1 = pi[NT];
+            v1 = (unsigned long long)__double_as_longlong(pv[NT]);
         }
         // 2. temporal group in their shadow: frames [e0, e1) within the LUT's unsaturated reach of cur
         if (has_group) {
@@ -1164,52 +1178,53 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
                 lower(j, v);
             }
         }
+        FPROF(0)
         __syncthreads();   // group writes before list writes (list values of same-group frames are <= the group values); hidden under the list loads
+        RPROF_MARK(1)
         // 3. list entries: unique columns, plain writes
         if (j0 >= 0) lower(j0, v0);
         if (j1 >= 0) lower(j1, v1);
-        for (int t = tid + 2 * NT; t < l_len; t += NT) lower(lidx[l_off + t], (unsigned long long)__double_as_longlong(lval[l_off + t]));
-        // 4. deferred work that must not race with the reads made before the barrier above
-        if (lane == 0 && pend_lb >= 0) {
-            pend_hi.y = (unsigned)pend_idx;   // n_boxes slot := frame the record belongs to
-            blk_rec[2 * pend_lb] = pend_lo;
-            blk_rec[2 * pend_lb + 1] = pend_hi;
-            pend_lb = -1;
-        }
-        if (tid == 0 && to_flag >= 0) {   // :182 assert, evaluated a phase late so that the flag load is off the chain
+        for (int t = tid + 2 * NT; t < l_len; t += NT) lower(pi[t - tid], (unsigned long long)__double_as_longlong(pv[t - tid]));
+        // records copied into blk_rec by last step's refresh: landed long ago; waited for here, where none of this thread's
+        // own loads is in flight (the wait is a scoreboard barrier that would also wait for those)
+        if (lane == 0) cp_async_wait_all();
+        FPROF(2)
+        // 4. the selected flag of the row's frame: :182 assert, evaluated a phase late so that the flag load is off the chain
+        if (tid == 0 && to_flag >= 0) {
             if (flag_check && flag_seen) {
-                sh.err = 1;
                 sh.err_frame = to_flag;
+                sh.nd[par].y = 1;                       // read with the block count after the next barrier
             } else {
                 sel_bytes[to_flag] = 1;
             }
             to_flag = -1;
         }
     };
-
-    // re-reduce the first nd blocks of dirty_list, one warp per block
-    auto refresh = [&](int nd) {
-        for (int q = wid; q < nd; q += NW) {
-            const int lb = dirty_list[q];
-            const int base = (lb << SHIFT) + lane;
-            unsigned hi[PER], lo[PER];
-            int idx[PER];
+    // Re-reduce one block: every lane PER entries, three REDUX; lane 0 stores the maximum and starts the asynchronous
+    // copy of the best frame's record into the block's cache slot (valid once both halves carry the frame's tag).
+    auto refresh_block = [&](int lb, int step) {
+        const int base = (lb << SHIFT) + lane;
+        unsigned hi[PER], lo[PER];
+        int idx[PER];
 #pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const unsigned long long v = fps_s[base + 32 * i];
-                hi[i] = (unsigned)(v >> 32);
-                lo[i] = (unsigned)v;
-                idx[i] = base + 32 * i < n ? base + 32 * i : 0x7fffffff;
-            }
-            const Win x = warp_argmax<PER>(hi, lo, idx);
-            if (lane == 0) {
-                blk_val[lb] = ((unsigned long long)x.hi << 32) | x.lo;
-                blk_idx[lb] = x.idx;
-                if (x.idx != 0x7fffffff) {   // its record: in flight now, stored into blk_rec during the next apply
-                    pend_lb = lb;
-                    pend_idx = x.idx;
-                    ldg_rec_async(recs + x.idx, pend_lo, pend_hi);
-                }
+        for (int i = 0; i < PER; ++i) {
+            const unsigned long long v = fps_s[base + 32 * i];
+            hi[i] = (unsigned)(v >> 32);
+            lo[i] = (unsigned)v;
+            idx[i] = base + 32 * i < n ? base + 32 * i : 0x7fffffff;
+        }
+        if (PROFILE) asm volatile("" ::"r"(hi[0] + hi[PER - 1] + lo[0]));
+        FPROF(5)
+        const Win x = warp_argmax<PER>(hi, lo, idx);
+        if (PROFILE) asm volatile("" ::"r"(x.idx));
+        FPROF(6)
+        if (lane == 0) {
+            blk_val[lb] = ((unsigned long long)x.hi << 32) | x.lo;
+            blk_idx[lb] = x.idx;
+            blk_step[lb] = step;
+            if (x.idx != 0x7fffffff) {
+                cp_async16(blk_rec + 2 * lb, recs + x.idx);
+                cp_async16(blk_rec + 2 * lb + 1, reinterpret_cast<const char *>(recs + x.idx) + 16);
             }
         }
     };
@@ -1233,6 +1248,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             for (int t = 0; t < a.n_sampled; ++t) sel_bytes[a.sampled[t]] = 1;
         if (a.n_sampled == 0) {   // empty buffer: the caller's random.choice is taken and costed up front (:168,172-174)
             cur = a.first_index;
+            cur_blk = cur >> SHIFT;
             uint4 lo, hi;
             ldg_rec_async(recs + cur, lo, hi);
             const double box_cost = take_rec(lo, hi);
@@ -1252,35 +1268,37 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
                 __syncthreads();
             }
             marking = true;
+            cur_blk = -1;
             // every block maximum and its cached record from scratch
-            for (int lb = tid; lb < nblk; lb += NT) dirty_list[lb] = lb;
-            __syncthreads();
-            refresh(nblk);
-            pend_lb = -1;
-            __syncthreads();
-            for (int lb = tid; lb < nblk; lb += NT) {
-                const int best = blk_idx[lb];
-                if (best != 0x7fffffff) {
-                    uint4 lo, hi;
-                    ldg_rec_async(recs + best, lo, hi);
-                    hi.y = (unsigned)best;
-                    blk_rec[2 * lb] = lo;
-                    blk_rec[2 * lb + 1] = hi;
-                }
-            }
+            for (int lb = wid; lb < nblk; lb += NW) refresh_block(lb, -1);
+            if (lane == 0) cp_async_wait_all();
             __syncthreads();
         }
         while (true) {
-            RPROF_MARK(7)
             if (!seeding) apply();
-            RPROF_MARK(0)
+            FPROF(3)
             __syncthreads();
-            RPROF_MARK(1)
-            refresh(sh.ndirty[par]);
-            RPROF_MARK(2)
+            RPROF_MARK(4)
+            // re-reduce the row's own block (warp 0) and the blocks whose maximum was lowered (the other warps)
+            const int2 nde = sh.nd[par];
+            const int nd = nde.x;
+            if (nde.y) {   // :182 assert -- the frame applied in this step had been selected before
+                stop = 2;
+                break;
+            }
+            if (PROFILE && tid == 0) {
+                prof_acc[13] += nd > 0 ? 1 : 0;
+                prof_acc[14] += nd;
+            }
+            if (wid == 0) {
+                if (cur_blk >= 0) refresh_block(cur_blk, (int)steps);
+            } else {
+                for (int q = wid - 1; q < nd; q += NW - 1) refresh_block(dirty_list[q], (int)steps);
+            }
+            FPROF(7)
             __syncthreads();
-            RPROF_MARK(3)
-            if (tid == 0) sh.ndirty[par] = 0;   // the next apply counts in the other word (zeroed a step ago)
+            RPROF_MARK(8)
+            if (tid == 0) sh.nd[par] = make_int2(0, 0);   // the next apply counts in the other word (zeroed a step ago)
             par ^= 1;
             // arg-max over the block maxima, by every warp (no broadcast, no barrier)
             Win y;
@@ -1298,27 +1316,31 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
                     lo[q] = (unsigned)v;
                     idx[q] = ok ? blk_idx[b] : 0x7fffffff;
                 }
+                if (PROFILE) asm volatile("" ::"r"(hi[0] + hi[3] + idx[0] + idx[3]));
+                FPROF(9)
                 const Win w = warp_argmax<4>(hi, lo, idx);
                 const bool take = w.hi > y.hi || (w.hi == y.hi && (w.lo > y.lo || (w.lo == y.lo && w.idx < y.idx)));
                 if (take) y = w;
             }
-            RPROF_MARK(4)
+            FPROF(10)
+            const int this_step = (int)steps;
             ++steps;
-            if (sh.err) {   // :182 assert -- the frame applied in this step had been selected before
-                stop = 2;
-                break;
-            }
             const int nxt = y.idx;
             if (nxt < 0 || nxt >= n) {   // empty pool: cannot happen with n > 0
                 if (tid == 0) a.result[1] = (double)ADSEL_ERR_INVALID;
                 stop = 2;
                 break;
             }
-            // the winner's record: cached with its block's maximum, else one global round trip
-            uint4 rlo = blk_rec[2 * (nxt >> SHIFT)], rhi = blk_rec[2 * (nxt >> SHIFT) + 1];
-            if (rhi.y != (unsigned)nxt) ldg_rec_async(recs + nxt, rlo, rhi);
-            const double box_cost = take_rec(rlo, rhi);
+            // The winner's record: cached with its block's maximum (both halves tagged with the frame).  A block re-reduced in
+            // THIS step may still be receiving its record (cp.async), so it is not trusted: one global round trip instead.
             cur = nxt;
+            cur_blk = nxt >> SHIFT;
+            uint4 rlo = blk_rec[2 * cur_blk], rhi = blk_rec[2 * cur_blk + 1];
+            if (blk_step[cur_blk] == this_step || rlo.w != (unsigned)nxt || rhi.w != (unsigned)nxt) {
+                ldg_rec_async(recs + nxt, rlo, rhi);
+                if (PROFILE && tid == 0) prof_acc[12] += 1;
+            }
+            const double box_cost = take_rec(rlo, rhi);
             if (seeding) {   // :165,172-174 -- always taken, no budget check
                 seeding = false;
                 if (tid == 0) out[0] = nxt;
@@ -1330,7 +1352,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             }
             if (tid == 0) flag_seen = __ldcg(sel_bytes + nxt);   // consumed in the next apply, or below when the loop ends here
             cost = __dadd_rn(cost, cost_f);        // :184
-            cost = __dadd_rn(cost, box_cost);      // :185 (n_boxes * cost_b, one rounded product)
+            cost = __dadd_rn(cost, box_cost);      // :185
             const bool over = cost > budget;       // :186
             const bool full = !over && m >= out_cap;
             if (over || full) {
@@ -1350,11 +1372,12 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             m += 1;
             to_flag = nxt;
             flag_check = true;
-            RPROF_MARK(5)
+            FPROF(11)
         }
     }
     __syncthreads();
-    if (stop == 2 && sh.err && tid == 0) {
+    if (lane == 0) cp_async_wait_all();
+    if (stop == 2 && sh.err_frame >= 0 && tid == 0) {
         a.result[1] = (double)ADSEL_ERR_RESELECTED;
         a.result[4] = (double)sh.err_frame;
     }
@@ -1364,7 +1387,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
         a.result[2] = (double)m;
         a.result[3] = (double)steps;
         if (PROFILE)
-            for (int i = 0; i < 12; ++i) a.prof[i] = prof_acc[i];
+            for (int i = 0; i < 16; ++i) a.prof[i] = prof_acc[i];
     }
 }
 
@@ -1485,7 +1508,7 @@ static bool plan_fast(const adsel_handle *h, const GreedyArgs &a, bool sharded, 
     const size_t budget = 232448 - 128;   // 227 KB opt-in maximum per CTA minus the static shared variables
     for (int rb = 128; rb <= 256; rb *= 2) {
         const long long cols = ((long long)a.n + rb - 1) / rb * rb, nblk = cols / rb;
-        const size_t fixed = (size_t)cols * 8 + (size_t)nblk * (8 + 32 + 4 + 8);
+        const size_t fixed = (size_t)cols * 8 + (size_t)nblk * (8 + 32 + 4 + 8 + 4);
         if (fixed > budget) continue;
         long long g = (long long)((budget - fixed) / 8);
         if (g > g_want) g = g_want;
@@ -1761,9 +1784,17 @@ int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *
         ADSEL_CUDA(cudaMemcpyAsync(result, h->d_result.p, sizeof(result), cudaMemcpyDeviceToHost, h->stream));
         ADSEL_TRY(end_stage(h, 3));
         if (getenv("ADSEL_GREEDY_PROFILE")) {
-            unsigned long long prof[12];
+            unsigned long long prof[16];
             cudaMemcpy(prof, greedy_prof_ptr(), sizeof(prof), cudaMemcpyDeviceToHost);
             const double steps = result[3] > 0 ? result[3] : 1;
+            if (h->greedy_cluster == 1)
+                fprintf(stderr, "[fast profile] cycles/step: issue+group %.0f | bar0 %.0f | list lower %.0f | pend+flags %.0f | bar1 %.0f | "
+                                "refresh loads %.0f | refresh argmax %.0f | refresh store %.0f | bar2 %.0f | reduce loads %.0f | reduce argmax %.0f | bookkeeping %.0f\n",
+                        prof[0] / steps, prof[1] / steps, prof[2] / steps, prof[3] / steps, prof[4] / steps, prof[5] / steps, prof[6] / steps,
+                        prof[7] / steps, prof[8] / steps, prof[9] / steps, prof[10] / steps, prof[11] / steps);
+            if (h->greedy_cluster == 1)
+                fprintf(stderr, "[fast profile] record-cache misses %.3f per step; steps with other blocks to re-reduce %.3f, blocks per step %.3f\n",
+                        prof[12] / steps, prof[13] / steps, prof[14] / steps);
             fprintf(stderr, "[greedy profile] cycles/step: apply %.0f | wait B1 %.0f | refresh %.0f | wait B2 %.0f | reduce(+exchange) %.0f | "
                             "fetch+bookkeeping %.0f | wait B3 %.0f | loop %.0f\n",
                     prof[0] / steps, prof[1] / steps, prof[2] / steps, prof[3] / steps, prof[4] / steps, prof[5] / steps,
