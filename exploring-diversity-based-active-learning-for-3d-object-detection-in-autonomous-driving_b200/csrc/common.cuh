@@ -287,4 +287,39 @@ __device__ __forceinline__ double aggregate_value(double s, double t, int agg, d
     return fmax(s, t);
 }
 
+// Row value from its spatial and temporal terms (one-term selectors pass the other term through).
+__device__ __forceinline__ double combine(int spatial, int temporal, int aggregate, double lambda_t, double s, double t) {
+    if (spatial != ADSEL_SPATIAL_NONE && temporal) return aggregate_value(s, t, aggregate, lambda_t);
+    return spatial != ADSEL_SPATIAL_NONE ? s : t;
+}
+
+
+struct Win {
+    unsigned hi, lo;
+    int idx;
+};
+
+// Warp-wide arg-max over CNT (hi, lo, idx) candidates per lane: largest 64-bit key, lowest idx among equal keys.
+template <int CNT>
+__device__ __forceinline__ Win warp_argmax(const unsigned (&hi)[CNT], const unsigned (&lo)[CNT], const int (&idx)[CNT]) {
+    const unsigned full = 0xffffffffu;
+    unsigned h = hi[0];
+#pragma unroll
+    for (int i = 1; i < CNT; ++i) h = max(h, hi[i]);
+    const unsigned mhi = __reduce_max_sync(full, h);
+    unsigned l = 0u;
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) l = max(l, hi[i] == mhi ? lo[i] : 0u);
+    const unsigned mlo = __reduce_max_sync(full, l);
+    int c = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) c = min(c, (hi[i] == mhi && lo[i] == mlo) ? idx[i] : 0x7fffffff);
+    Win w;
+    w.hi = mhi;
+    w.lo = mlo;
+    w.idx = __reduce_min_sync(full, c);
+    return w;
+}
+
+
 }  // namespace adsel

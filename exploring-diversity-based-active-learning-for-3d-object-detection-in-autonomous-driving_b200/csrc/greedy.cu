@@ -96,11 +96,6 @@ __device__ __forceinline__ Best warp_best(Best x) {
     return r;
 }
 
-__device__ __forceinline__ double combine(int spatial, int temporal, int aggregate, double lambda_t, double s, double t) {
-    if (spatial != ADSEL_SPATIAL_NONE && temporal) return aggregate_value(s, t, aggregate, lambda_t);
-    return spatial != ADSEL_SPATIAL_NONE ? s : t;
-}
-
 struct GreedyShared {
     FrameRec rec;
     double2 me;
@@ -967,6 +962,9 @@ static double host_normalize_far(int norm_mode, double d, double divisor) {
 }
 
 int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, bool sharded);
+bool lazy_wanted(const adsel_handle *h, const adsel_select_params *p);
+int lazy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled, int32_t first_index,
+                int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
 int lists_prepare(adsel_handle *h, bool sharded);
 int grow_lists(adsel_handle *h, long long needed);
 int comm_view(adsel_handle *h, CommView *view);
@@ -1005,37 +1003,14 @@ static int greedy_threads() {
 #define ADSEL_PIN64(x) asm volatile("" : "+l"(x))
 #define ADSEL_PINF64(x) asm volatile("" : "+d"(x))
 
-struct __align__(8) FastShared {
-    int2 nd[2];           // per step parity: x = blocks listed for a re-reduce, y = the step's frame had been selected before
+struct __align__(16) FastShared {
+    int4 nd[2];                  // per step parity: x = blocks listed for a re-reduce, y = the step's frame had been selected before,
+                                 // z = an entry of the previous step's block was lowered (that block is re-reduced in full)
+    uint4 sub_rec[8][2];         // record of every sub-block's best frame of the row's own block, copied in asynchronously
+    unsigned long long sub_val[8];
+    int sub_idx[8];
     int err, err_frame, sat;
 };
-
-struct Win {
-    unsigned hi, lo;
-    int idx;
-};
-
-// Warp-wide arg-max over CNT (hi, lo, idx) candidates per lane: largest 64-bit key, lowest idx among equal keys.
-template <int CNT>
-__device__ __forceinline__ Win warp_argmax(const unsigned (&hi)[CNT], const unsigned (&lo)[CNT], const int (&idx)[CNT]) {
-    const unsigned full = 0xffffffffu;
-    unsigned h = hi[0];
-#pragma unroll
-    for (int i = 1; i < CNT; ++i) h = max(h, hi[i]);
-    const unsigned mhi = __reduce_max_sync(full, h);
-    unsigned l = 0u;
-#pragma unroll
-    for (int i = 0; i < CNT; ++i) l = max(l, hi[i] == mhi ? lo[i] : 0u);
-    const unsigned mlo = __reduce_max_sync(full, l);
-    int c = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < CNT; ++i) c = min(c, (hi[i] == mhi && lo[i] == mlo) ? idx[i] : 0x7fffffff);
-    Win w;
-    w.hi = mhi;
-    w.lo = mlo;
-    w.idx = __reduce_min_sync(full, c);
-    return w;
-}
 
 __device__ __forceinline__ int atom_inc_shared(int *p) {
     int old;
@@ -1046,11 +1021,19 @@ __device__ __forceinline__ int atom_inc_shared(int *p) {
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ uint4 lds128_volatile(const void *p) {   // one 16-byte access: a half is seen whole or not at all
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"((unsigned)__cvta_generic_to_shared(p))
+                 : "memory");
+    return v;
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int RB, bool PROFILE>
 __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs a) {
-    constexpr int NT = RES_NT, NW = NT / 32, PER = RB / 32;
+    constexpr int NT = RES_NT, NW = NT / 32, PER = RB / 32, NSUB = RB / 32;   // NSUB <= NW: one sub-block of the own block per warp
     constexpr int SHIFT = RB == 256 ? 8 : 7;
     static_assert(RB == 128 || RB == 256, "block size");
     unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1106,7 +1089,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
         blk_rec[2 * lb + 1] = hi;
     }
     if (tid == 0) {
-        sh.nd[0] = sh.nd[1] = make_int2(0, 0);
+        sh.nd[0] = sh.nd[1] = make_int4(0, 0, 0, 0);
         sh.err = 0;
         sh.err_frame = -1;
         sh.sat = 0;
@@ -1129,7 +1112,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
 
     // ---- state replicated in the registers of every thread ----
     double cost = a.cost_start;
-    int m = 0, cur = -1, cur_blk = -1, stop = 0, par = 0;
+    int m = 0, cur = -1, cur_blk = -1, prev_blk = -1, stop = 0, par = 0;
     long long l_off = 0;
     int l_len = 0, e0 = 0, e1 = 0;
     int to_flag = -1;                // thread 0: frame whose selected flag is checked / set in the next apply
@@ -1142,9 +1125,13 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             fps_s[j] = v;
             const int lb = j >> SHIFT;
             // Only the entry that IS a block's maximum can change it by decreasing.  The block of the row's own
-            // frame is always re-reduced (warp 0), so it is not listed; another block can be listed twice per step
-            // (group phase, list phase) and is then re-reduced twice with the same result.
-            if (lb != cur_blk && marking && blk_idx[lb] == j) dirty_list[atom_inc_shared(&sh.nd[par].x)] = lb;
+            // frame is always re-reduced (by all warps), so it is not listed; the block of the PREVIOUS row's frame gets
+            // its maximum written while this row is applied, so it is re-reduced in full when anything in it is lowered;
+            // another block can be listed twice per step (group phase, list phase): re-reduced twice, same result.
+            if (lb != cur_blk && marking) {
+                if (lb == prev_blk) sh.nd[par].z = 1;
+                else if (blk_idx[lb] == j) dirty_list[atom_inc_shared(&sh.nd[par].x)] = lb;
+            }
         }
     };
     auto take_rec = [&](const uint4 &lo, const uint4 &hi) -> double {   // FrameRec words -> row state; returns the box cost
@@ -1279,8 +1266,10 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             FPROF(3)
             __syncthreads();
             RPROF_MARK(4)
-            // re-reduce the row's own block (warp 0) and the blocks whose maximum was lowered (the other warps)
-            const int2 nde = sh.nd[par];
+            // Re-reduce (a) the row's own block, cooperatively: warp w takes its w-th 32 frames (one per lane, three REDUX) and
+            // starts the asynchronous copy of that sub-block's best record -- half of all steps pick their next frame from
+            // this very block; (b) rarely (4 % of the steps) other blocks whose maximum was lowered, one warp each, in full.
+            const int4 nde = sh.nd[par];
             const int nd = nde.x;
             if (nde.y) {   // :182 assert -- the frame applied in this step had been selected before
                 stop = 2;
@@ -1290,35 +1279,63 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
                 prof_acc[13] += nd > 0 ? 1 : 0;
                 prof_acc[14] += nd;
             }
-            if (wid == 0) {
-                if (cur_blk >= 0) refresh_block(cur_blk, (int)steps);
-            } else {
+            const int ref_blk = cur_blk;   // -1: nothing was applied in this iteration (seeding)
+            if (ref_blk >= 0 && wid < NSUB) {
+                const int j = (ref_blk << SHIFT) + 32 * wid + lane;
+                const unsigned long long v = fps_s[j];
+                unsigned hi[1] = {(unsigned)(v >> 32)}, lo[1] = {(unsigned)v};
+                int idx[1] = {j < n ? j : 0x7fffffff};
+                const Win x = warp_argmax<1>(hi, lo, idx);
+                if (lane == 0) {
+                    sh.sub_val[wid] = ((unsigned long long)x.hi << 32) | x.lo;
+                    sh.sub_idx[wid] = x.idx;
+                    if (x.idx != 0x7fffffff) {
+                        cp_async_wait_all();   // the slot's previous copy (a step ago) has landed: no reordering of two copies
+                        cp_async16(&sh.sub_rec[wid][0], recs + x.idx);
+                        cp_async16(&sh.sub_rec[wid][1], reinterpret_cast<const char *>(recs + x.idx) + 16);
+                    }
+                }
+            }
+            if (wid > 0) {
+                if (wid == 1 && nde.z && prev_blk >= 0 && prev_blk != ref_blk) refresh_block(prev_blk, (int)steps);
                 for (int q = wid - 1; q < nd; q += NW - 1) refresh_block(dirty_list[q], (int)steps);
             }
             FPROF(7)
             __syncthreads();
             RPROF_MARK(8)
-            if (tid == 0) sh.nd[par] = make_int2(0, 0);   // the next apply counts in the other word (zeroed a step ago)
+            if (tid == 0) sh.nd[par] = make_int4(0, 0, 0, 0);   // the next apply counts in the other word (zeroed a step ago)
             par ^= 1;
-            // arg-max over the block maxima, by every warp (no broadcast, no barrier)
+            // arg-max over the block maxima (the own block's entry replaced by its fresh sub-block maxima), by every warp:
+            // no broadcast, no barrier
+            unsigned shi = 0u, slo = 0u;
+            int sidx = 0x7fffffff;
+            if (ref_blk >= 0 && lane < NSUB) {
+                const unsigned long long v = sh.sub_val[lane];
+                shi = (unsigned)(v >> 32);
+                slo = (unsigned)v;
+                sidx = sh.sub_idx[lane];
+            }
             Win y;
             y.hi = y.lo = 0u;
             y.idx = 0x7fffffff;
             for (int b0 = 0; b0 < nblk; b0 += 4 * 32) {   // uniform trip count: the REDUX inside need every lane
-                unsigned hi[4], lo[4];
-                int idx[4];
+                unsigned hi[5], lo[5];
+                int idx[5];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int b = b0 + lane + 32 * q;
-                    const bool ok = b < nblk;
+                    const bool ok = b < nblk && b != ref_blk;
                     const unsigned long long v = ok ? blk_val[b] : 0ull;
                     hi[q] = (unsigned)(v >> 32);
                     lo[q] = (unsigned)v;
                     idx[q] = ok ? blk_idx[b] : 0x7fffffff;
                 }
+                hi[4] = b0 == 0 ? shi : 0u;
+                lo[4] = b0 == 0 ? slo : 0u;
+                idx[4] = b0 == 0 ? sidx : 0x7fffffff;
                 if (PROFILE) asm volatile("" ::"r"(hi[0] + hi[3] + idx[0] + idx[3]));
                 FPROF(9)
-                const Win w = warp_argmax<4>(hi, lo, idx);
+                const Win w = warp_argmax<5>(hi, lo, idx);
                 const bool take = w.hi > y.hi || (w.hi == y.hi && (w.lo > y.lo || (w.lo == y.lo && w.idx < y.idx)));
                 if (take) y = w;
             }
@@ -1331,14 +1348,44 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
                 stop = 2;
                 break;
             }
-            // The winner's record: cached with its block's maximum (both halves tagged with the frame).  A block re-reduced in
-            // THIS step may still be receiving its record (cp.async), so it is not trusted: one global round trip instead.
+            // The last warp folds the sub-block maxima into the own block's entry while the others go on (it is next read two
+            // barriers from here; lower() does not consult it for this block during the next row, see prev_blk).
+            if (wid == NW - 1 && ref_blk >= 0) {
+                unsigned hi[1] = {shi}, lo[1] = {slo};
+                int idx[1] = {sidx};
+                const Win x = warp_argmax<1>(hi, lo, idx);
+                if (lane == 0) {
+                    blk_val[ref_blk] = ((unsigned long long)x.hi << 32) | x.lo;
+                    blk_idx[ref_blk] = x.idx;
+                    if (x.idx != 0x7fffffff) {
+                        cp_async_wait_all();
+                        cp_async16(blk_rec + 2 * ref_blk, recs + x.idx);
+                        cp_async16(blk_rec + 2 * ref_blk + 1, reinterpret_cast<const char *>(recs + x.idx) + 16);
+                    }
+                }
+            }
+            // The winner's record.  From its own block's sub-block copies when the next frame comes from the block just
+            // re-reduced: that copy was started before the barrier and is polled until both halves carry the frame's tag.
+            // Else from the cache slot of its block (landed a step or more ago); a block re-reduced in full in THIS step
+            // may still be receiving its record and is not trusted: one global round trip instead.
+            prev_blk = ref_blk;
             cur = nxt;
             cur_blk = nxt >> SHIFT;
-            uint4 rlo = blk_rec[2 * cur_blk], rhi = blk_rec[2 * cur_blk + 1];
-            if (blk_step[cur_blk] == this_step || rlo.w != (unsigned)nxt || rhi.w != (unsigned)nxt) {
-                ldg_rec_async(recs + nxt, rlo, rhi);
-                if (PROFILE && tid == 0) prof_acc[12] += 1;
+            uint4 rlo, rhi;
+            if (cur_blk == ref_blk) {
+                const int w = (nxt >> 5) & (NSUB - 1);
+                do {
+                    rlo = lds128_volatile(&sh.sub_rec[w][0]);
+                    rhi = lds128_volatile(&sh.sub_rec[w][1]);
+                } while (rlo.w != (unsigned)nxt || rhi.w != (unsigned)nxt);
+                if (PROFILE && tid == 0) prof_acc[15] += 1;
+            } else {
+                rlo = blk_rec[2 * cur_blk];
+                rhi = blk_rec[2 * cur_blk + 1];
+                if (blk_step[cur_blk] == this_step || rlo.w != (unsigned)nxt || rhi.w != (unsigned)nxt) {
+                    ldg_rec_async(recs + nxt, rlo, rhi);
+                    if (PROFILE && tid == 0) prof_acc[12] += 1;
+                }
             }
             const double box_cost = take_rec(rlo, rhi);
             if (seeding) {   // :165,172-174 -- always taken, no budget check
@@ -1505,7 +1552,7 @@ static bool plan_fast(const adsel_handle *h, const GreedyArgs &a, bool sharded, 
     if (c && *c && atoi(c) != 1) return false;   // an explicit cluster size (or 0: global-memory kernel) was asked for
     if (sharded || a.spatial == ADSEL_SPATIAL_EUCLID || (a.temporal && !a.groups_contiguous)) return false;
     if (a.list_capacity >= (1ll << 40)) return false;
-    const size_t budget = 232448 - 128;   // 227 KB opt-in maximum per CTA minus the static shared variables
+    const size_t budget = 232448 - 512;   // 227 KB opt-in maximum per CTA minus the static shared variables (FastShared: 400 B)
     for (int rb = 128; rb <= 256; rb *= 2) {
         const long long cols = ((long long)a.n + rb - 1) / rb * rb, nblk = cols / rb;
         const size_t fixed = (size_t)cols * 8 + (size_t)nblk * (8 + 32 + 4 + 8 + 4);
@@ -1575,7 +1622,7 @@ int greedy_preload() {
     return ADSEL_OK;
 }
 
-static int validate_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
+int validate_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
                            int32_t first_index, int32_t out_cap) {
     ADSEL_REQUIRE(h->n > 0, "adsel_select: call adsel_set_pool first");
     ADSEL_REQUIRE(p && out_cap > 0, "adsel_select: null argument");
@@ -1616,6 +1663,26 @@ static double far_temporal(const adsel_select_params *p) {
     return p->temporal ? host_normalize_far(p->normalize, TEMPORAL_MARGIN, p->max_temporal) : 0.0;
 }
 
+// The value every untouched entry of a row takes: aggregate(normalize_s(inf), normalize_t(1e6)) -- the largest value a
+// row entry can have (normalize and aggregate are monotone, lambda_t >= 0).
+double far_value(const adsel_select_params *p, double *s_far_out, double *t_far_out) {
+    const double inf = host_inf();
+    const double s_far = p->spatial == ADSEL_SPATIAL_GEODESIC ? host_normalize_far(p->normalize, inf, p->max_spatial)
+                         : p->spatial == ADSEL_SPATIAL_EUCLID ? TEMPORAL_MARGIN : 0.0;
+    const double t_far = far_temporal(p);
+    double far;
+    if (p->spatial != ADSEL_SPATIAL_NONE && p->temporal) {
+        if (p->aggregate == ADSEL_AGG_SUM) far = s_far + p->lambda_t * t_far;   // unfused on the host (no -ffast-math)
+        else if (p->aggregate == ADSEL_AGG_MIN) far = s_far < t_far ? s_far : t_far;
+        else far = s_far > t_far ? s_far : t_far;
+    } else {
+        far = p->spatial != ADSEL_SPATIAL_NONE ? s_far : t_far;
+    }
+    if (s_far_out) *s_far_out = s_far;
+    if (t_far_out) *t_far_out = t_far;
+    return far;
+}
+
 // Enqueues temporal LUT -> neighbour lists (skipped when the resident ones match) on the handle's stream.
 static int enqueue_lists(adsel_handle *h, const adsel_select_params *p, bool sharded) {
     const int n = h->n;
@@ -1649,19 +1716,7 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
     a.groups_contiguous = h->groups_contiguous ? 1 : 0;
     a.pull = getenv("ADSEL_GREEDY_PULL") ? atoi(getenv("ADSEL_GREEDY_PULL")) : 0;
     a.lambda_t = p->lambda_t;
-    const double inf = host_inf();
-    // the value every untouched entry of a row takes
-    a.s_far = p->spatial == ADSEL_SPATIAL_GEODESIC ? host_normalize_far(p->normalize, inf, p->max_spatial)
-              : p->spatial == ADSEL_SPATIAL_EUCLID ? TEMPORAL_MARGIN : 0.0;
-    a.t_far = far_temporal(p);
-    double far;
-    if (a.spatial != ADSEL_SPATIAL_NONE && a.temporal) {
-        if (a.aggregate == ADSEL_AGG_SUM) far = a.s_far + a.lambda_t * a.t_far;   // unfused on the host (no -ffast-math)
-        else if (a.aggregate == ADSEL_AGG_MIN) far = a.s_far < a.t_far ? a.s_far : a.t_far;
-        else far = a.s_far > a.t_far ? a.s_far : a.t_far;
-    } else {
-        far = a.spatial != ADSEL_SPATIAL_NONE ? a.s_far : a.t_far;
-    }
+    const double far = far_value(p, &a.s_far, &a.t_far);   // the value every untouched entry of a row takes
     unsigned long long far_bits;
     memcpy(&far_bits, &far, 8);
 
@@ -1737,7 +1792,7 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
     return ADSEL_OK;
 }
 
-static int finish_select(adsel_handle *h, const double *result, int32_t *out_idx, int32_t *out_m, double *out_cost,
+int finish_select(adsel_handle *h, const double *result, int32_t *out_idx, int32_t *out_m, double *out_cost,
                          const char *who) {
     const int m = (int)result[2];
     const int status = (int)result[1];
@@ -1773,6 +1828,8 @@ int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *
                   int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {
     ADSEL_TRY(validate_select(h, p, sampled, n_sampled, first_index, out_cap));
     ADSEL_REQUIRE(out_idx && out_m, "adsel_select: null argument");
+    if (lazy_wanted(h, p))   // rows without a saturation radius on a large pool: one search per selected frame (lazy.cu)
+        return lazy_select(h, p, sampled, n_sampled, first_index, out_idx, out_cap, out_m, out_cost);
     ADSEL_TRY(greedy_prepare(h, p, n_sampled, out_cap, false));
     for (int attempt = 0; attempt < 2; ++attempt) {
         ADSEL_TRY(begin_stage(h));
@@ -1793,8 +1850,8 @@ int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *
                         prof[0] / steps, prof[1] / steps, prof[2] / steps, prof[3] / steps, prof[4] / steps, prof[5] / steps, prof[6] / steps,
                         prof[7] / steps, prof[8] / steps, prof[9] / steps, prof[10] / steps, prof[11] / steps);
             if (h->greedy_cluster == 1)
-                fprintf(stderr, "[fast profile] record-cache misses %.3f per step; steps with other blocks to re-reduce %.3f, blocks per step %.3f\n",
-                        prof[12] / steps, prof[13] / steps, prof[14] / steps);
+                fprintf(stderr, "[fast profile] record-cache misses %.3f per step, next frame from the own block %.3f; steps with other blocks to re-reduce %.3f, blocks per step %.3f\n",
+                        prof[12] / steps, prof[15] / steps, prof[13] / steps, prof[14] / steps);
             fprintf(stderr, "[greedy profile] cycles/step: apply %.0f | wait B1 %.0f | refresh %.0f | wait B2 %.0f | reduce(+exchange) %.0f | "
                             "fetch+bookkeeping %.0f | wait B3 %.0f | loop %.0f\n",
                     prof[0] / steps, prof[1] / steps, prof[2] / steps, prof[3] / steps, prof[4] / steps, prof[5] / steps,

@@ -81,7 +81,7 @@ def run_case(classes, sel_name, paths, kwargs, rounds, workdir, keep_store=None)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pool", default="P2K")
-    ap.add_argument("--only", default="all", help="all | st (SpatialTemporal exp/sum only) | temporal (TemporalSelector only) | random | spatial (SpatialSelector at budget 1200)")
+    ap.add_argument("--only", default="all", help="all | st (SpatialTemporal exp/sum only) | st_linear | temporal (TemporalSelector only) | random | spatial (SpatialSelector at budget 1200)")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
     ap.add_argument("--budget", type=int, default=600, help="base budget B; chained cases use B/2,B/2,B")
     args = ap.parse_args()
@@ -104,6 +104,10 @@ def main():
                       ("temporal_rounds", "TemporalSelector", {}, [600, 600])]
         elif args.only == "spatial":    # BASELINE config 2's engine at full size: SpatialSelector, budget 1200 (~6 min at P28K)
             cases += [("spatial_1200", "SpatialSelector", {}, [1200])]
+        elif args.only == "st_linear":  # far = inf rows at full size: the lazy-row path (one SSSP per selected frame)
+            cases += [("st_linear_sum_1200", "SpatialTemporalSelector", {"normalize": "linear"}, [1200]),
+                      ("st_linear_min_600", "SpatialTemporalSelector", {"normalize": "linear", "aggregate": "min"}, [600]),
+                      ("st_linear_sum_rounds", "SpatialTemporalSelector", {"normalize": "linear"}, [300, 300])]
         elif args.only == "random":     # the random baseline every experiment of the paper is compared with
             cases += [("random", "RandomSelector", {}, [B]),
                       ("random_rounds", "RandomSelector", {}, [H, H, B]),
