@@ -259,7 +259,7 @@ def run_reference_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(world, n),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": kind, "sample": sample,
-                         "full_workload": full},
+                         "sample_frames": m, "sample_budget": sample_budget, "full_workload": full},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if isinstance(full, dict) and full.get("cold_s"):

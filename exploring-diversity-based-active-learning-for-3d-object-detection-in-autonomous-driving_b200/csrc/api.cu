@@ -28,7 +28,7 @@ int knn_prepare(adsel_handle *h, int32_t k, bool own_tables);
 int greedy_prepare(adsel_handle *h, const adsel_select_params *p, int32_t n_sampled, int32_t out_cap, bool sharded);
 void comm_destroy(adsel_handle *h);
 int greedy_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
-                                int32_t first_index, int32_t out_cap);
+                                int32_t first_index, int32_t out_cap, bool replicate);
 int greedy_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
 
 static int refresh_nnz(adsel_handle *h) {
@@ -270,7 +270,14 @@ int adsel_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, co
                                int32_t first_index, int32_t out_cap) {
     ADSEL_REQUIRE(h, "adsel_select_sharded_begin: null handle");
     ADSEL_CUDA(cudaSetDevice(h->device));
-    return greedy_select_sharded_begin(h, p, sampled, n_sampled, first_index, out_cap);
+    return greedy_select_sharded_begin(h, p, sampled, n_sampled, first_index, out_cap, false);
+}
+
+int adsel_select_replicated_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
+                                  int32_t first_index, int32_t out_cap) {
+    ADSEL_REQUIRE(h, "adsel_select_replicated_begin: null handle");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return greedy_select_sharded_begin(h, p, sampled, n_sampled, first_index, out_cap, true);
 }
 
 int adsel_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost) {

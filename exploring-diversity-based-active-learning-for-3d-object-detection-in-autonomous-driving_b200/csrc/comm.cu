@@ -267,6 +267,9 @@ int adsel_comm_check(adsel_handle *h) {
                                cudaMemcpyDeviceToHost, h->stream));
     ADSEL_CUDA(cudaStreamSynchronize(h->stream));
     if (flag != 0) {
+        // reported once: the word is cleared so that a later, healthy call is not blamed for this one
+        ADSEL_CUDA(cudaMemsetAsync(reinterpret_cast<unsigned long long *>(h->arena) + COMM_ERROR_WORD, 0, sizeof(flag), h->stream));
+        ADSEL_CUDA(cudaStreamSynchronize(h->stream));
         set_error("device barrier " + std::to_string(flag) + " timed out waiting for a peer rank");
         return ADSEL_ERR_COMM;
     }

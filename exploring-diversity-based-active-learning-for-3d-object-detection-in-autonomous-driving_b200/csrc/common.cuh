@@ -186,6 +186,7 @@ struct adsel_handle {
     double *knn_dist_p = nullptr;
     // pending sharded selection (begin/end split so several ranks can be driven from one host thread)
     bool pending = false;
+    bool pending_replicated = false;             // the pending selection runs the whole greedy loop on this rank
     int32_t pending_cap = 0;
     cudaEvent_t pending_ev[2] = {nullptr, nullptr};
     cudaEvent_t knn_ev[2] = {nullptr, nullptr};

@@ -75,6 +75,7 @@ struct ListArgs {
     const int32_t *group_id;
     const double *tlut;
     int world, per;                 // owner of column v = min(v / per, world - 1)
+    int replicate;                  // 1: every rank receives every entry (sharded build, greedy loop replicated on each rank)
     ListStore dest[8];
 };
 
@@ -101,14 +102,15 @@ geodesic_lists_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__rest
         for (int t = threadIdx.x; t < nt; t += SSSP_THREADS) {
             const int v = sc.touched[t];
             const double d = __longlong_as_double((long long)__ldcg(&sc.dist[v]));
-            if (d < radius) atomicAdd(&n_keep[min(v / la.per, la.world - 1)], 1);
+            if (d < radius) atomicAdd(&n_keep[la.replicate ? 0 : min(v / la.per, la.world - 1)], 1);
         }
         __syncthreads();
         if (threadIdx.x < la.world) {
             const int o = threadIdx.x;
-            const unsigned long long b = n_keep[o] ? atomicAdd_system(la.dest[o].cursor, (unsigned long long)n_keep[o]) : 0ull;
+            const int cnt = n_keep[la.replicate ? 0 : o];
+            const unsigned long long b = cnt ? atomicAdd_system(la.dest[o].cursor, (unsigned long long)cnt) : 0ull;
             base_off[o] = b;
-            fits[o] = (long long)(b + n_keep[o]) <= la.dest[o].capacity;
+            fits[o] = (long long)(b + cnt) <= la.dest[o].capacity;
         }
         __syncthreads();
         const int gsrc = la.temporal ? la.group_id[src] : 0;
@@ -116,16 +118,24 @@ geodesic_lists_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__rest
             const int v = sc.touched[t];
             const double d = __longlong_as_double((long long)__ldcg(&sc.dist[v]));
             if (d < radius) {
-                const int o = min(v / la.per, la.world - 1);
-                if (fits[o]) {
+                const int o = la.replicate ? 0 : min(v / la.per, la.world - 1);
+                if (la.replicate || fits[o]) {
                     const int pos = atomicAdd(&n_written[o], 1);
                     double val = normalize_value(d, la.norm_mode, la.divisor);
                     if (la.temporal) {
                         const double tv = la.group_id[v] == gsrc ? la.tlut[abs(v - src)] : la.t_far;
                         val = aggregate_value(val, tv, la.aggregate, la.lambda_t);
                     }
-                    la.dest[o].idx[base_off[o] + pos] = v;
-                    la.dest[o].val[base_off[o] + pos] = val;
+                    if (la.replicate) {   // the same position in every rank's pool that has room (peer stores over NVLink)
+                        for (int r = 0; r < la.world; ++r)
+                            if (fits[r]) {
+                                la.dest[r].idx[base_off[r] + pos] = v;
+                                la.dest[r].val[base_off[r] + pos] = val;
+                            }
+                    } else {
+                        la.dest[o].idx[base_off[o] + pos] = v;
+                        la.dest[o].val[base_off[o] + pos] = val;
+                    }
                 }
             }
             sc.dist[v] = INF_BITS;
@@ -133,7 +143,7 @@ geodesic_lists_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__rest
         if (threadIdx.x < la.world) {
             const int o = threadIdx.x;
             la.dest[o].off[src] = (int64_t)base_off[o];
-            la.dest[o].len[src] = fits[o] ? n_keep[o] : 0;
+            la.dest[o].len[src] = fits[o] ? n_keep[la.replicate ? 0 : o] : 0;
         }
         __syncthreads();
     }
@@ -252,8 +262,9 @@ int grow_lists(adsel_handle *h, long long needed) {
 // Enqueues the neighbour-list build for these selection parameters unless the resident lists were
 // built for the same ones; radius is 38 for exp, inf otherwise.  h->tlut must already be enqueued.
 // sharded: this rank searches from the sources of its slice and appends every entry to the pool of the rank
-// that owns the entry's column; device barriers separate cursor reset / build / use across ranks.
-int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, bool sharded) {
+// that owns the entry's column -- or, with `replicate`, to EVERY rank's pool (each rank then runs the whole greedy
+// loop on complete lists: no exchange per step); device barriers separate cursor reset / build / use across ranks.
+int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, bool sharded, bool replicate) {
     ADSEL_REQUIRE(h->graph_ready, "adsel_select: call adsel_build_knn_graph first");
     const int n = h->n;
     const int lo = sharded ? h->shard_lo : 0, hi = sharded ? h->shard_hi : n;
@@ -263,6 +274,7 @@ int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, boo
     key.aggregate = key.temporal ? p->aggregate : 0;
     key.lo = lo;
     key.hi = sharded ? -hi : hi;     // a sharded build never matches a single-GPU one
+    key.pad = replicate ? 1 : 0;
     key.max_spatial = p->normalize == ADSEL_NORM_LINEAR ? p->max_spatial : 0.0;
     key.max_temporal = (key.temporal && p->normalize == ADSEL_NORM_LINEAR) ? p->max_temporal : 0.0;
     key.lambda_t = (key.temporal && p->aggregate == ADSEL_AGG_SUM) ? p->lambda_t : 0.0;
@@ -282,6 +294,7 @@ int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, boo
     la.t_far = t_far;
     la.group_id = h->group_id.p;
     la.tlut = h->tlut.p;
+    la.replicate = (sharded && replicate) ? 1 : 0;
     if (sharded) {
         la.world = h->world;
         long long per = ((long long)n + h->world - 1) / h->world;

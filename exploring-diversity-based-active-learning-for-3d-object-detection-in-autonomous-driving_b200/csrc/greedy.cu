@@ -961,7 +961,7 @@ static double host_normalize_far(int norm_mode, double d, double divisor) {
     return d;
 }
 
-int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, bool sharded);
+int build_lists(adsel_handle *h, const adsel_select_params *p, double t_far, bool sharded, bool replicate);
 bool lazy_wanted(const adsel_handle *h, const adsel_select_params *p);
 int lazy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled, int32_t first_index,
                 int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
@@ -1684,7 +1684,7 @@ double far_value(const adsel_select_params *p, double *s_far_out, double *t_far_
 }
 
 // Enqueues temporal LUT -> neighbour lists (skipped when the resident ones match) on the handle's stream.
-static int enqueue_lists(adsel_handle *h, const adsel_select_params *p, bool sharded) {
+static int enqueue_lists(adsel_handle *h, const adsel_select_params *p, bool sharded, bool replicate = false) {
     const int n = h->n;
     if (p->temporal) {
         temporal_lut_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->tlut.p, n, p->normalize, p->max_temporal);
@@ -1692,7 +1692,7 @@ static int enqueue_lists(adsel_handle *h, const adsel_select_params *p, bool sha
         ADSEL_CUDA(cudaGetLastError());
     }
     if (p->spatial == ADSEL_SPATIAL_GEODESIC)
-        ADSEL_TRY(build_lists(h, p, far_temporal(p), sharded));
+        ADSEL_TRY(build_lists(h, p, far_temporal(p), sharded, replicate));
     return ADSEL_OK;
 }
 
@@ -1869,15 +1869,19 @@ int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *
 }
 
 // ---- pool-sharded selection: enqueue on every rank, then collect ------------------------------------
+// replicate: the lists are built by the rank that owns the SOURCE frames and stored into every rank's arena; each rank
+// then runs the whole greedy loop (resident in its shared memory) on complete lists -- no exchange per step, the same
+// result on every rank (like the reference, where every rank computes the whole selection, base_selector.py:57).
 int greedy_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
-                                int32_t first_index, int32_t out_cap) {
+                                int32_t first_index, int32_t out_cap, bool replicate) {
     ADSEL_TRY(validate_select(h, p, sampled, n_sampled, first_index, out_cap));
     ADSEL_REQUIRE(h->comm_ready, "adsel_select_sharded_begin: call adsel_comm_init / adsel_comm_attach first");
     ADSEL_REQUIRE(!h->pending, "adsel_select_sharded_begin: a sharded selection is already pending");
     ADSEL_TRY(greedy_prepare(h, p, n_sampled, out_cap, true));
     ADSEL_CUDA(cudaEventRecord(h->pending_ev[0], h->stream));
-    ADSEL_TRY(enqueue_lists(h, p, true));
-    ADSEL_TRY(enqueue_greedy(h, p, sampled, n_sampled, first_index, out_cap, true));
+    ADSEL_TRY(enqueue_lists(h, p, true, replicate));
+    ADSEL_TRY(enqueue_greedy(h, p, sampled, n_sampled, first_index, out_cap, !replicate));
+    h->pending_replicated = replicate;
     ADSEL_CUDA(cudaEventRecord(h->pending_ev[1], h->stream));
     h->pending = true;
     h->pending_cap = out_cap;
@@ -1898,7 +1902,9 @@ int greedy_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap
     const int status = (int)result[1];
     // every rank ran the same number of exchanges unless the launch failed; after a failure the tags are
     // moved to a fresh epoch (all ranks observe the same failure through the exchanged abort record)
-    if (status == 0 || status == ADSEL_ERR_RESELECTED) h->comm_seq += (unsigned)result[3];
+    if (h->pending_replicated) {
+        // no mailbox exchange ran: the tags stay where they are
+    } else if (status == 0 || status == ADSEL_ERR_RESELECTED) h->comm_seq += (unsigned)result[3];
     else h->comm_seq = ((h->comm_seq >> 24) + 1u) << 24;
     // an overflowing list region of the arena cannot grow in place: the caller re-creates the arenas with
     // adsel_comm_init(list_cap = the largest adsel_get_counters()[2] over the ranks) and rebuilds

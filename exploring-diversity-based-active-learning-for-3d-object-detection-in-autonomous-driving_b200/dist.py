@@ -24,3 +24,51 @@ def master_only(func):
         return None
 
     return wrapper
+
+
+def _group_device():
+    """Device on which small control tensors live for the default group's backend (NCCL needs CUDA tensors)."""
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def agree_from_rank0(values):
+    """Rank 0's tuple of integers on every rank (``values`` unchanged when not distributed).  The sharded engines do
+    the greedy bookkeeping redundantly on every rank, so anything drawn from a per-process RNG (the first frame of an
+    empty buffer, base_selector.py / spatial_temporal_selector.py:168) must be rank 0's draw everywhere."""
+    rank, world = get_dist_info()
+    if world <= 1:
+        return tuple(values)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=_group_device())
+    dist.broadcast(t, src=0)
+    return tuple(int(v) for v in t.tolist())
+
+
+def all_ranks_max(value: int) -> int:
+    """Largest ``value`` over the ranks: lets every rank take the same branch (retry / raise) after a collective call."""
+    rank, world = get_dist_info()
+    if world <= 1:
+        return int(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(value)], dtype=torch.int64, device=_group_device())
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
+def check_same_on_all_ranks(values, what: str):
+    """Raise on every rank when the ranks do not hold the same integers (cheap guard before a collective kernel)."""
+    rank, world = get_dist_info()
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=_group_device())
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if not torch.equal(lo, hi):
+        raise RuntimeError(f"ranks disagree on {what}: min {lo.tolist()} max {hi.tolist()} (this rank {t.tolist()})")

@@ -84,6 +84,8 @@ _SIGNATURES = {
     "adsel_build_knn_graph_sharded": (ctypes.c_int, [_P, ctypes.c_int32]),
     "adsel_select_sharded_begin": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.c_int32]),
+    "adsel_select_replicated_begin": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, ctypes.c_int32, ctypes.c_int32,
+                                                     ctypes.c_int32]),
     "adsel_select_sharded_end": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                                 ctypes.POINTER(ctypes.c_double)]),
     "adsel_feature_distance_build": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
@@ -305,13 +307,15 @@ class Handle:
 
     def select_sharded_begin(self, *, spatial, temporal, normalize, aggregate="sum", lambda_t=1.0, max_spatial=0.0,
                              max_temporal=0.0, cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=0.0,
-                             forbid_sampled=False, sampled=(), first_index=-1, out_cap=None):
+                             forbid_sampled=False, sampled=(), first_index=-1, out_cap=None, replicate=False):
+        """``replicate``: sharded build, every rank receives every list entry and runs the whole greedy loop itself."""
         p = self._select_params(spatial, temporal, normalize, aggregate, lambda_t, max_spatial, max_temporal, cost_b,
                                 cost_f, cost_start, budget, forbid_sampled)
         sampled = np.ascontiguousarray(sampled, dtype=np.int32)
         self._out_cap = self.n if out_cap is None else int(out_cap)
-        _check(load().adsel_select_sharded_begin(self._h, ctypes.byref(p), _ptr(sampled) if len(sampled) else None,
-                                                 len(sampled), int(first_index), self._out_cap))
+        fn = load().adsel_select_replicated_begin if replicate else load().adsel_select_sharded_begin
+        _check(fn(self._h, ctypes.byref(p), _ptr(sampled) if len(sampled) else None, len(sampled), int(first_index),
+                  self._out_cap))
 
     def select_sharded_end(self):
         """Returns ``(selected, cost)``; raises ``RetrySharded`` when every rank must call begin/end again."""

@@ -79,6 +79,13 @@ class BaseSelector(object):
         if len(sampled) == 0:
             # consumes the caller-seeded python RNG exactly like the reference (:168)
             first_index = random.choice(range(len(self.infos_origin)))
+        if getattr(handle, "world", 1) > 1:
+            # The ranks of a sharded engine do the bookkeeping redundantly: they must start from rank 0's draw and the
+            # same buffer (in the reference an unsynchronised per-rank RNG is harmless: full replicas, rank 0 dumps).
+            from .. import dist as _d
+            (first_index,) = _d.agree_from_rank0((first_index,))
+            _d.check_same_on_all_ranks((len(sampled), sum(sampled) % (1 << 31), int(self.current_budget)),
+                                       "the buffer they resume from")
         selected, cost = handle.select(cost_b=self.cost_b, cost_f=self.cost_f, cost_start=self.get_cost_amount(),
                                        budget=int(self.current_budget), sampled=sampled, first_index=first_index,
                                        **select_kwargs)

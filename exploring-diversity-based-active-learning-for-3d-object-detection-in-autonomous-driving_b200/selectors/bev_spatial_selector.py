@@ -102,6 +102,11 @@ class BevSpatialSelector(BaseSelector):
             handle.dense_build(n, self.batch_frames, load_batch, self.point_range, self.voxel_size)
             sampled = list(self.buffer[self.get_max_key()])
             first_index = random.choice(range(n)) if len(sampled) == 0 else -1   # spatial_selector.py:111
+            if getattr(handle, "world", 1) > 1:     # sharded engine: every rank starts from rank 0's draw and the same buffer
+                from .. import dist as _d
+                (first_index,) = _d.agree_from_rank0((first_index,))
+                _d.check_same_on_all_ranks((len(sampled), sum(sampled) % (1 << 31), int(self.current_budget)),
+                                           "the buffer they resume from")
             selected, cost = handle.dense_select(pool.box_counts(self.infos_origin), cost_b=self.cost_b,
                                                  cost_f=self.cost_f, cost_start=self.get_cost_amount(),
                                                  budget=int(self.current_budget), forbid_sampled=True,

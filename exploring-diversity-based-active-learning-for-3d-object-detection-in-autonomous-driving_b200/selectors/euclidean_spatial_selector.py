@@ -1,6 +1,7 @@
 """``EuSpatialSelector``: 2-D Euclidean ego distance inside a city, margin 1e6 across cities
 (det3d/selectors/euclidean_spatial_selector.py:16-143)."""
 import logging
+import os
 from typing import Optional
 
 import numpy as np
@@ -24,6 +25,9 @@ class EuSpatialSelector(BaseSelector):
         self.distance_store_file = distance_store_file   # accepted, unused (see SpatialTemporalSelector)
 
     def select_samples(self, **kwargs) -> None:
+        if self.distance_store_file and os.path.exists(self.distance_store_file):
+            self.logger.warning(f"{self.distance_store_file} exists but is ignored: the geodesic rows are rebuilt on the GPU "
+                                "(the reference would load this cached N x N map instead of recomputing it)")
         infos = self.infos_origin
         names, locations, n_boxes = pool.extract_slice(infos)
         city = pool.city_groups(names, load(self.logs_file))   # :57-60,75-76

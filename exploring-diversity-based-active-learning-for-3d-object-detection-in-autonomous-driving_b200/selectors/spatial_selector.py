@@ -1,5 +1,6 @@
 """``SpatialSelector``: geodesic term only, raw distances (det3d/selectors/spatial_selector.py:16-138)."""
 import logging
+import os
 from typing import Optional
 
 from .. import pool, sharded
@@ -23,6 +24,9 @@ class SpatialSelector(BaseSelector):
         self.distance_store_file = distance_store_file   # accepted, unused (see SpatialTemporalSelector)
 
     def select_samples(self, **kwargs) -> None:
+        if self.distance_store_file and os.path.exists(self.distance_store_file):
+            self.logger.warning(f"{self.distance_store_file} exists but is ignored: the geodesic rows are rebuilt on the GPU "
+                                "(the reference would load this cached N x N map instead of recomputing it)")
         infos = self.infos_origin
         names, locations, n_boxes = pool.extract_slice(infos)
         known = {l["logfile"] for l in load(self.logs_file)}

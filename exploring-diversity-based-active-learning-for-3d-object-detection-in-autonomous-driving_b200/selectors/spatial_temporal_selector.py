@@ -5,6 +5,7 @@ Same registry name, constructor keywords, assertions and results as the referenc
 sm_100a library through ``native.Handle``.
 """
 import logging
+import os
 from typing import Optional
 
 from .. import pool, sharded
@@ -38,6 +39,9 @@ class SpatialTemporalSelector(BaseSelector):
         self.logger.info(f"lambda_t: {self.lambda_t}")
 
     def select_samples(self, **kwargs) -> None:
+        if self.distance_store_file and os.path.exists(self.distance_store_file):
+            self.logger.warning(f"{self.distance_store_file} exists but is ignored: the geodesic rows are rebuilt on the GPU "
+                                "(the reference would load this cached N x N map instead of recomputing it)")
         import time
         t0 = time.perf_counter()
         infos = self.infos_origin

@@ -27,6 +27,35 @@ def shard_bounds(n: int, world: int, rank: int):
     return native.shard_bounds_256(n, world, rank)
 
 
+REPLICATE_MAX_FRAMES = 440_000      # 16 CTAs x 27.5 k columns: what a thread-block cluster's shared memory holds
+
+
+def shard_mode(n: int) -> str:
+    """How several ranks split one selection.
+
+    ``replicate`` (default while the pool fits one GPU's resident greedy kernel): the kNN rows and the neighbour lists
+    are BUILT by the rank that owns the source frames and stored into every rank's arena over NVLink; each rank then
+    runs the whole greedy loop in its own shared memory.  A resident step costs about as much as ONE NVLink round trip,
+    so exchanging a (value, index) pair per step -- ``columns``, the round-1 schedule, kept for pools beyond 440 k
+    frames -- can only lose (measured: 9.8 ms on one GPU, 14.5 ms on eight).
+    ``ADSEL_SHARD=columns|replicate`` forces one; ``ADSEL_SHARD=0`` makes every rank an independent replica."""
+    env = os.environ.get("ADSEL_SHARD", "auto")
+    if env in ("columns", "replicate"):
+        return env
+    return "replicate" if n <= REPLICATE_MAX_FRAMES else "columns"
+
+
+def lazy_rows(n: int, kw) -> bool:
+    """Mirrors csrc/lazy.cu:lazy_wanted -- rows without a saturation radius on a large pool are searched per selected
+    frame by every rank on its own (no lists to shard)."""
+    if kw.get("spatial") != "geodesic" or kw.get("normalize") == "exp":
+        return False
+    env = os.environ.get("ADSEL_LAZY", "")
+    if env:
+        return env != "0"
+    return n >= 16384
+
+
 def pick_global_best(records):
     """The exchange's reduction rule on the host: ``records`` = ``[(value_key, index), ...]`` per rank ->
     the record with the largest key, lowest index among equal keys (np.argmax's first maximum)."""
@@ -58,8 +87,9 @@ class _WorldBase:
 class LocalWorld(_WorldBase):
     """``world`` ranks of this process; ``devices[r]`` is rank r's CUDA device (default: all on device 0)."""
 
-    def __init__(self, world: int, devices=None, timeout: float = 20.0):
+    def __init__(self, world: int, devices=None, timeout: float = 20.0, mode: str = "columns"):
         super().__init__()
+        self.mode = mode
         self.world = int(world)
         devices = [0] * self.world if devices is None else list(devices)
         assert len(devices) == self.world
@@ -72,6 +102,8 @@ class LocalWorld(_WorldBase):
         self.handles = []
 
     def _ensure(self, k: int, dim: int = 0):
+        if self.mode == "replicate" and self._list_cap == 0 and k > 0:
+            self._list_cap = self.n * 288            # every rank holds every entry
         shape = (self.n, int(k), int(dim), self._list_cap)
         if self._arena_shape != shape:
             for r, h in enumerate(self.handles):
@@ -157,7 +189,7 @@ class LocalWorld(_WorldBase):
             for h in self.handles:
                 h.shard_prepare(k=max(self.k, 1), n_sampled=len(sampled), out_cap=kw.get("out_cap"), **prep)
             for h in self.handles:
-                h.select_sharded_begin(**kw)
+                h.select_sharded_begin(replicate=self.mode == "replicate", **kw)
             results, retry, error = [], False, None
             for h in self.handles:   # every rank is collected even if one raises (their kernels are all in flight)
                 try:
@@ -214,6 +246,9 @@ class DistWorld(_WorldBase):
             self.handle = None
 
     def _ensure(self, k: int, dim: int = 0):
+        self.mode = shard_mode(self.n)
+        if self.mode == "replicate" and self._list_cap == 0 and k > 0:
+            self._list_cap = self.n * 288            # every rank holds every entry
         shape = (self.n, int(k), int(dim), self._list_cap)
         if self._arena_shape != shape:
             if self._arena_shape is not None:       # nobody may still map an arena that is about to be freed
@@ -246,7 +281,9 @@ class DistWorld(_WorldBase):
 
     def dense_select(self, n_boxes, **kw):
         self.handle.select_dense_sharded_begin(n_boxes, **kw)
-        return self.handle.select_dense_sharded_end()
+        out = self.handle.select_dense_sharded_end()
+        self.handle.comm_check()        # a device barrier of the build that timed out left partial peer data behind
+        return out
 
     def shard_range(self):
         return self.handle.shard_range()
@@ -260,16 +297,29 @@ class DistWorld(_WorldBase):
         return self.handle.geodesic_max_finite()
 
     def select(self, **kw):
+        from . import dist as _d
         self._ensure(self.k)
+        if lazy_rows(self.n, kw):            # one search per selected frame: nothing to shard, every rank a replica
+            return self.handle.select(**kw)
         for _ in range(self.MAX_RETRIES):
-            self.handle.select_sharded_begin(**kw)
+            self.handle.select_sharded_begin(replicate=self.mode == "replicate", **kw)
+            out, code, error = None, 0, None
             try:
-                return self.handle.select_sharded_end()
-            except native.RetrySharded:      # raised on EVERY rank by the same call: the loop stays collective
-                needs = [None] * self.world
-                self._dist.all_gather_object(needs, self.handle.counters()["list_entries"], group=self.group)
-                self._list_cap = int(max(needs) * 1.1) + 1024
-                self.build_knn_graph(self.k)    # new arenas sized for the largest need, graph rebuilt
+                out = self.handle.select_sharded_end()
+                self.handle.comm_check()     # a timed-out device barrier (graph / list build) left partial peer data
+            except native.RetrySharded:
+                code = 1
+            except (AssertionError, native.NativeError) as e:
+                code, error = 2, e
+            # every rank takes the same branch: a rank that failed alone must not leave its peers in a collective
+            worst = _d.all_ranks_max(code)
+            if worst == 2:
+                raise error if error is not None else native.NativeError(native.ERR_PEER_ABORT, "a peer rank failed the selection")
+            if worst == 0:
+                return out
+            need = _d.all_ranks_max(self.handle.counters()["list_entries"])
+            self._list_cap = int(need * 1.1) + 1024
+            self.build_knn_graph(self.k)     # new arenas sized for the largest need, graph rebuilt
         raise native.NativeError(native.ERR_CAPACITY, "sharded selection kept overflowing its neighbour-list pools")
 
     def get_fps(self):

@@ -155,6 +155,14 @@ int adsel_build_knn_graph_sharded(adsel_handle *h, int32_t k);
 int adsel_select_sharded_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled,
                                int32_t n_sampled, int32_t first_index, int32_t out_cap);
 int adsel_select_sharded_end(adsel_handle *h, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
+/* The default multi-GPU schedule since the greedy loop became resident in one SM's shared memory (a step costs less
+ * than one NVLink round trip): only the BUILD is sharded.  Every rank searches from the sources of its slice and stores
+ * each list entry into EVERY rank's arena over NVLink (size the arenas with list_cap >= the total entry count, e.g.
+ * 288 n); then each rank runs the whole greedy loop on the complete lists -- no exchange per step, the same result on
+ * every rank, which is what the reference does per rank (base_selector.py:57) minus the redundant build.  Collect with
+ * adsel_select_sharded_end (ADSEL_ERR_CAPACITY: the same on every rank, re-create the arenas larger and repeat). */
+int adsel_select_replicated_begin(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled,
+                                  int32_t n_sampled, int32_t first_index, int32_t out_cap);
 
 /* ---- BEV density descriptor from LiDAR points (north_star kernel 1; no reference function -- the
  *      binning semantics are those of det3d/ops/point_cloud/bev_ops.py:27-53, see csrc/bev.cu) -------

@@ -85,9 +85,13 @@ class FakeShardHandle:
             return s + kw.get("lambda_t", 1.0) * t
         return np.stack([s, t]).min(0) if agg == "min" else np.stack([s, t]).max(0)
 
-    def select_sharded_begin(self, **kw):
+    def select_sharded_begin(self, replicate=False, **kw):
         assert self.attached
+        self.replicate = replicate          # the schedule (who runs the loop) does not change what is selected
         self.pending = kw
+
+    def comm_check(self):
+        self.calls.append(("comm_check",))
 
     def _argmax_exchange(self, fps, lo):
         if len(fps):

@@ -21,8 +21,12 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "pool_frames_scored_and_selected_per_sec"
     assert line["unit"] == "frames/s" and line["higher_is_better"] is True and line["n_gpus"] == 1
     assert line["config"]["workload"].startswith("P28K/SpatialTemporalSelector") and line["config"]["pool_frames"] == 28130
-    assert line["value"] > 0 and abs(line["value"] - 28130 / (line["ms_per_step"] * 1e-3)) < 1e-6 * line["value"]
-    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] == 1
+    # each step is a bounded sample of the workload: the first `sample_frames` frames of the pool through the same selector
+    m = line["cpu_baseline"]["sample_frames"]
+    assert 1000 <= m <= 28130 and line["cpu_baseline"]["sample_budget"] == max(60, round(4800 * m / 28130))
+    assert line["value"] > 0 and abs(line["value"] - m / (line["ms_per_step"] * 1e-3)) < 1e-6 * line["value"]
+    assert line["steps"] == 1 and line["warmup"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
     assert line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 

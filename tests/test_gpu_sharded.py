@@ -300,3 +300,36 @@ def test_p281k_budget_4800_single_gpu_and_sharded(pools):
         assert got8 == golden["selected_index"]["4800"]
     finally:
         w.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_replicated_schedule_sharded_build_whole_loop_on_every_rank(pools, world):
+    """The default multi-GPU schedule: lists built by the rank owning the SOURCE frames and stored into every rank's
+    arena, then every rank runs the whole (resident) greedy loop: same selection, cost and min-distance vector on every
+    rank as on one GPU, also when a second round resumes from the first and when the arenas start too small."""
+    infos = pools("P2K")["infos"]
+    loc, run_id, max_td, n_boxes = _arrays(infos)
+    single = native.Handle(0)
+    single.set_pool(loc, run_id, n_boxes)
+    single.build_knn_graph(8)
+    kw = dict(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0, budget=300, first_index=17)
+    want, want_cost = single.select(**kw)
+    want_fps = single.get_fps()
+    want2, _ = single.select(**{**kw, "budget": 500, "sampled": want, "first_index": -1, "cost_start": want_cost})
+    entries = single.counters()["list_entries"]
+    single.close()
+    for list_cap in (0, entries // 3):          # default size; too small -> collective retry with larger arenas
+        w = sharded.LocalWorld(world, timeout=10.0, mode="replicate")
+        w._list_cap = list_cap
+        try:
+            w.set_pool(loc, run_id, n_boxes)
+            w.build_knn_graph(8)
+            got, cost = w.select(**kw)
+            assert got == want and cost == want_cost
+            for h in w.handles:                  # every rank holds the whole vector and every list entry
+                assert np.array_equal(h.get_fps().view(np.uint64), want_fps.view(np.uint64))
+                assert h.counters()["list_entries"] == entries
+            got2, _ = w.select(**{**kw, "budget": 500, "sampled": got, "first_index": -1, "cost_start": cost})
+            assert got2 == want2
+        finally:
+            w.close()
