@@ -11,14 +11,18 @@ One "step" = one whole selection: kNN graph -> geodesic neighbour lists -> greed
   value : device-timed (CUDA events on the launching stream), pool arrays already resident in HBM.
   e2e   : the user-facing call ``SpatialTemporalSelector.select_samples()`` on host-resident infos
           (host string/pose extraction, H2D copies, kernels, D2H of the selected indices), wall clock.
-  N > 1 : one process per GPU, the pool SHARDED by column over the N ranks (sharded.DistWorld: kNN rows
-          stored into every rank's table over NVLink, one peer-memory mailbox exchange per greedy step,
-          DESIGN.md §7).  "weak": the pool grows with N (N x 28,130 frames, the same generator with N x
-          the scenes over N x the area -- BASELINE.json config 5 is the 10x pool), budget 4800 fixed;
-          value = pool frames / max-over-ranks time.  extras.strong_p28k reports the fixed 28,130-frame pool on the same N ranks.
+  N > 1 : one process per GPU (sharded.DistWorld).  The BUILD is sharded: every rank computes the kNN rows and the
+          geodesic neighbour lists of its slice of the frames and stores them into every rank's arena over NVLink
+          (peer-memory stores from inside the kernels, device-side barriers); the greedy loop -- resident in one SM's
+          shared memory, a step costs about one NVLink round trip -- then runs replicated on every rank (DESIGN.md §7;
+          ADSEL_SHARD=columns restores round 1's per-step exchange).  "weak": the pool grows with N (N x 28,130 frames,
+          the same generator with N x the scenes over N x the area -- BASELINE.json config 5 is the 10x pool), budget
+          4800 fixed; value = pool frames / max-over-ranks time.  extras.strong_p28k reports the fixed 28,130-frame pool
+          on the same N ranks and the process exits non-zero if that selection differs from the reference golden.
 
-``--impl reference`` times the CPU implementation of the same workload on the host cores: the
-unmodified reference when /root/reference is present (this container), else the oracle port.
+``--impl reference`` times the UNMODIFIED reference selector on the host cores (/root/reference here, its byte-for-byte
+copy oracle/_ref on the GPU box; the oracle port only if neither exists): each step a bounded sample of the workload,
+plus ONE full-size cold and warm selection (cpu_baseline.full_workload).
 """
 import argparse
 import json
@@ -273,21 +277,27 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # BEV-descriptor configuration (BASELINE.json configs[1]/[2]: north_star kernels 1 and 3)
 # ------------------------------------------------------------------------------------------------
-def greedy_latency_floor(greedy_ms, steps, clock_info):
-    """What bounds the greedy loop is the LENGTH of its dependency chain, not bandwidth: per step four
-    dependent L2 hits (frame record, list entries, min-distance entries, block re-read; 262 cycles each on the far die)
-    and three CTA barriers (~34 cycles) -- /opt/skills/guides/B300_MICROARCH.md, L2 and barrier rows.  Reported next to
-    the achieved time per step so that the headroom of the loop is a number; it is a model, not a measurement."""
+def greedy_latency_floor(greedy_ms, steps, clock_info, kernel="greedy_fast_kernel"):
+    """What bounds the greedy loop is the LENGTH of its dependency chain, not bandwidth.  The model is the
+    chain of a step with the latencies MEASURED on this pool's B200s by tools/microbench/latency.cu (one SM, 8 warps):
+    dependent L2 hit 295 cycles, LDS 31, REDUX 26, CTA barrier + consumer 71.  Resident kernels: one L2 round trip (the
+    selected frame's list entries), three barriers, two arg-max chains (LDS + 3 REDUX each), one record read.  The
+    global-memory kernel (pools beyond a cluster's shared memory): four L2 round trips and three barriers.  Reported next
+    to the achieved time per step so that the headroom is a number; a model, not a measurement."""
     try:
         sm_mhz = float((clock_info or {}).get("sm_mhz") or 1965.0)
     except (TypeError, ValueError, AttributeError):
         sm_mhz = 1965.0
-    cycles = 4 * 262 + 3 * 34
+    if kernel == "greedy_select_kernel":
+        cycles, model = 4 * 295 + 3 * 71, "4 dependent L2 hits x 295 cycles + 3 CTA barriers x 71 cycles per step"
+    else:
+        cycles = 295 + 3 * 71 + 2 * (31 + 3 * 26) + 31
+        model = "1 L2 hit x 295 + 3 CTA barriers x 71 + 2 arg-max chains x (LDS 31 + 3 REDUX x 26) + record LDS 31 cycles per step"
     floor_us = cycles / sm_mhz
     achieved_us = greedy_ms * 1e3 / max(int(steps), 1)
-    return {"model": "4 dependent L2 hits x 262 cycles + 3 CTA barriers x 34 cycles per step", "cycles_per_step": cycles,
-            "floor_us_per_step": floor_us, "achieved_us_per_step": achieved_us,
-            "frac": floor_us / achieved_us if achieved_us > 0 else None}
+    return {"model": model, "cycles_per_step": cycles, "floor_us_per_step": floor_us, "achieved_us_per_step": achieved_us,
+            "frac": floor_us / achieved_us if achieved_us > 0 else None,
+            "latencies_source": "tools/microbench/latency.cu on B200 (profiles/r02_latency_microbench.txt)"}
 
 
 def profiled_traffic():
@@ -435,6 +445,7 @@ def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_r
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_b200_arm(args):
+    failed = False
     import numpy as np
     import torch
     import adsel_b200  # noqa: F401
@@ -568,13 +579,33 @@ def run_b200_arm(args):
             golden = json.load(open(gpath))["cases"]["st_exp_sum_4800"]["selected_index"][str(BUDGET)]
             golden_ok = bool(golden == sel)
 
-        # ---- CPU baseline: oracle port on the same workload, rank 0, N=1 only --------------------
+        # ---- CPU baseline, rank 0, N=1 only: the UNMODIFIED reference (oracle/_ref on the GPU box) on a bounded sample ----
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            sec, cpu_sel = cpu_port_once(infos, logs, BUDGET)
-            cpu = {"value": n / sec, "unit": "frames/s", "cores": 1, "kind": "port",
-                   "sample": f"full workload once ({sec:.1f} s): streaming oracle port of the selector, single-threaded "
-                             f"numpy/scipy on a {os.cpu_count()}-core host; selected list identical: {cpu_sel == sel}"}
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            from reference_loader import reference_available
+            use_ref = reference_available()
+            sample_paths, m_s, b_s = reference_sample(paths, infos, tmp, REF_SAMPLE_FRAMES)
+            if use_ref:
+                sec, cpu_sel = cpu_reference_once(sample_paths, b_s, tmp)
+            else:
+                sec, cpu_sel = cpu_port_once(infos[:m_s], logs, b_s)
+            hs = native.Handle(local_rank)                       # the same sample through this library: identical list?
+            try:
+                sub = infos[:m_s]
+                run_s, _ = pool.consecutive_runs(pool.logfile_names(sub))
+                hs.set_pool(pool.ego_locations(sub), run_s, pool.box_counts(sub))
+                hs.build_knn_graph(8)
+                gpu_sel, _ = hs.select(spatial="geodesic", temporal=True, normalize="exp", aggregate="sum", lambda_t=1.0,
+                                       cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=b_s, first_index=first_index(m_s))
+            finally:
+                hs.close()
+            cpu = {"value": m_s / sec, "unit": "frames/s", "cores": 1, "kind": "reference" if use_ref else "port",
+                   "sample_frames": m_s, "sample_budget": b_s,
+                   "sample": f"the {'unmodified reference' if use_ref else 'oracle port of the'} SpatialTemporalSelector on the first {m_s} of "
+                             f"the {n} frames, budget {b_s} (= {BUDGET} x {m_s}/{n}), cold, once: {sec:.2f} s, single-threaded numpy/scipy "
+                             f"on a {os.cpu_count()}-core host; frames/s on the sub-pool OVERSTATES the reference on the full pool "
+                             f"(all-pairs Dijkstra, superlinear); this library selects the identical list on the sample: {gpu_sel == cpu_sel}"}
         # ---- strong scaling on the fixed 28,130-frame pool, same N ranks (N > 1) ------------------
         strong = None
         if world > 1:
@@ -611,7 +642,33 @@ def run_b200_arm(args):
                     boxes_big = np.random.default_rng(1).integers(0, 60, size=nbig).astype(np.int32)
                     bev_sh.update(bev_extras_sharded(h, nbig, boxes_big, first_index(nbig), peaks, max_over_ranks, barrier, reps=2,
                                                      budget=BUDGET, key="bev_sharded_scaled_pool"))
+        greedy_info = h.greedy_info()
         h.close()
+
+        # ---- one-shot CLI, cold: a fresh `python tools/active_select.py` process (the reference's unit of work,
+        # tools/active_select.py:74-163): interpreter + imports + unpickling the pool + CUDA context + module load + selection
+        cold_cli = None
+        if rank == 0 and world == 1 and not args.no_cold_cli:
+            cli_buf = os.path.join(tmp, "cli_buffer.json")
+            cli_cfg = os.path.join(tmp, "cli_cfg.py")
+            with open(cli_cfg, "w") as f:
+                f.write(f"selector = dict(type='SpatialTemporalSelector', budget=1, buffer_file={cli_buf!r}, "
+                        f"infos_origin={paths['infos']!r}, logs_file={paths['logs']!r}, "
+                        f"distance_store_file={os.path.join(tmp, 'unused.npy')!r})\n")
+            cli = [sys.executable, os.path.join(ROOT, "tools", "active_select.py"), "--config", cli_cfg, "--budget", str(BUDGET)]
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+            subprocess.run(cli, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)   # writes the empty buffer
+            times = []
+            for _ in range(2):
+                json.dump({"0": []}, open(cli_buf, "w"))
+                t0 = time.perf_counter()
+                rc = subprocess.run(cli, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300).returncode
+                times.append(time.perf_counter() - t0)
+            cli_sel = json.load(open(cli_buf)).get(str(BUDGET))
+            cold_cli = {"seconds_first": times[0], "seconds_second": times[1], "rc": rc, "identical_to_this_run": cli_sel == sel,
+                        "what": "wall clock of `python tools/active_select.py --config cfg --budget 4800` as a fresh process: interpreter, "
+                                "imports, unpickling the 28,130-frame infos list, CUDA context, loading the library's kernels, "
+                                "selection, buffer JSON + infos subset written"}
 
         # ---- BEV-descriptor configuration: HBM-bound histogram and tensor-core distance tiles ----
         extras = None
@@ -635,50 +692,62 @@ def run_b200_arm(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     dominant = max(stages, key=stages.get)
     steps_per_sel = counters["steps"]
+    gkernel = greedy_info["kernel"]
     if dominant == "greedy":
         # one greedy step = 24*N algorithmic bytes (read row 8N, read+write fps 16N)
         alg_bytes = 24.0 * n * steps_per_sel
-        kernel = "greedy_select_kernel"
+        kernel = gkernel
     elif dominant == "geodesic_lists":
         # per source: CSR of the touched neighbourhood is irregular; lower bound = list entries written (12 B each)
         alg_bytes = 12.0 * counters["list_entries"] + 12.0 * counters["nnz"] + 4.0 * n
         kernel = "geodesic_lists_kernel"
     else:
         alg_bytes = 16.0 * n + 12.0 * 9 * n
-        kernel = "knn_bruteforce_kernel"
+        kernel = "knn_grid_kernel"
     achieved = alg_bytes / (stages[dominant] * 1e-3) / 1e9
-    traffic = None        # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same workload, N = 1)
+    traffic, traffic_src = None, None   # DRAM bytes per launch of this kernel from the committed ncu --set full capture (same workload, N = 1)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if world == 1 and os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(kernel, {}).get("bytes")
+        entry = json.load(open(tpath)).get(kernel, {})
+        traffic, traffic_src = entry.get("bytes"), entry.get("source")
+    us_step = stages["greedy"] * 1e3 / max(steps_per_sel, 1)
     roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "note": "latency-bound dependency chain (one CTA, %d sequential steps, %.2f us/step); see DESIGN.md §6"
-                        % (steps_per_sel, stages["greedy"] * 1e3 / max(steps_per_sel, 1))}
-    roofline["latency_floor"] = greedy_latency_floor(stages["greedy"], steps_per_sel, clock_info)
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": (f"profiles/{traffic_src} (ncu --set full capture of this kernel on this workload; DRAM counters "
+                                   "cannot be read inside a timed run)") if traffic_src else None,
+                "peak_source": peak_src,
+                "note": "latency-bound dependency chain (%s, %d CTA(s), %d sequential steps, %.2f us/step): the sparse formulation "
+                        "touches ~1e3 entries per step where SURVEY's 24*N bytes describe the dense one; see latency_floor and DESIGN.md §6"
+                        % (gkernel, max(greedy_info["cluster"], 1), steps_per_sel, us_step)}
+    roofline["latency_floor"] = greedy_latency_floor(stages["greedy"], steps_per_sel, clock_info, gkernel)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": n / (ms_per_step * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(world), "pool_frames": n, "budget": BUDGET, "selected_frames": len(sel),
-                       "greedy_steps": steps_per_sel, "l2": "flushed between timed iterations (256 MiB write)",
-                       "parallelism": (f"1 process per GPU, pool sharded by column over {world} ranks, kNN rows and the "
-                                       "per-step (value,index) exchange over peer memory (NVLink)") if world > 1 else "single GPU",
-                       "identical_to_reference_golden": golden_ok},
+            "config": bench_config(world, n),
+            "result": {"selected_frames": len(sel), "greedy_steps": steps_per_sel, "greedy_kernel": greedy_info,
+                       "us_per_greedy_step": us_step, "identical_to_reference_golden": golden_ok},
             "stages_ms": stages, "selection_ms_per_budget": per_budget, "wall_ms_per_step": wall_ms / args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": n / e2e_sec, "unit": "frames/s", "ms_per_step": e2e_sec * 1e3,
                     "rank0_host_ms_last_step": selector.last_stats.get("host_ms"),
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clock_info,
+            "e2e_cold_cli_s": cold_cli,
             "extras": extras,
         }
         print(json.dumps(line), flush=True)
+        if golden_ok is False:
+            sys.stderr.write("bench.py: the selection differs from the reference golden (tests/golden/P28K_st.json)\n")
+            failed = True
+        if strong is not None and strong.get("identical_to_reference_golden") is False:
+            sys.stderr.write("bench.py: the multi-process selection of the 28,130-frame pool differs from the reference golden\n")
+            failed = True
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return 1 if failed else 0
 
 
 def main():
@@ -692,6 +761,7 @@ def main():
     ap.add_argument("--no-full-reference", action="store_true",
                     help="--impl reference: skip the one full-size cold + warm selection of the unmodified reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cold-cli", action="store_true", help="skip the wall-clock of a fresh tools/active_select.py process")
     ap.add_argument("--no-bev", action="store_true", help="skip the BEV-descriptor extras (histogram / tcgen05 tiles)")
     ap.add_argument("--bev-scale", type=int, default=1, help="N > 1 only: also run the dense BEV path on a pool of "
                     "28,130 x this many frames, budget 4800 (10 = the 281,300-frame pool: a 316 GB distance matrix)")

@@ -320,6 +320,13 @@ int adsel_get_counters(adsel_handle *h, int64_t *c4) {
     return ADSEL_OK;
 }
 
+int adsel_get_greedy_info(adsel_handle *h, int32_t *info2) {
+    ADSEL_REQUIRE(h && info2, "adsel_get_greedy_info: null argument");
+    info2[0] = h->greedy_variant;
+    info2[1] = h->greedy_cluster;
+    return ADSEL_OK;
+}
+
 int adsel_bev_set_points(adsel_handle *h, const float *points, const int64_t *frame_off, int32_t n_frames) {
     ADSEL_REQUIRE(h, "adsel_bev_set_points: null handle");
     ADSEL_CUDA(cudaSetDevice(h->device));

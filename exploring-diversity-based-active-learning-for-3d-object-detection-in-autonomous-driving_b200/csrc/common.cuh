@@ -166,6 +166,7 @@ struct adsel_handle {
     adsel::DevBuf<int32_t> d_sampled, d_out;
     adsel::DevBuf<double> d_result;              // [0] cost, [1] status, [2] m, [3] steps, [4] offending frame
     int greedy_cluster = 0;                      // cluster size of the last greedy launch (0: global-memory variant)
+    int greedy_variant = 0;                      // kernel of the last selection: 0 global-memory, 1 fast resident CTA, 2 resident cluster, 3 lazy rows
     bool groups_contiguous = false;              // every group is one contiguous index range (consecutive runs)
 
     // pool sharding across ranks (comm.cu): this rank owns frames [shard_lo, shard_hi)

@@ -1769,11 +1769,13 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
         ADSEL_CUDA(a.prof ? (fast.rb == 128 ? launch_fast<128, true>(h, a, fast.smem) : launch_fast<256, true>(h, a, fast.smem))
                           : (fast.rb == 128 ? launch_fast<128, false>(h, a, fast.smem) : launch_fast<256, false>(h, a, fast.smem)));
         h->greedy_cluster = 1;
+        h->greedy_variant = 1;
     } else if (!sharded && plan_resident(h, a, tl_want, &plan)) {   // fps resident in shared memory (one CTA or a cluster)
         ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n * plan.csize, h->stream));
         int unused = 0;
         ADSEL_CUDA(dispatch_resident(h, a, plan, false, &unused));
         h->greedy_cluster = plan.csize;
+        h->greedy_variant = 2;
     } else {
         ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, n, h->stream));
         fill_u64_kernel2<<<h->num_sms * 2, 256, 0, h->stream>>>(h->fps.p, (size_t)n, far_bits);
@@ -1786,6 +1788,7 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
         if (sharded) launch_greedy<true>(h, a, view, smem);
         else launch_greedy<false>(h, a, view, smem);
         h->greedy_cluster = 0;
+        h->greedy_variant = 0;
     }
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
@@ -1844,12 +1847,12 @@ int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *
             unsigned long long prof[16];
             cudaMemcpy(prof, greedy_prof_ptr(), sizeof(prof), cudaMemcpyDeviceToHost);
             const double steps = result[3] > 0 ? result[3] : 1;
-            if (h->greedy_cluster == 1)
+            if (h->greedy_variant == 1)
                 fprintf(stderr, "[fast profile] cycles/step: issue+group %.0f | bar0 %.0f | list lower %.0f | pend+flags %.0f | bar1 %.0f | "
                                 "refresh loads %.0f | refresh argmax %.0f | refresh store %.0f | bar2 %.0f | reduce loads %.0f | reduce argmax %.0f | bookkeeping %.0f\n",
                         prof[0] / steps, prof[1] / steps, prof[2] / steps, prof[3] / steps, prof[4] / steps, prof[5] / steps, prof[6] / steps,
                         prof[7] / steps, prof[8] / steps, prof[9] / steps, prof[10] / steps, prof[11] / steps);
-            if (h->greedy_cluster == 1)
+            if (h->greedy_variant == 1)
                 fprintf(stderr, "[fast profile] record-cache misses %.3f per step, next frame from the own block %.3f; steps with other blocks to re-reduce %.3f, blocks per step %.3f\n",
                         prof[12] / steps, prof[15] / steps, prof[13] / steps, prof[14] / steps);
             fprintf(stderr, "[greedy profile] cycles/step: apply %.0f | wait B1 %.0f | refresh %.0f | wait B2 %.0f | reduce(+exchange) %.0f | "

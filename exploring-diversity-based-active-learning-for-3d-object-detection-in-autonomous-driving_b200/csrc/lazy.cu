@@ -307,7 +307,8 @@ int lazy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sa
     double result[8];
     ADSEL_CUDA(cudaMemcpyAsync(result, h->d_result.p, sizeof(result), cudaMemcpyDeviceToHost, h->stream));
     ADSEL_TRY(end_stage(h, 3));
-    h->greedy_cluster = -1;   // lazy rows
+    h->greedy_cluster = 1;
+    h->greedy_variant = 3;   // lazy rows
     return finish_select(h, result, out_idx, out_m, out_cost, "adsel_select");
 }
 

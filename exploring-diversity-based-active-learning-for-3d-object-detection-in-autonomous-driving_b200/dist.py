@@ -4,10 +4,10 @@ import functools
 
 def get_dist_info():
     """``(rank, world_size)`` of the default torch.distributed group, ``(0, 1)`` when not initialised."""
-    try:
-        import torch.distributed as dist
-    except ImportError:  # pragma: no cover - torch is part of the image
-        return 0, 1
+    import sys
+    dist = sys.modules.get("torch.distributed")
+    if dist is None:         # nobody imported it, so no process group can exist: a single-process run (the CLI's one-shot
+        return 0, 1          # selection) does not pay the import of torch for this question
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1

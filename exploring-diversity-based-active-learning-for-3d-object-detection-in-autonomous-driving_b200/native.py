@@ -64,6 +64,7 @@ _SIGNATURES = {
     "adsel_get_fps": (ctypes.c_int, [_P, _P]),
     "adsel_get_stage_ms": (ctypes.c_int, [_P, _P]),
     "adsel_get_counters": (ctypes.c_int, [_P, _P]),
+    "adsel_get_greedy_info": (ctypes.c_int, [_P, _P]),
     "adsel_exp_f64": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P]),
     "adsel_exp_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P]),
     "adsel_pairdist_set_descriptors": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32]),
@@ -345,6 +346,14 @@ class Handle:
         c = np.zeros(4, dtype=np.int64)
         _check(load().adsel_get_counters(self._h, _ptr(c)))
         return dict(zip(("launches", "steps", "list_entries", "nnz"), c.tolist()))
+
+    GREEDY_KERNELS = ("greedy_select_kernel", "greedy_fast_kernel", "greedy_resident_kernel", "greedy_lazy_kernel")
+
+    def greedy_info(self):
+        """Kernel of the last selection and its cluster size (csrc/greedy.cu, csrc/lazy.cu)."""
+        v = np.zeros(2, dtype=np.int32)
+        _check(load().adsel_get_greedy_info(self._h, _ptr(v)))
+        return {"kernel": self.GREEDY_KERNELS[int(v[0])], "cluster": int(v[1])}
 
     # -- BEV descriptors ------------------------------------------------------------------------
     NUSC_RANGE = (-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)     # examples/active/cbgs_spatial_temporal.py:280

@@ -331,6 +331,9 @@ class DistWorld(_WorldBase):
     def counters(self):
         return self.handle.counters()
 
+    def greedy_info(self):
+        return self.handle.greedy_info()
+
 
 _ENGINES = {}
 

@@ -117,6 +117,10 @@ int adsel_get_stage_ms(adsel_handle *h, float *ms8);
 /* counters of the last select: [0] kernels launched since adsel_create, [1] greedy steps,
  * [2] total neighbour-list entries, [3] csr nnz */
 int adsel_get_counters(adsel_handle *h, int64_t *c4);
+/* which greedy kernel the last selection ran: info2[0] = 0 global-memory loop (pool beyond a cluster's shared memory, column
+ * shards), 1 fast resident CTA, 2 resident thread-block cluster, 3 lazy rows (one search per selected frame);
+ * info2[1] = CTAs of the cluster */
+int adsel_get_greedy_info(adsel_handle *h, int32_t *info2);
 
 /* ---- pool sharded over the GPUs of one NVSwitch box -------------------------------
  * The reference issues no collective here: under torch.distributed.launch every rank recomputes the

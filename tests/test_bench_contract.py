@@ -112,9 +112,11 @@ def test_bev_extras_bookkeeping_with_a_stub_engine():
 def test_greedy_latency_floor_model():
     sys.path.insert(0, ROOT)
     import bench
-    m = bench.greedy_latency_floor(9.02, 4047, {"sm_mhz": 1965.0})
-    assert m["cycles_per_step"] == 4 * 262 + 3 * 34
-    assert abs(m["floor_us_per_step"] - 1150 / 1965.0) < 1e-12 and abs(m["achieved_us_per_step"] - 9020.0 / 4047) < 1e-9
-    assert abs(m["frac"] - m["floor_us_per_step"] / m["achieved_us_per_step"]) < 1e-12 and 0.2 < m["frac"] < 0.3
-    assert bench.greedy_latency_floor(9.02, 4047, None)["floor_us_per_step"] == m["floor_us_per_step"]   # clocks unavailable
+    m = bench.greedy_latency_floor(9.02, 4047, {"sm_mhz": 1965.0}, "greedy_select_kernel")
+    assert m["cycles_per_step"] == 4 * 295 + 3 * 71
+    assert abs(m["floor_us_per_step"] - 1393 / 1965.0) < 1e-12 and abs(m["achieved_us_per_step"] - 9020.0 / 4047) < 1e-9
+    assert abs(m["frac"] - m["floor_us_per_step"] / m["achieved_us_per_step"]) < 1e-12 and 0.25 < m["frac"] < 0.4
+    r = bench.greedy_latency_floor(5.4, 4047, {"sm_mhz": 1965.0})                      # resident kernels: one L2 round trip
+    assert r["cycles_per_step"] == 295 + 3 * 71 + 2 * (31 + 3 * 26) + 31 and r["cycles_per_step"] < m["cycles_per_step"]
+    assert bench.greedy_latency_floor(9.02, 4047, None)["floor_us_per_step"] == r["floor_us_per_step"]   # clocks unavailable
     assert bench.greedy_latency_floor(0.0, 0, {"sm_mhz": None})["frac"] is None
