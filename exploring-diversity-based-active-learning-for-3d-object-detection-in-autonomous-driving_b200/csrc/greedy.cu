@@ -561,7 +561,7 @@ __device__ __forceinline__ Best cluster_exchange(unsigned long long *xslot, unsi
     }
 
 #define FPROF(slot)                                       \
-    if (PROFILE && threadIdx.x == 0) {                     \
+    if (PROFILE && threadIdx.x == 0 && blockIdx.x == 0) { \
         long long now;                                    \
         asm volatile("mov.u64 %0, %%clock64;" : "=l"(now) :: "memory"); \
         prof_acc[slot] += (unsigned long long)(now - prof_t); \
@@ -1009,7 +1009,8 @@ struct __align__(16) FastShared {
     uint4 sub_rec[8][2];         // record of every sub-block's best frame of the row's own block, copied in asynchronously
     unsigned long long sub_val[8];
     int sub_idx[8];
-    int err, err_frame, sat;
+    int err, err_frame, sat, winner;
+    uint4 xrec[2];               // CLUSTER: this CTA's (value, frame) maximum of the step, read by the peers
 };
 
 __device__ __forceinline__ int atom_inc_shared(int *p) {
@@ -1031,7 +1032,7 @@ __device__ __forceinline__ uint4 lds128_volatile(const void *p) {   // one 16-by
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int RB, bool PROFILE>
+template <int RB, bool CLUSTER, bool PROFILE>
 __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs a) {
     constexpr int NT = RES_NT, NW = NT / 32, PER = RB / 32, NSUB = RB / 32;   // NSUB <= NW: one sub-block of the own block per warp
     constexpr int SHIFT = RB == 256 ? 8 : 7;
@@ -1039,6 +1040,17 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_t = PROFILE ? clock64() : 0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // CLUSTER: the columns are split over the CTAs of a thread-block cluster; this CTA holds frames [c_lo, c_hi).  Every CTA
+    // applies the part of a row that falls into its slice, reduces its own block maxima, and the CTAs' maxima are exchanged
+    // through distributed shared memory behind the hardware cluster barrier (a mailbox of tagged words polled by the
+    // CTAs, 414 cycles in isolation -- tools/microbench/dsmem.cu -- cost 4,600 cycles per step inside this loop; the
+    // barrier form costs ~1,500); the bookkeeping is replicated, CTA 0 writes the results.
+    int crank = 0, csize = 1;
+    if (CLUSTER) {
+        crank = (int)cg::this_cluster().block_rank();
+        csize = a.csize;
+    }
+    const bool writer = crank == 0 && tid == 0;
 
     // ---- hot arguments, pinned in registers ----
     int n = a.n, cols = a.cta_cols, nblk = a.r_nblk, G = a.tl_n, out_cap = a.out_cap;
@@ -1046,13 +1058,16 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     const double *lval = a.list_val;
     const FrameRec *recs = a.rec;
     int32_t *out = a.out;
-    unsigned char *sel_bytes = a.is_selected;
+    unsigned char *sel_bytes = a.is_selected + (size_t)crank * a.n;   // this CTA's private copy of the flags
+    int c_lo = min(crank * a.cta_cols, a.n), c_len = min(a.cta_cols, a.n - c_lo);   // this CTA's frames [c_lo, c_lo + c_len)
     double budget = a.budget, cost_f = a.cost_f, cost_b = a.cost_b;
     const bool has_list = a.spatial == ADSEL_SPATIAL_GEODESIC, has_group = a.temporal != 0;
     ADSEL_PIN32(n);
     ADSEL_PIN32(nblk);
     ADSEL_PIN32(G);
     ADSEL_PIN32(out_cap);
+    ADSEL_PIN32(c_lo);
+    ADSEL_PIN32(c_len);
     ADSEL_PIN64(lidx);
     ADSEL_PIN64(lval);
     ADSEL_PIN64(recs);
@@ -1073,13 +1088,13 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     __shared__ FastShared sh;
 
     const unsigned long long far_bits = a.far_bits;
-    for (int i = tid; i < cols; i += NT) fps_s[i] = i < n ? far_bits : 0ull;
+    for (int i = tid; i < cols; i += NT) fps_s[i] = i < c_len ? far_bits : 0ull;
     for (int d = tid; d < G; d += NT)
         gval[d] = (unsigned long long)__double_as_longlong(combine(a.spatial, a.temporal, a.aggregate, a.lambda_t, a.s_far, a.tlut[d]));
     // every fps entry starts at `far`, so a block's best is its first frame: no initial refresh
     for (int lb = tid; lb < nblk; lb += NT) {
-        const int first = lb << SHIFT;
-        const bool nonempty = first < n;
+        const int first = c_lo + (lb << SHIFT);
+        const bool nonempty = (lb << SHIFT) < c_len;
         blk_val[lb] = nonempty ? far_bits : 0ull;
         blk_idx[lb] = nonempty ? first : 0x7fffffff;
         blk_step[lb] = -1;
@@ -1120,10 +1135,11 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     unsigned flag_seen = 0;
     bool marking = true;             // false while the rows of the buffer are applied (all blocks are re-reduced afterwards)
 
-    auto lower = [&](int j, unsigned long long v) {
-        if (v < fps_s[j]) {
-            fps_s[j] = v;
-            const int lb = j >> SHIFT;
+    auto lower = [&](int j, unsigned long long v) {   // j: frame of this CTA's slice
+        const int lj = j - c_lo;
+        if (v < fps_s[lj]) {
+            fps_s[lj] = v;
+            const int lb = lj >> SHIFT;
             // Only the entry that IS a block's maximum can change it by decreasing.  The block of the row's own
             // frame is always re-reduced (by all warps), so it is not listed; the block of the PREVIOUS row's frame gets
             // its maximum written while this row is applied, so it is re-reduced in full when anything in it is lowered;
@@ -1157,7 +1173,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
         }
         // 2. temporal group in their shadow: frames [e0, e1) within the LUT's unsaturated reach of cur
         if (has_group) {
-            const int g0 = max(e0, cur - sat + 1), g1 = min(e1, cur + sat);
+            const int g0 = max(max(e0, cur - sat + 1), c_lo), g1 = min(min(e1, cur + sat), c_lo + c_len);
             for (int j = g0 + tid; j < g1; j += NT) {
                 const int d = abs(j - cur);
                 const unsigned long long v = d < G ? gval[d]
@@ -1169,9 +1185,16 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
         __syncthreads();   // group writes before list writes (list values of same-group frames are <= the group values); hidden under the list loads
         RPROF_MARK(1)
         // 3. list entries: unique columns, plain writes
-        if (j0 >= 0) lower(j0, v0);
-        if (j1 >= 0) lower(j1, v1);
-        for (int t = tid + 2 * NT; t < l_len; t += NT) lower(pi[t - tid], (unsigned long long)__double_as_longlong(pv[t - tid]));
+        if (CLUSTER) {   // entries of other CTAs' columns are theirs to apply
+            if ((unsigned)(j0 - c_lo) < (unsigned)c_len) lower(j0, v0);
+            if ((unsigned)(j1 - c_lo) < (unsigned)c_len) lower(j1, v1);
+            for (int t = tid + 2 * NT; t < l_len; t += NT)
+                if ((unsigned)(pi[t - tid] - c_lo) < (unsigned)c_len) lower(pi[t - tid], (unsigned long long)__double_as_longlong(pv[t - tid]));
+        } else {
+            if (j0 >= 0) lower(j0, v0);
+            if (j1 >= 0) lower(j1, v1);
+            for (int t = tid + 2 * NT; t < l_len; t += NT) lower(pi[t - tid], (unsigned long long)__double_as_longlong(pv[t - tid]));
+        }
         // records copied into blk_rec by last step's refresh: landed long ago; waited for here, where none of this thread's
         // own loads is in flight (the wait is a scoreboard barrier that would also wait for those)
         if (lane == 0) cp_async_wait_all();
@@ -1198,7 +1221,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             const unsigned long long v = fps_s[base + 32 * i];
             hi[i] = (unsigned)(v >> 32);
             lo[i] = (unsigned)v;
-            idx[i] = base + 32 * i < n ? base + 32 * i : 0x7fffffff;
+            idx[i] = base + 32 * i < c_len ? c_lo + base + 32 * i : 0x7fffffff;
         }
         if (PROFILE) asm volatile("" ::"r"(hi[0] + hi[PER - 1] + lo[0]));
         FPROF(5)
@@ -1219,15 +1242,16 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     bool local_abort = false;
     {
         const unsigned long long needed = a.list_cursor ? *a.list_cursor : 0ull;
-        if (tid == 0) a.result[5] = (double)needed;
+        if (writer) a.result[5] = (double)needed;
         if ((long long)needed > a.list_capacity) {   // neighbour-list pool too small: the host grows it and reruns
             local_abort = true;
-            if (tid == 0) {
+            if (writer) {
                 a.result[1] = (double)ADSEL_ERR_CAPACITY;
                 a.result[4] = -1.0;
             }
         }
     }
+    if (CLUSTER) cg::this_cluster().sync();   // every CTA of the cluster is resident before the first exchange
     long long steps = 0;
     bool seeding = a.n_sampled > 0;   // first pick = argmax without a preceding update (:165)
     if (!local_abort) {
@@ -1235,11 +1259,11 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             for (int t = 0; t < a.n_sampled; ++t) sel_bytes[a.sampled[t]] = 1;
         if (a.n_sampled == 0) {   // empty buffer: the caller's random.choice is taken and costed up front (:168,172-174)
             cur = a.first_index;
-            cur_blk = cur >> SHIFT;
+            cur_blk = (unsigned)(cur - c_lo) < (unsigned)c_len ? (cur - c_lo) >> SHIFT : -1;
             uint4 lo, hi;
             ldg_rec_async(recs + cur, lo, hi);
             const double box_cost = take_rec(lo, hi);
-            if (tid == 0) out[0] = cur;
+            if (writer) out[0] = cur;
             m = 1;
             to_flag = cur;
             cost = __dadd_rn(cost, cost_f);
@@ -1281,10 +1305,10 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             }
             const int ref_blk = cur_blk;   // -1: nothing was applied in this iteration (seeding)
             if (ref_blk >= 0 && wid < NSUB) {
-                const int j = (ref_blk << SHIFT) + 32 * wid + lane;
-                const unsigned long long v = fps_s[j];
+                const int lj = (ref_blk << SHIFT) + 32 * wid + lane;
+                const unsigned long long v = fps_s[lj];
                 unsigned hi[1] = {(unsigned)(v >> 32)}, lo[1] = {(unsigned)v};
-                int idx[1] = {j < n ? j : 0x7fffffff};
+                int idx[1] = {lj < c_len ? c_lo + lj : 0x7fffffff};
                 const Win x = warp_argmax<1>(hi, lo, idx);
                 if (lane == 0) {
                     sh.sub_val[wid] = ((unsigned long long)x.hi << 32) | x.lo;
@@ -1339,12 +1363,31 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
                 const bool take = w.hi > y.hi || (w.hi == y.hi && (w.lo > y.lo || (w.lo == y.lo && w.idx < y.idx)));
                 if (take) y = w;
             }
+            if (CLUSTER) {   // the CTAs' maxima -> the cluster's maximum, on every warp of every CTA
+                // every CTA publishes its maximum in its own shared memory, the hardware cluster barrier orders it, every warp
+                // reads the peers' records through distributed shared memory (records double-buffered by step parity)
+                const int xp = (int)(steps & 1);
+                if (tid == 0) sh.xrec[xp] = make_uint4(y.hi, y.lo, (unsigned)y.idx, 0u);
+                asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+                unsigned hi1[1] = {0u}, lo1[1] = {0u};
+                int idx1[1] = {0x7fffffff};
+                if (lane < csize) {
+                    unsigned src;
+                    uint4 r;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(src) : "r"((unsigned)__cvta_generic_to_shared(&sh.xrec[xp])), "r"(lane));
+                    asm volatile("ld.shared::cluster.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(src) : "memory");
+                    hi1[0] = r.x;
+                    lo1[0] = r.y;
+                    idx1[0] = (int)r.z;
+                }
+                y = warp_argmax<1>(hi1, lo1, idx1);
+            }
             FPROF(10)
             const int this_step = (int)steps;
             ++steps;
             const int nxt = y.idx;
             if (nxt < 0 || nxt >= n) {   // empty pool: cannot happen with n > 0
-                if (tid == 0) a.result[1] = (double)ADSEL_ERR_INVALID;
+                if (writer) a.result[1] = (double)ADSEL_ERR_INVALID;
                 stop = 2;
                 break;
             }
@@ -1370,14 +1413,18 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             // may still be receiving its record and is not trusted: one global round trip instead.
             prev_blk = ref_blk;
             cur = nxt;
-            cur_blk = nxt >> SHIFT;
+            cur_blk = (unsigned)(nxt - c_lo) < (unsigned)c_len ? (nxt - c_lo) >> SHIFT : -1;   // -1: another CTA's frame
             uint4 rlo, rhi;
-            if (cur_blk == ref_blk) {
-                const int w = (nxt >> 5) & (NSUB - 1);
-                do {
+            if (cur_blk < 0) {   // CLUSTER only: one global round trip (the owner's cache is not visible from here)
+                ldg_rec_async(recs + nxt, rlo, rhi);
+            } else if (cur_blk == ref_blk) {
+                const int w = ((nxt - c_lo) >> 5) & (NSUB - 1);
+                while (true) {
                     rlo = lds128_volatile(&sh.sub_rec[w][0]);
                     rhi = lds128_volatile(&sh.sub_rec[w][1]);
-                } while (rlo.w != (unsigned)nxt || rhi.w != (unsigned)nxt);
+                    if (rlo.w == (unsigned)nxt && rhi.w == (unsigned)nxt) break;
+                    __nanosleep(20);   // 256 threads spinning would occupy the port the copy arrives through
+                }
                 if (PROFILE && tid == 0) prof_acc[15] += 1;
             } else {
                 rlo = blk_rec[2 * cur_blk];
@@ -1390,7 +1437,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             const double box_cost = take_rec(rlo, rhi);
             if (seeding) {   // :165,172-174 -- always taken, no budget check
                 seeding = false;
-                if (tid == 0) out[0] = nxt;
+                if (writer) out[0] = nxt;
                 m = 1;
                 cost = __dadd_rn(cost, cost_f);
                 cost = __dadd_rn(cost, box_cost);
@@ -1403,7 +1450,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             const bool over = cost > budget;       // :186
             const bool full = !over && m >= out_cap;
             if (over || full) {
-                if (tid == 0) {
+                if (writer) {
                     if (flag_seen) {               // :182 comes before the cost test
                         a.result[1] = (double)ADSEL_ERR_RESELECTED;
                         a.result[4] = (double)nxt;
@@ -1415,7 +1462,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
                 stop = over ? 1 : 2;
                 break;
             }
-            if (tid == 0) out[m] = nxt;
+            if (writer) out[m] = nxt;
             m += 1;
             to_flag = nxt;
             flag_check = true;
@@ -1424,18 +1471,19 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     }
     __syncthreads();
     if (lane == 0) cp_async_wait_all();
-    if (stop == 2 && sh.err_frame >= 0 && tid == 0) {
+    if (stop == 2 && sh.err_frame >= 0 && writer) {
         a.result[1] = (double)ADSEL_ERR_RESELECTED;
         a.result[4] = (double)sh.err_frame;
     }
-    for (int i = tid; i < n; i += NT) a.fps[i] = fps_s[i];   // adsel_get_fps
-    if (tid == 0) {
+    for (int i = tid; i < c_len; i += NT) a.fps[c_lo + i] = fps_s[i];   // adsel_get_fps
+    if (writer) {
         a.result[0] = cost;
         a.result[2] = (double)m;
         a.result[3] = (double)steps;
         if (PROFILE)
             for (int i = 0; i < 16; ++i) a.prof[i] = prof_acc[i];
     }
+    if (CLUSTER) cg::this_cluster().sync();   // no CTA leaves while a peer may still read its record
 }
 
 // ---- host side of the resident variant -----------------------------------------------------------
@@ -1539,44 +1587,96 @@ static bool plan_resident(adsel_handle *h, GreedyArgs &a, int tl_want, ResidentP
 
 // ---- host side of the fast variant ---------------------------------------------------------------
 struct FastPlan {
-    int rb = 0, cols = 0, nblk = 0, g = 0;
+    int rb = 0, cols = 0, nblk = 0, g = 0, csize = 0;
     size_t smem = 0;
 };
 
-// One resident CTA with the lean step (greedy_fast_kernel): no Euclid term, contiguous temporal groups, the
-// whole pool on this device, columns + block tables within 227 KB.  ADSEL_GREEDY_FAST=0 disables it.
-static bool plan_fast(const adsel_handle *h, const GreedyArgs &a, bool sharded, int g_want, FastPlan *out) {
+template <int RB, bool CLUSTER, bool PROFILE>
+static cudaError_t launch_fast(adsel_handle *h, const GreedyArgs &a, size_t smem, bool dry_run, int *max_clusters) {
+    auto kernel = greedy_fast_kernel<RB, CLUSTER, PROFILE>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (CLUSTER && a.csize > 8) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(CLUSTER ? a.csize : 1), 1, 1);
+    cfg.blockDim = dim3(RES_NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)(CLUSTER ? a.csize : 1);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CLUSTER ? 1 : 0;
+    if (dry_run) {   // can a cluster of this size and shared-memory footprint be scheduled at all?
+        *max_clusters = 1;
+        return CLUSTER ? cudaOccupancyMaxActiveClusters(max_clusters, kernel, &cfg) : cudaSuccess;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
+static cudaError_t dispatch_fast(adsel_handle *h, const GreedyArgs &a, const FastPlan &pl, bool dry_run, int *max_clusters) {
+    if (pl.csize > 1) return a.prof ? launch_fast<256, true, true>(h, a, pl.smem, dry_run, max_clusters)
+                                    : launch_fast<256, true, false>(h, a, pl.smem, dry_run, max_clusters);
+    if (a.prof) return pl.rb == 128 ? launch_fast<128, false, true>(h, a, pl.smem, dry_run, max_clusters)
+                                    : launch_fast<256, false, true>(h, a, pl.smem, dry_run, max_clusters);
+    return pl.rb == 128 ? launch_fast<128, false, false>(h, a, pl.smem, dry_run, max_clusters)
+                        : launch_fast<256, false, false>(h, a, pl.smem, dry_run, max_clusters);
+}
+
+// The lean step (greedy_fast_kernel): no Euclid term, contiguous temporal groups, the whole pool on this device, its
+// columns resident in the shared memory of ONE CTA when they fit (<= 28.4 k frames), else of the smallest thread-block
+// cluster that holds them (2 / 4 / 8 / 16 CTAs: up to ~450 k frames).  ADSEL_GREEDY_FAST=0 disables it;
+// ADSEL_GREEDY_CLUSTER=1/2/4/8/16 forces the cluster size.
+static bool plan_fast(adsel_handle *h, GreedyArgs &a, bool sharded, int g_want, FastPlan *out) {
     const char *e = getenv("ADSEL_GREEDY_FAST");
     if (e && atoi(e) == 0) return false;
     const char *c = getenv("ADSEL_GREEDY_CLUSTER");
-    if (c && *c && atoi(c) != 1) return false;   // an explicit cluster size (or 0: global-memory kernel) was asked for
+    const int forced = (c && *c) ? atoi(c) : -1;
+    if (forced == 0) return false;               // the global-memory kernel was asked for
     if (sharded || a.spatial == ADSEL_SPATIAL_EUCLID || (a.temporal && !a.groups_contiguous)) return false;
     if (a.list_capacity >= (1ll << 40)) return false;
     const size_t budget = 232448 - 512;   // 227 KB opt-in maximum per CTA minus the static shared variables (FastShared: 400 B)
-    for (int rb = 128; rb <= 256; rb *= 2) {
-        const long long cols = ((long long)a.n + rb - 1) / rb * rb, nblk = cols / rb;
-        const size_t fixed = (size_t)cols * 8 + (size_t)nblk * (8 + 32 + 4 + 8 + 4);
-        if (fixed > budget) continue;
-        long long g = (long long)((budget - fixed) / 8);
-        if (g > g_want) g = g_want;
-        if ((nblk + g) & 1) g += ((size_t)(g + 1) * 8 <= budget - fixed) ? 1 : -1;   // cached records are 16-byte aligned
-        if (g < 0) continue;
-        out->rb = rb;
-        out->cols = (int)cols;
-        out->nblk = (int)nblk;
-        out->g = (int)g;
-        out->smem = fixed + (size_t)g * 8;
-        return true;
+    for (int cs = 1; cs <= CLUSTER_MAX; cs *= 2) {
+        if (forced > 0 && cs != forced) continue;
+        for (int rb = 128; rb <= 256; rb *= 2) {
+            if (cs > 1 && rb != 256) continue;
+            long long cols = ((long long)a.n + cs - 1) / cs;
+            cols = (cols + rb - 1) / rb * rb;
+            const long long nblk = cols / rb;
+            const size_t fixed = (size_t)cols * 8 + (size_t)nblk * (8 + 32 + 4 + 8 + 4) + 8;
+            if (fixed > budget) continue;
+            long long g = (long long)((budget - fixed) / 8);
+            if (g > g_want) g = g_want;
+            if ((nblk + g) & 1) g += ((size_t)(g + 1) * 8 <= budget - fixed) ? 1 : -1;   // cached records are 16-byte aligned
+            if (g < 0) continue;
+            FastPlan pl;
+            pl.rb = rb;
+            pl.cols = (int)cols;
+            pl.nblk = (int)nblk;
+            pl.g = (int)g;
+            pl.csize = cs;
+            pl.smem = fixed + (size_t)g * 8;
+            a.csize = cs;
+            a.cta_cols = pl.cols;
+            a.r_nblk = pl.nblk;
+            a.tl_n = pl.g;
+            a.sel_words = 0;
+            int max_clusters = 0;
+            if (dispatch_fast(h, a, pl, true, &max_clusters) != cudaSuccess || max_clusters < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            *out = pl;
+            return true;
+        }
     }
     return false;
-}
-
-template <int RB, bool PROFILE>
-static cudaError_t launch_fast(adsel_handle *h, const GreedyArgs &a, size_t smem) {
-    cudaError_t e = cudaFuncSetAttribute(greedy_fast_kernel<RB, PROFILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    greedy_fast_kernel<RB, PROFILE><<<1, RES_NT, smem, h->stream>>>(a);
-    return cudaGetLastError();
 }
 
 template <bool SHARDED>
@@ -1611,8 +1711,9 @@ int greedy_preload() {
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<256, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<512, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<1024, false>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<128, false>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<128, false, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, false, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, true, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<128, false, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<256, false, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<128, true, false>));
@@ -1759,18 +1860,14 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
     ResidentPlan plan;
     FastPlan fast;
     const int tl_want = a.temporal ? (p->normalize == ADSEL_NORM_EXP && a.tl_n > 64 ? 64 : a.tl_n) : 0;
-    if (plan_fast(h, a, sharded, tl_want, &fast)) {   // one resident CTA, lean step
-        a.csize = 1;
-        a.cta_cols = fast.cols;
-        a.r_nblk = fast.nblk;
-        a.tl_n = fast.g;
-        a.sel_words = 0;
-        ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n, h->stream));
-        ADSEL_CUDA(a.prof ? (fast.rb == 128 ? launch_fast<128, true>(h, a, fast.smem) : launch_fast<256, true>(h, a, fast.smem))
-                          : (fast.rb == 128 ? launch_fast<128, false>(h, a, fast.smem) : launch_fast<256, false>(h, a, fast.smem)));
-        h->greedy_cluster = 1;
+    const int tl_all = a.tl_n, sel_all = a.sel_words;
+    if (plan_fast(h, a, sharded, tl_want, &fast)) {   // resident in one CTA or a cluster, lean step
+        ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n * fast.csize, h->stream));
+        int unused = 0;
+        ADSEL_CUDA(dispatch_fast(h, a, fast, false, &unused));
+        h->greedy_cluster = fast.csize;
         h->greedy_variant = 1;
-    } else if (!sharded && plan_resident(h, a, tl_want, &plan)) {   // fps resident in shared memory (one CTA or a cluster)
+    } else if ((a.tl_n = tl_all, a.sel_words = sel_all, !sharded) && plan_resident(h, a, tl_want, &plan)) {   // fps resident in shared memory (one CTA or a cluster)
         ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n * plan.csize, h->stream));
         int unused = 0;
         ADSEL_CUDA(dispatch_resident(h, a, plan, false, &unused));
