@@ -44,6 +44,9 @@ int geodesic_max_finite(adsel_handle *h, double *out);
 int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sampled, int32_t n_sampled,
                   int32_t first_index, int32_t *out_idx, int32_t out_cap, int32_t *out_m, double *out_cost);
 
+int fused_feature_select(adsel_handle *h, const adsel_select_params *p, double lambda_f, int32_t seed_spatial_only,
+                         const int32_t *sampled, int32_t n_sampled, int32_t first_index, int32_t *out_idx, int32_t out_cap,
+                         int32_t *out_m, double *out_cost);
 int bev_generate(adsel_handle *h, int32_t n_frames, const int64_t *frame_off_host, int32_t n_sweeps, uint64_t seed);
 int bev_set_points(adsel_handle *h, const float *pts_host, const int64_t *frame_off_host, int32_t n_frames);
 int bev_build(adsel_handle *h, const adsel_bev_params *p, int aggregate_atomics, int32_t frame_base, int32_t total_frames);
@@ -394,6 +397,15 @@ int adsel_select_dense(adsel_handle *h, const adsel_select_params *p, const int3
     ADSEL_REQUIRE(h, "adsel_select_dense: null handle");
     ADSEL_CUDA(cudaSetDevice(h->device));
     return dense_select(h, p, n_boxes, sampled, n_sampled, first_index, out_idx, out_cap, out_m, out_cost);
+}
+
+int adsel_select_fused_feature(adsel_handle *h, const adsel_select_params *p, double lambda_f, int32_t seed_spatial_only,
+                               const int32_t *sampled, int32_t n_sampled, int32_t first_index, int32_t *out_idx,
+                               int32_t out_cap, int32_t *out_m, double *out_cost) {
+    ADSEL_REQUIRE(h, "adsel_select_fused_feature: null handle");
+    ADSEL_REQUIRE(lambda_f >= 0.0, "adsel_select_fused_feature: lambda_f must be >= 0");
+    ADSEL_CUDA(cudaSetDevice(h->device));
+    return fused_feature_select(h, p, lambda_f, seed_spatial_only, sampled, n_sampled, first_index, out_idx, out_cap, out_m, out_cost);
 }
 
 int adsel_feature_distance_build(adsel_handle *h, const float *feats, int32_t n, int32_t dim, int32_t p) {

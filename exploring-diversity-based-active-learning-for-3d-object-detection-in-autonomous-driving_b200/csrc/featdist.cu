@@ -9,10 +9,19 @@
 //
 // Arithmetic: per element d = fl(a - b) and the term |d| (p == 2: sqrt(fl(d*d)), which in binary
 // floating point equals |d| whenever d*d neither underflows nor overflows; outside that range the
-// square root is evaluated literally).  The float32 sum over the feature dimension runs in index order
-// here, whereas torch uses a vectorised cascade sum whose order depends on the CPU's vector width, so
-// the map agrees with the reference to float32 summation accuracy (tests: 1e-5 relative), not bitwise;
-// the features themselves need the trained detector (out of scope), tests use synthetic ones.
+// square root is evaluated literally).
+//
+// Summation order.  torch's CPU `.sum(1)` of a contiguous float32 [N, C] tensor is a vectorised cascade sum
+// (aten/src/ATen/native/cpu/SumKernel.cpp: 8 float lanes x 4 interleaved accumulators, blocks of 16 vectors
+// folded through four levels, then the four accumulators, then the scalar tail, then the 8 lanes in order);
+// oracle/restatement.py::torch_sum_f32 restates it and tests/test_oracle_feature.py pins it bit for bit against
+// torch 2.11 for C = 16 .. 8192.  feature_l1_torch_kernel follows exactly that order whenever C is a multiple of
+// 32 (the reference's C is 512): lane l of a warp IS accumulator (l / 8, l % 8), so the map equals the
+// reference's BIT FOR BIT and every comparison of the greedy loop resolves the same way.  Other C fall back to
+// feature_l1_kernel (index-order sum: rows agree to float32 summation accuracy, 1e-5 relative, not bitwise).
+// The features themselves need the trained detector (out of scope), tests use synthetic ones.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace adsel {
@@ -96,6 +105,104 @@ feature_l1_kernel(const float *__restrict__ x, int n, int dim, int p2, float *__
     }
 }
 
+
+// ---- torch's summation order, bit for bit ---------------------------------------------------------------------
+// One warp per output at a time: lane l accumulates the terms c = 32 pos + l (pos = 0 .. C/32 - 1), i.e. it is torch's
+// accumulator (k = l / 8, lane = l % 8) of the 4 x 8 interleaved vector accumulators; every 16 terms the running sum is
+// folded into the next level exactly as multi_row_sum does.  Then ((a0 + a1) + a2) + a3 over k and the 8 lanes in
+// order.  A CTA stages 64 "j" rows in shared memory; each of its 8 warps takes 8 "i" rows, one after the other, with
+// the i row in registers.  Two outputs are in flight per warp so that the serial shuffle tail of one overlaps the
+// accumulation of the other.
+constexpr int FT_ROWS = 64, FT_THREADS = 256, FT_MAXREG = 32;   // C <= 32 * FT_MAXREG = 1024 keeps the i row in registers
+
+__device__ __forceinline__ float torch_tail(float acc) {   // acc: this lane's accumulator (k = lane / 8, l8 = lane % 8)
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    // partial_sums[0] += partial_sums[k], k = 1, 2, 3 (lanes 0..7 hold the result)
+    float v = acc;
+    v = __fadd_rn(v, __shfl_sync(full, acc, (lane & 7) + 8));
+    v = __fadd_rn(v, __shfl_sync(full, acc, (lane & 7) + 16));
+    v = __fadd_rn(v, __shfl_sync(full, acc, (lane & 7) + 24));
+    // final_acc = 0; final_acc += partials[0..7] in order
+    float s = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) s = __fadd_rn(s, __shfl_sync(full, v, l));
+    return s;
+}
+
+template <int P2>
+__global__ void __launch_bounds__(FT_THREADS)
+feature_l1_torch_kernel(const float *__restrict__ x, int n, int dim, float *__restrict__ out, int ld, int rows) {
+    extern __shared__ float ft_smem[];   // [rows][dim]: 64 rows, fewer (an even number) when 64 do not fit 227 KB
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int j0 = blockIdx.x * rows, i0 = blockIdx.y * rows;
+    const int nvec = dim / 32;            // torch's size_ilp: vectors per interleaved accumulator
+    for (int e = threadIdx.x; e < rows * dim; e += FT_THREADS) {
+        const int r = e / dim, c = e - r * dim;
+        ft_smem[e] = j0 + r < n ? x[(size_t)(j0 + r) * dim + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int ii = wid; ii < rows; ii += FT_THREADS / 32) {
+        const int i = i0 + ii;
+        if (i >= n) break;
+        float a[FT_MAXREG];
+#pragma unroll
+        for (int q = 0; q < FT_MAXREG; ++q) a[q] = q < nvec ? x[(size_t)i * dim + 32 * q + lane] : 0.0f;
+        for (int jj = 0; jj < rows; jj += 2) {
+            const float *b0 = ft_smem + (size_t)jj * dim + lane, *b1 = b0 + dim;
+            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            int pos = 0;
+#pragma unroll 1
+            for (; pos + 16 <= nvec; ) {
+#pragma unroll
+                for (int q = 0; q < FT_MAXREG; ++q) {
+                    if (q >= pos && q < pos + 16) {
+                        const float d0 = __fsub_rn(b0[32 * q], a[q]), d1 = __fsub_rn(b1[32 * q], a[q]);
+                        acc[0][0] = __fadd_rn(acc[0][0], P2 ? __fsqrt_rn(__fmul_rn(d0, d0)) : fabsf(d0));
+                        acc[1][0] = __fadd_rn(acc[1][0], P2 ? __fsqrt_rn(__fmul_rn(d1, d1)) : fabsf(d1));
+                    }
+                }
+                pos += 16;
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {   // fold through the levels like multi_row_sum (level_power = 4)
+                    acc[o][1] = __fadd_rn(acc[o][1], acc[o][0]);
+                    acc[o][0] = 0.f;
+                    if ((pos & 0xf0) == 0) {
+                        acc[o][2] = __fadd_rn(acc[o][2], acc[o][1]);
+                        acc[o][1] = 0.f;
+                        if ((pos & 0xf00) == 0) {
+                            acc[o][3] = __fadd_rn(acc[o][3], acc[o][2]);
+                            acc[o][2] = 0.f;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < FT_MAXREG; ++q) {
+                if (q >= pos && q < nvec) {
+                    const float d0 = __fsub_rn(b0[32 * q], a[q]), d1 = __fsub_rn(b1[32 * q], a[q]);
+                    acc[0][0] = __fadd_rn(acc[0][0], P2 ? __fsqrt_rn(__fmul_rn(d0, d0)) : fabsf(d0));
+                    acc[1][0] = __fadd_rn(acc[1][0], P2 ? __fsqrt_rn(__fmul_rn(d1, d1)) : fabsf(d1));
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+                float t = __fadd_rn(acc[o][0], acc[o][1]);
+                t = __fadd_rn(t, acc[o][2]);
+                t = __fadd_rn(t, acc[o][3]);
+                const float s = torch_tail(t);
+                const int j = j0 + jj + o;
+                if (lane == 0 && j < ld) out[(size_t)i * ld + j] = j < n ? s : 0.0f;
+            }
+        }
+    }
+}
+
+__global__ void feature_finite_kernel(const float *__restrict__ x, size_t count, int *bad) {
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x)
+        if (!isfinite(x[e])) atomicExch(bad, 1);
+}
+
 int feature_distance_build(adsel_handle *h, const float *feats_host, int32_t n, int32_t dim, int32_t p) {
     ADSEL_REQUIRE(feats_host && n > 0 && dim > 0, "adsel_feature_distance_build: null/empty argument");
     ADSEL_REQUIRE(p == 1 || p == 2, "adsel_feature_distance_build: p must be 1 or 2 (feature_selector.py:47)");
@@ -108,9 +215,33 @@ int feature_distance_build(adsel_handle *h, const float *feats_host, int32_t n, 
     h->pd_ld = ld;
     h->pd_col0 = 0;
     h->pd_cols = n;
+    // NaN / inf features would break the ordered-bit-pattern view the greedy loop takes of the map: refused
+    ADSEL_TRY(h->d_result.reserve(8));
+    ADSEL_CUDA(cudaMemsetAsync(h->d_result.p, 0, sizeof(int), h->stream));
+    feature_finite_kernel<<<h->num_sms * 4, 256, 0, h->stream>>>(h->feat.p, (size_t)n * dim, reinterpret_cast<int *>(h->d_result.p));
+    int bad = 0;
+    ADSEL_CUDA(cudaMemcpyAsync(&bad, h->d_result.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    ADSEL_CUDA(cudaStreamSynchronize(h->stream));
+    h->launches += 1;
+    ADSEL_REQUIRE(bad == 0, "adsel_feature_distance_build: the features contain NaN or inf");
     ADSEL_TRY(begin_stage(h));
-    dim3 grid((n + FD_TILE - 1) / FD_TILE, (n + FD_TILE - 1) / FD_TILE);
-    feature_l1_kernel<<<grid, FD_THREADS, 0, h->stream>>>(h->feat.p, n, dim, p == 2 ? 1 : 0, reinterpret_cast<float *>(h->d2_p), ld);
+    const bool exact = dim % 32 == 0 && dim <= 32 * FT_MAXREG && !getenv("ADSEL_FEATDIST_INDEX_ORDER");
+    if (exact) {   // torch's summation order: the map is the reference's, bit for bit
+        int rows = FT_ROWS;
+        while ((size_t)rows * dim * sizeof(float) > 220 * 1024) rows -= 2;
+        dim3 grid((n + rows - 1) / rows, (n + rows - 1) / rows);
+        const size_t smem = sizeof(float) * rows * dim;
+        if (p == 2) {
+            ADSEL_CUDA(cudaFuncSetAttribute(feature_l1_torch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            feature_l1_torch_kernel<1><<<grid, FT_THREADS, smem, h->stream>>>(h->feat.p, n, dim, reinterpret_cast<float *>(h->d2_p), ld, rows);
+        } else {
+            ADSEL_CUDA(cudaFuncSetAttribute(feature_l1_torch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            feature_l1_torch_kernel<0><<<grid, FT_THREADS, smem, h->stream>>>(h->feat.p, n, dim, reinterpret_cast<float *>(h->d2_p), ld, rows);
+        }
+    } else {
+        dim3 grid((n + FD_TILE - 1) / FD_TILE, (n + FD_TILE - 1) / FD_TILE);
+        feature_l1_kernel<<<grid, FD_THREADS, 0, h->stream>>>(h->feat.p, n, dim, p == 2 ? 1 : 0, reinterpret_cast<float *>(h->d2_p), ld);
+    }
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());
     ADSEL_TRY(end_stage(h, 6));

@@ -89,6 +89,9 @@ _SIGNATURES = {
                                                      ctypes.c_int32]),
     "adsel_select_sharded_end": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                                 ctypes.POINTER(ctypes.c_double)]),
+    "adsel_select_fused_feature": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), ctypes.c_double, ctypes.c_int32, _P, ctypes.c_int32,
+                                                  ctypes.c_int32, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                                  ctypes.POINTER(ctypes.c_double)]),
     "adsel_feature_distance_build": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "adsel_pairdist_build_sharded": (ctypes.c_int, [_P]),
     "adsel_select_dense_prepare": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32]),
@@ -347,7 +350,8 @@ class Handle:
         _check(load().adsel_get_counters(self._h, _ptr(c)))
         return dict(zip(("launches", "steps", "list_entries", "nnz"), c.tolist()))
 
-    GREEDY_KERNELS = ("greedy_select_kernel", "greedy_fast_kernel", "greedy_resident_kernel", "greedy_lazy_kernel")
+    GREEDY_KERNELS = ("greedy_select_kernel", "greedy_fast_kernel", "greedy_resident_kernel", "greedy_lazy_kernel",
+                      "fused_feature_kernel")
 
     def greedy_info(self):
         """Kernel of the last selection and its cluster size (csrc/greedy.cu, csrc/lazy.cu)."""
@@ -412,6 +416,26 @@ class Handle:
         assert feats.ndim == 2
         self.pd_n = self.pd_cols = feats.shape[0]
         _check(load().adsel_feature_distance_build(self._h, _ptr(feats), feats.shape[0], feats.shape[1], int(p)))
+
+    def select_fused_feature(self, *, temporal, aggregate="sum", lambda_t=1.0, lambda_f=1.0, seed_spatial_only=False,
+                             max_temporal=0.0, cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=0.0, forbid_sampled=False,
+                             sampled=(), first_index=-1, out_cap=None):
+        """Greedy loop of SpatialFeatureSelector (``temporal=False``, ``seed_spatial_only=True``) /
+        SpatialTemporalFeatureSelector (``temporal=True``) on the built graph and feature map (csrc/fused.cu)."""
+        p = SelectParams(SPATIAL["geodesic"], int(bool(temporal)), NORMALIZE["exp"], AGGREGATE[aggregate], float(lambda_t), 0.0,
+                         float(max_temporal), float(cost_b), float(cost_f), float(cost_start), float(budget),
+                         int(bool(forbid_sampled)), 0)
+        sampled = np.ascontiguousarray(sampled, dtype=np.int32)
+        out_cap = self.n if out_cap is None else out_cap
+        out = np.empty(out_cap, dtype=np.int32)
+        m, cost = ctypes.c_int32(0), ctypes.c_double(0.0)
+        status = load().adsel_select_fused_feature(self._h, ctypes.byref(p), float(lambda_f), int(bool(seed_spatial_only)),
+                                                   _ptr(sampled) if len(sampled) else None, len(sampled), int(first_index),
+                                                   _ptr(out), out_cap, ctypes.byref(m), ctypes.byref(cost))
+        if status == ERR_RESELECTED:
+            raise AssertionError(load().adsel_last_error().decode())
+        _check(status)
+        return out[: m.value].tolist(), cost.value
 
     def feature_distance_rows(self, row0, rows):
         return self.pairdist_get_rows(row0, rows).view(np.float32)

@@ -216,6 +216,16 @@ int adsel_select_dense(adsel_handle *h, const adsel_select_params *p, const int3
  *      replaces the descriptor distance matrix of the handle: adsel_pairdist_get_rows returns the float32 bit
  *      patterns (non-negative floats order like their int32 bits) and adsel_select_dense runs the greedy loop. */
 int adsel_feature_distance_build(adsel_handle *h, const float *feats, int32_t n, int32_t dim, int32_t p);
+/* Greedy loop of the selectors that add the feature term to the geodesic (and temporal) terms:
+ * det3d/selectors/spatial_feature_selector.py:186-237 (p->temporal = 0, p->aggregate = sum | min | max, seed_spatial_only = 1:
+ * the min-distance vector is seeded from the normalised SPATIAL rows only, :201-209) and
+ * spatial_temporal_feature_selector.py:208-258 (p->temporal = 1, sum with p->lambda_t and lambda_f, seed_spatial_only = 0).
+ * p->spatial must be geodesic, p->normalize exp; the feature term is normalised with numpy's float32 exp and, in the
+ * three-term sum, multiplied by float32(lambda_f) in float32, as numpy does.  Needs adsel_build_knn_graph and
+ * adsel_feature_distance_build (whose map is the reference's bit for bit when the feature dimension is a multiple of 32). */
+int adsel_select_fused_feature(adsel_handle *h, const adsel_select_params *p, double lambda_f, int32_t seed_spatial_only,
+                               const int32_t *sampled, int32_t n_sampled, int32_t first_index, int32_t *out_idx,
+                               int32_t out_cap, int32_t *out_m, double *out_cost);
 
 /* ---- the BEV / dense path sharded over ranks (after adsel_comm_init with dim = cells, n = pool frames) ----
  * adsel_bev_build then stores each frame's descriptor into EVERY rank's arena (the all-gather is fused into

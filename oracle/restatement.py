@@ -314,6 +314,53 @@ def select(kind, infos, logs, buffer, budget, first_index, cost_b=0.04, cost_f=0
 # feature-distance selector (det3d/selectors/feature_selector.py:87-172), restated with the reference's own
 # torch expressions (float32 on the CPU), rows computed lazily
 # --------------------------------------------------------------------------------------------
+def torch_sum_f32(x: np.ndarray) -> np.float32:
+    """``torch.from_numpy(x).sum()`` of a contiguous float32 vector on the CPU, restated: the vectorised cascade sum of
+    aten/src/ATen/native/cpu/SumKernel.cpp (``vectorized_inner_sum`` -> ``row_sum`` -> ``multi_row_sum``) with 8 float
+    lanes, 4 interleaved accumulators and four cascade levels of 16 vectors; the scalar tail is added before the 8 lanes.
+    Pinned bit for bit against torch 2.11 for lengths 16 .. 8192 (tests/test_oracle_feature.py); csrc/featdist.cu follows
+    the same order on the device."""
+    import math
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    W, ILP, LEVELS = 8, 4, 4
+    n = len(x)
+    vec_size = n // W
+    vecs = x[: vec_size * W].reshape(vec_size, W)
+    size_ilp = vec_size // ILP
+    ceil_log2 = 0 if size_ilp <= 1 else math.ceil(math.log2(size_ilp))
+    level_power = max(4, ceil_log2 // LEVELS)
+    level_step, level_mask = 1 << level_power, (1 << level_power) - 1
+    acc = np.zeros((LEVELS, ILP, W), dtype=np.float32)
+    i = 0
+    while i + level_step <= size_ilp:
+        for _ in range(level_step):
+            for k in range(ILP):
+                acc[0, k] = acc[0, k] + vecs[i * ILP + k]
+            i += 1
+        for j in range(1, LEVELS):
+            acc[j] = acc[j] + acc[j - 1]
+            acc[j - 1] = 0
+            if (i & (level_mask << (j * level_power))) != 0:
+                break
+    while i < size_ilp:
+        for k in range(ILP):
+            acc[0, k] = acc[0, k] + vecs[i * ILP + k]
+        i += 1
+    for j in range(1, LEVELS):
+        acc[0] = acc[0] + acc[j]
+    part = acc[0].copy()
+    for v in range(size_ilp * ILP, vec_size):
+        part[0] = part[0] + vecs[v]
+    for k in range(1, ILP):
+        part[0] = part[0] + part[k]
+    s = np.float32(0)
+    for e in x[vec_size * W:]:
+        s = np.float32(s + e)
+    for k in range(W):
+        s = np.float32(s + part[0][k])
+    return s
+
+
 def feature_row(feats, i: int, p: int = 2) -> np.ndarray:
     """``distance_map[i]`` of feature_selector.py:96-101 as float32 numpy (``feats``: float32 [N, C] array)."""
     import torch

@@ -1,8 +1,9 @@
-"""GPU: feature-distance map (csrc/featdist.cu) and FeatureSelector against the reference.
+"""GPU: feature-distance map (csrc/featdist.cu), FeatureSelector and the fused feature selectors (csrc/fused.cu) against
+the reference.
 
-Tolerance: the map is float32; torch sums the 512 terms with a vectorised cascade whose order depends on the CPU,
-the kernel sums in index order, so rows agree to 1e-5 relative (north_star's fp32 tolerance), not bitwise.  The
-selection on the committed fixture is nevertheless identical to what the unmodified reference selected."""
+The map is float32.  For feature dimensions that are multiples of 32 (the reference's 512) the kernel follows torch's
+vectorised cascade sum and the map equals the reference's bit for bit; other dimensions are summed in index order and
+agree to 1e-5 relative (north_star's fp32 tolerance)."""
 import json
 import pickle
 
@@ -31,6 +32,50 @@ def test_feature_distance_rows_within_fp32_tolerance(n, dim, p):
         assert np.array_equal(got, got.T)                    # |a-b| == |b-a| term by term, same summation order
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("n,dim,p", [(130, 96, 2), (300, 512, 1), (300, 512, 2), (257, 32, 1), (150, 768, 2), (90, 1024, 1)])
+def test_feature_distance_rows_bit_for_bit_in_torchs_summation_order(n, dim, p):
+    feats = synthetic.synthetic_features(n, dim, seed=n + dim)
+    feats[n // 2] = feats[0]
+    h = native.Handle(0)
+    try:
+        h.feature_distance_build(feats, p)
+        got = h.feature_distance_rows(0, n)
+        ref = np.stack([R.feature_row(feats, i, p) for i in range(n)])       # torch itself
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+        with pytest.raises(native.NativeError):
+            bad = feats.copy()
+            bad[3, 5] = np.nan
+            h.feature_distance_build(bad, p)
+    finally:
+        h.close()
+
+
+def test_fused_feature_selectors_drop_in_select_like_the_reference(pools, tmp_path):
+    """SpatialFeatureSelector / SpatialTemporalFeatureSelector through the registry, 11 cases recorded from the UNMODIFIED
+    classes: sum / min / max, p = 1, other k and lambdas, chained rounds, a resumed buffer."""
+    import random
+    import torch
+    golden = load_golden("P2K_fused_feature.json")
+    pl = pools("P2K")
+    feats = synthetic.synthetic_features(golden["n_frames"], golden["dim"], golden["feature_seed"])
+    feat_path = str(tmp_path / "feature_pred.pt")
+    torch.save(torch.from_numpy(feats), feat_path)
+    for cid, case in golden["cases"].items():
+        buffer_file = str(tmp_path / f"buffer_{cid}.json")
+        json.dump(case["initial_buffer"], open(buffer_file, "w"))
+        res = {}
+        for budget in case["rounds"]:
+            random.seed(3407)
+            sel = build_selector(dict(type=case["selector"], budget=budget, buffer_file=buffer_file,
+                                      infos_origin=pl["paths"]["infos"], buffer_path=feat_path, logs_file=pl["paths"]["logs"],
+                                      distance_store_file=str(tmp_path / "unused.npy"), pred=False, **case["kwargs"]))
+            sel.select_samples(local_rank=0)
+            sel.dump_file()
+            res.update(sel.get_selected_samples())
+        assert res == case["selected_index"], cid
+    assert len(golden["cases"]) == 11
 
 
 def test_p2_extreme_magnitudes_follow_the_literal_expression():

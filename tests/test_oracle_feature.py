@@ -45,3 +45,18 @@ def test_fused_feature_restatement_reproduces_the_reference(pools):
             assert sel == case["selected_index"][key], cid
             buffer[key] = sel
     assert len(golden["cases"]) == 11
+
+
+def test_torch_sum_restatement_is_torchs_sum_bit_for_bit():
+    """The summation order csrc/featdist.cu follows (oracle/restatement.py::torch_sum_f32) IS torch's CPU ``.sum(1)`` of a
+    contiguous float32 matrix: lengths below / at / above one cascade block, multiples of 32 and ragged tails."""
+    import torch
+    rng = np.random.default_rng(5)
+    for dim in (16, 24, 32, 100, 512, 520, 768, 1000, 1024, 2048, 8192):
+        feats = rng.standard_normal((12, dim)).astype(np.float32)
+        t = torch.from_numpy(feats)
+        for p in (1, 2):
+            want = (torch.abs(t - t[3]).sum(1) if p == 1 else torch.sqrt((t - t[3]) ** 2).sum(1)).numpy()
+            terms = np.abs(feats - feats[3]) if p == 1 else np.sqrt((feats - feats[3]) ** 2)
+            got = np.array([R.torch_sum_f32(row) for row in terms], dtype=np.float32)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (dim, p)
