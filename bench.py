@@ -377,6 +377,32 @@ def bev_extras(native, device, n_frames, n_boxes, first, peaks, reps=3, batch=20
     return out
 
 
+def feature_extras(native, device, n, dim=512, reps=2):
+    """The N x N float32 feature-distance map of the feature selectors (feature_selector.py:87-109) at the pool's size, on
+    synthetic features: SIMT FP32 work (one subtract and one add per term, no FMA to fuse), so the bound is the FP32 pipe."""
+    import numpy as np
+    import torch
+    from adsel_b200 import synthetic
+    feats = synthetic.synthetic_features(n, dim, 11)
+    h = native.Handle(device)
+    try:
+        ms = []
+        for rep in range(reps + 1):
+            h.feature_distance_build(feats, 2)
+            ms.append(h.stage_ms()["pairdist"])
+        ms = sum(ms[1:]) / reps
+    finally:
+        h.close()
+    props = torch.cuda.get_device_properties(device)
+    peak = props.multi_processor_count * 128 * 1.965e9 / 1e12          # FP32 lane-operations per second (adds/subs; an FMA would count 2)
+    ops = 2.0 * n * n * dim / (ms * 1e-3) / 1e12
+    return {"feature_distance_map": {
+        "n": n, "dim": dim, "ms": ms, "summation_order": "torch's vectorised cascade sum (bit-exact rows)",
+        "roofline": {"bound": "fp32", "kernel": "feature_l1_torch_kernel", "achieved": ops, "peak": peak, "unit": "T lane-op/s",
+                     "frac": ops / peak, "traffic": None,
+                     "peak_source": "SMs x 128 FP32 lanes x 1.965 GHz (non-FMA operations)"}}}
+
+
 def bev_extras_sharded(world_engine, n_frames, n_boxes, first, peaks, max_over_ranks, barrier, reps=2, batch=1024,
                        pts_per_frame=300_000, budget=1200, key="bev_sharded_budget1200"):
     """BASELINE.json config 3 shape on N ranks: every rank histograms its own slice of the 28,130 frames x ~300k
@@ -679,6 +705,7 @@ def run_b200_arm(args):
                      "bf16_source": ("measured burst (MEASURED_PEAKS.json bf16_tflops): kernel timed alone"
                                      if pk else "fallback (B200_PROFILING.md)")}
             extras = bev_extras(native, local_rank, n, n_boxes, first, peaks)
+            extras.update(feature_extras(native, local_rank, n))
         if strong is not None:
             extras = {"strong_p28k": strong}
             if not args.no_bev:

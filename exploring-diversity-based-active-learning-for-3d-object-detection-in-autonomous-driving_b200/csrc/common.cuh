@@ -186,6 +186,7 @@ struct adsel_handle {
     int32_t *knn_idx_p = nullptr;                // kNN table in use: own buffers or the arena's (sharded build)
     double *knn_dist_p = nullptr;
     // pending sharded selection (begin/end split so several ranks can be driven from one host thread)
+    bool sampled_is_device = false;              // adsel_select_device: the `sampled` argument is a device pointer
     bool pending = false;
     bool pending_replicated = false;             // the pending selection runs the whole greedy loop on this rank
     int32_t pending_cap = 0;

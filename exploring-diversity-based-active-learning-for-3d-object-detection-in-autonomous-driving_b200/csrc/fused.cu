@@ -307,7 +307,7 @@ int fused_feature_select(adsel_handle *h, const adsel_select_params *p, double l
         a.out = h->d_out.p;
         a.result = h->d_result.p;
         if (n_sampled > 0)
-            ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyHostToDevice, h->stream));
+            ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyDefault, h->stream));   // host or device list
         ADSEL_CUDA(cudaMemsetAsync(h->d_result.p, 0, sizeof(double) * 8, h->stream));
         fused_feature_kernel<<<1, FUSED_NT, 0, h->stream>>>(a);
         h->launches += 1;

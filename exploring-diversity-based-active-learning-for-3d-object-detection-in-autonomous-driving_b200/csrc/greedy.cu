@@ -1735,7 +1735,8 @@ int validate_select(adsel_handle *h, const adsel_select_params *p, const int32_t
                   "adsel_select: lambda_t must be >= 0 (row maximum argument, DESIGN.md §5)");
     ADSEL_REQUIRE(n_sampled >= 0 && (n_sampled == 0 || sampled), "adsel_select: bad sampled list");
     ADSEL_REQUIRE(n_sampled > 0 || (first_index >= 0 && first_index < h->n), "adsel_select: first_index out of range");
-    for (int i = 0; i < n_sampled; ++i) ADSEL_REQUIRE(sampled[i] >= 0 && sampled[i] < h->n, "adsel_select: sampled index out of range");
+    if (!h->sampled_is_device)   // (a device-resident list is range-checked by a kernel in adsel_select_device)
+        for (int i = 0; i < n_sampled; ++i) ADSEL_REQUIRE(sampled[i] >= 0 && sampled[i] < h->n, "adsel_select: sampled index out of range");
     ADSEL_REQUIRE((h->n + BLK - 1) / BLK <= MAX_BLKS, "adsel_select: pool larger than 1,254,400 frames");
     if (p->normalize == ADSEL_NORM_LINEAR) {
         ADSEL_REQUIRE(p->spatial != ADSEL_SPATIAL_GEODESIC || p->max_spatial > 0.0, "adsel_select: linear needs max_spatial");
@@ -1851,7 +1852,7 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
     a.prof = getenv("ADSEL_GREEDY_PROFILE") ? greedy_prof_ptr() : nullptr;
 
     if (n_sampled > 0)
-        ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyHostToDevice, h->stream));
+        ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyDefault, h->stream));   // host or device list
     ADSEL_CUDA(cudaMemsetAsync(h->d_result.p, 0, sizeof(double) * 8, h->stream));
     a.sel_words = n <= 524288 ? (n + 31) / 32 : 0;
     a.far_bits = far_bits;

@@ -292,7 +292,7 @@ int lazy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sa
     a.sc.q1 = h->sc_q1.p;
     a.sc.touched = h->sc_touched.p;
     if (n_sampled > 0)
-        ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyHostToDevice, h->stream));
+        ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyDefault, h->stream));   // host or device list
     ADSEL_CUDA(cudaMemsetAsync(h->d_result.p, 0, sizeof(double) * 8, h->stream));
     if (p->temporal) {
         temporal_lut_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->tlut.p, n, p->normalize, p->max_temporal);

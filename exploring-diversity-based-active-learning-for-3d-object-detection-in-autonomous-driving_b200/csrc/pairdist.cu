@@ -704,6 +704,162 @@ __global__ void __launch_bounds__(DG_THREADS, 1) dense_greedy_kernel(const Dense
     }
 }
 
+
+// ---- dense greedy over a thread-block cluster (one GPU) -------------------------------------------------------
+// The single-CTA loop above streams a whole row (4 N bytes: 112 KB at 28,130 frames) through ONE SM per step: 3.4 us per
+// step, 33 GB/s.  Here the columns are cut into DC_CTAS slices, one per CTA of a cluster (fps in registers, DC_ITEMS
+// columns per thread): a step is one wave of independent row loads per CTA, a local arg-max (two REDUX), and an exchange
+// of the CTAs' (value, index) maxima through distributed shared memory behind the hardware cluster barrier; every CTA
+// does the cost bookkeeping redundantly (identical values), CTA 0 writes the results.
+constexpr int DC_CTAS = 8, DC_THREADS = 512;
+
+template <int ITEMS>
+__global__ void __launch_bounds__(DC_THREADS, 1) dense_cluster_kernel(const DenseArgs a) {
+    __shared__ BestI warp_res[DC_THREADS / 32];
+    __shared__ int4 xrec[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int per = (a.n + DC_CTAS - 1) / DC_CTAS;
+    const int c_lo = min((int)crank * per, a.n), c_len = min(per, a.n - c_lo);
+    const bool writer = crank == 0 && tid == 0;
+    int fps_reg[ITEMS];
+    if (a.forbid_sampled)
+        for (int t = tid; t < a.n_sampled; t += DC_THREADS) a.is_selected[a.sampled[t]] = 1;   // every CTA writes the same flags
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int j = tid + DC_THREADS * i;
+        int v = 0x7fffffff;
+        if (j < c_len)
+            for (int t = 0; t < a.n_sampled; ++t) v = min(v, a.d2[(size_t)a.sampled[t] * a.ld + c_lo + j]);
+        fps_reg[i] = v;
+    }
+    double cost = a.cost_start;   // bookkeeping replicated in every thread of every CTA
+    int m = 0, cur = -1, status = 0, offending = -1;
+    if (a.n_sampled == 0) {       // empty buffer: the caller's random.choice, costed up front (spatial_selector.py:112-117)
+        cur = a.first_index;
+        if (writer) a.out[0] = cur;
+        if (tid == 0) a.is_selected[cur] = 1;
+        m = 1;
+        cost = __dadd_rn(cost, a.cost_f);
+        cost = __dadd_rn(cost, __dmul_rn((double)a.n_boxes[cur], a.cost_b));
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    long long steps = 0;
+    bool seeding = a.n_sampled > 0;
+    while (true) {
+        const int32_t *row = seeding ? nullptr : a.d2 + (size_t)cur * a.ld + c_lo;
+        BestI x{-1, 0x7fffffff};
+        int r[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int j = tid + DC_THREADS * i;
+            r[i] = (row && j < c_len) ? __ldcs(row + j) : 0x7fffffff;
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int j = tid + DC_THREADS * i;
+            fps_reg[i] = min(fps_reg[i], r[i]);
+            if (j < c_len && fps_reg[i] > x.v) {      // ascending j per thread: strict '>' keeps the first maximum
+                x.v = fps_reg[i];
+                x.i = a.col0 + c_lo + j;
+            }
+        }
+        x = warp_best_i(x);
+        if (lane == 0) warp_res[wid] = x;
+        __syncthreads();
+        const int xp = (int)(steps & 1);
+        if (wid == 0) {
+            const BestI y = warp_best_i(lane < DC_THREADS / 32 ? warp_res[lane] : BestI{-1, 0x7fffffff});
+            if (lane == 0) xrec[xp] = make_int4(y.v, y.i, 0, 0);
+        }
+        // publish, hardware cluster barrier, read every CTA's record through distributed shared memory
+        asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        BestI z{-1, 0x7fffffff};
+        if (lane < DC_CTAS) {
+            unsigned src;
+            int4 rec;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(src) : "r"((unsigned)__cvta_generic_to_shared(&xrec[xp])), "r"(lane));
+            asm volatile("ld.shared::cluster.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(rec.x), "=r"(rec.y), "=r"(rec.z), "=r"(rec.w) : "r"(src) : "memory");
+            z = BestI{rec.x, rec.y};
+        }
+        z = warp_best_i(z);   // every warp of every CTA holds the winner
+        ++steps;
+        const int nxt = z.i;
+        if (nxt < 0 || nxt >= a.col0 + a.n) {
+            status = ADSEL_ERR_INVALID;
+            break;
+        }
+        const double box_cost = __dmul_rn((double)a.n_boxes[nxt], a.cost_b);
+        if (seeding) {
+            seeding = false;
+            if (writer) a.out[0] = nxt;
+            if (tid == 0) a.is_selected[nxt] = 1;
+            m = 1;
+            cost = __dadd_rn(cost, a.cost_f);
+            cost = __dadd_rn(cost, box_cost);
+            cur = nxt;
+            continue;
+        }
+        if (__ldcg(&a.is_selected[nxt])) {   // flags of earlier steps: written before at least one cluster barrier
+            status = ADSEL_ERR_RESELECTED;
+            offending = nxt;
+            break;
+        }
+        cost = __dadd_rn(cost, a.cost_f);
+        cost = __dadd_rn(cost, box_cost);
+        if (cost > a.budget) break;
+        if (m >= a.out_cap) {
+            status = ADSEL_ERR_CAPACITY;
+            break;
+        }
+        if (writer) a.out[m] = nxt;
+        if (tid == 0) __stcg(&a.is_selected[nxt], (unsigned char)1);
+        m += 1;
+        cur = nxt;
+    }
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int j = tid + DC_THREADS * i;
+        if (j < c_len) a.fps[c_lo + j] = fps_reg[i];
+    }
+    if (writer) {
+        a.result[0] = cost;
+        a.result[1] = (double)status;
+        a.result[2] = (double)m;
+        a.result[3] = (double)steps;
+        a.result[4] = (double)offending;
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int ITEMS>
+static cudaError_t launch_dense_cluster(adsel_handle *h, const DenseArgs &a) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(DC_CTAS, 1, 1);
+    cfg.blockDim = dim3(DC_THREADS, 1, 1);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = DC_CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, dense_cluster_kernel<ITEMS>, a);
+}
+
+// true: launched.  Pools of up to 8 CTAs x 512 threads x 16 columns = 65,536 frames; ADSEL_DENSE_CLUSTER=0 keeps the single CTA.
+static bool try_dense_cluster(adsel_handle *h, const DenseArgs &a, cudaError_t *err) {
+    const char *e = getenv("ADSEL_DENSE_CLUSTER");
+    if (e && atoi(e) == 0) return false;
+    const int per_thread = (a.n + DC_CTAS * DC_THREADS - 1) / (DC_CTAS * DC_THREADS);
+    if (per_thread > 16 || a.n < 2048) return false;
+    *err = per_thread <= 4 ? launch_dense_cluster<4>(h, a) : per_thread <= 8 ? launch_dense_cluster<8>(h, a) : launch_dense_cluster<16>(h, a);
+    return true;
+}
+
 static int dense_validate(adsel_handle *h, const adsel_select_params *p, const int32_t *n_boxes_host, const int32_t *sampled,
                           int32_t n_sampled, int32_t first_index, int32_t out_cap) {
     ADSEL_REQUIRE(h->pd_n > 0, "adsel_select_dense: call adsel_pairdist_build first");
@@ -774,7 +930,9 @@ static int dense_enqueue(adsel_handle *h, const adsel_select_params *p, const in
         ADSEL_TRY(comm_view(h, &view));
         launch_dense<true>(h, a, view);
     } else {
-        launch_dense<false>(h, a, view);
+        cudaError_t cerr = cudaSuccess;
+        if (try_dense_cluster(h, a, &cerr)) ADSEL_CUDA(cerr);
+        else launch_dense<false>(h, a, view);
     }
     h->launches += 1;
     ADSEL_CUDA(cudaGetLastError());

@@ -54,6 +54,13 @@ _SIGNATURES = {
     "adsel_timer_start": (ctypes.c_int, [_P]),
     "adsel_timer_stop": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
     "adsel_set_pool": (ctypes.c_int, [_P, ctypes.c_int32, _P, _P, _P]),
+    "adsel_set_pool_device": (ctypes.c_int, [_P, ctypes.c_int32, _P, _P, _P]),
+    "adsel_select_device": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), _P, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)]),
+    "adsel_copy_selected_device": (ctypes.c_int, [_P, _P, ctypes.c_int32]),
+    "adsel_bev_set_points_device": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32]),
+    "adsel_bev_descriptors_device": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(_P), ctypes.POINTER(_P),
+                                                    ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]),
     "adsel_build_knn_graph": (ctypes.c_int, [_P, ctypes.c_int32]),
     "adsel_get_knn": (ctypes.c_int, [_P, _P, _P]),
     "adsel_get_csr": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ctypes.c_int64)]),
@@ -106,6 +113,7 @@ _SIGNATURES = {
     "adsel_bev_get_descriptors": (ctypes.c_int, [_P, _P, _P, _P, ctypes.POINTER(ctypes.c_int32)]),
 }
 _lib = None
+HOST_INPUT_BYTES = 0        # bytes of caller arrays handed to the library from HOST memory (tests: the device-pointer entry points add none)
 
 
 def library_path() -> str:
@@ -203,7 +211,32 @@ class Handle:
         n_boxes = np.ascontiguousarray(n_boxes, dtype=np.int32)
         assert loc_xy.ndim == 2 and loc_xy.shape[1] == 2 and len(group_id) == len(loc_xy) == len(n_boxes)
         self.n = len(loc_xy)
+        global HOST_INPUT_BYTES
+        HOST_INPUT_BYTES += loc_xy.nbytes + group_id.nbytes + n_boxes.nbytes
         _check(load().adsel_set_pool(self._h, self.n, _ptr(loc_xy), _ptr(group_id), _ptr(n_boxes)))
+
+    def set_pool_device(self, n, loc_ptr, group_ptr, boxes_ptr):
+        """``adsel_set_pool`` from DEVICE pointers (float64 [n,2], int32 [n], int32 [n] on this handle's device)."""
+        self.n = int(n)
+        _check(load().adsel_set_pool_device(self._h, self.n, _P(loc_ptr), _P(group_ptr), _P(boxes_ptr)))
+
+    def select_device(self, sampled_ptr, n_sampled, *, spatial, temporal, normalize, aggregate="sum", lambda_t=1.0,
+                      max_spatial=0.0, max_temporal=0.0, cost_b=0.04, cost_f=0.12, cost_start=0.0, budget=0.0,
+                      forbid_sampled=False, first_index=-1):
+        """``adsel_select`` with the list of already-selected frames read from a DEVICE pointer (int32); returns
+        ``(m, cost)``: the m selected indices stay on the device (``copy_selected_device``)."""
+        p = self._select_params(spatial, temporal, normalize, aggregate, lambda_t, max_spatial, max_temporal, cost_b, cost_f,
+                                cost_start, budget, forbid_sampled)
+        m, cost = ctypes.c_int32(0), ctypes.c_double(0.0)
+        status = load().adsel_select_device(self._h, ctypes.byref(p), _P(sampled_ptr) if n_sampled else None, int(n_sampled),
+                                            int(first_index), ctypes.byref(m), ctypes.byref(cost))
+        if status == ERR_RESELECTED:
+            raise AssertionError(load().adsel_last_error().decode())
+        _check(status)
+        return m.value, cost.value
+
+    def copy_selected_device(self, dst_ptr, m):
+        _check(load().adsel_copy_selected_device(self._h, _P(dst_ptr), int(m)))
 
     def build_knn_graph(self, k: int = 8):
         self.k = k
@@ -362,11 +395,27 @@ class Handle:
     # -- BEV descriptors ------------------------------------------------------------------------
     NUSC_RANGE = (-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)     # examples/active/cbgs_spatial_temporal.py:280
 
+    def bev_set_points_device(self, points_ptr, frame_off):
+        """``adsel_bev_set_points`` with the float32 [P,5] points read from a DEVICE pointer (frame offsets: host metadata)."""
+        frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
+        self.bev_batch, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
+        _check(load().adsel_bev_set_points_device(self._h, _P(points_ptr), _ptr(frame_off), self.bev_batch))
+
+    def bev_descriptors_device(self):
+        """Device pointers ``(counts, levels_bf16, norm2, frames, cells)`` of the descriptors of the last ``bev_build``."""
+        c, l, q = _P(), _P(), _P()
+        frames, cells = ctypes.c_int32(0), ctypes.c_int32(0)
+        _check(load().adsel_bev_descriptors_device(self._h, ctypes.byref(c), ctypes.byref(l), ctypes.byref(q),
+                                                   ctypes.byref(frames), ctypes.byref(cells)))
+        return c.value, l.value, q.value, frames.value, cells.value
+
     def bev_set_points(self, points, frame_off):
         points = np.ascontiguousarray(points, dtype=np.float32)
         frame_off = np.ascontiguousarray(frame_off, dtype=np.int64)
         assert points.ndim == 2 and points.shape[1] == 5 and frame_off[-1] == len(points)
         self.bev_batch, self.bev_points = len(frame_off) - 1, int(frame_off[-1])
+        global HOST_INPUT_BYTES
+        HOST_INPUT_BYTES += points.nbytes
         _check(load().adsel_bev_set_points(self._h, _ptr(points), _ptr(frame_off), self.bev_batch))
 
     def bev_generate(self, frame_off, n_sweeps=10, seed=20221107, first_frame=0):

@@ -10,11 +10,13 @@ namespace:
   torch.ops.adsel.bev_descriptors(points, frame_off, point_range, voxel) -> (counts, levels, norm2)
       adsel_bev_set_points + adsel_bev_build (binning of det3d/ops/point_cloud/bev_ops.py:27-53)
 
-The library's ABI takes HOST arrays (that is what the reference's selectors have), so tensor arguments on any
-device are brought to the host first; results are returned on the device of the first tensor argument.  The
-ops are registered with fake (meta) kernels, so they trace under ``torch.compile`` / ``FakeTensorMode`` as opaque
-calls with a data-dependent output length.  There is no CPU kernel: without the CUDA library or a device the call
-raises ``native.NativeError``.
+CUDA tensors stay where they are: the ops hand their ``data_ptr()`` to the device-pointer entry points of the C ABI
+(``adsel_set_pool_device``, ``adsel_select_device``, ``adsel_bev_set_points_device``; validation, bounding box and the
+frames-by-group table are computed by kernels) and the results are copied device-to-device into the returned tensors;
+only scalars (how many frames were selected, the 64-byte pool summary) cross to the host.  CPU tensors go through the
+host-array ABI, as the reference's selectors would.  The ops are registered with fake (meta) kernels, so they trace
+under ``torch.compile`` / ``FakeTensorMode`` as opaque calls with a data-dependent output length.  There is no CPU
+kernel: without the CUDA library or a device the call raises ``native.NativeError``.
 
 Importing this module registers the ops (idempotent); the package does not import it on its own, so the ctypes
 path has no torch dependency.
@@ -49,22 +51,38 @@ def select_frames(loc_xy: torch.Tensor, group_id: torch.Tensor, n_boxes: torch.T
     max_temporal: the reference's ``max_temporal_distance`` (only read by normalize="linear")."""
     if spatial not in native.SPATIAL or normalize not in native.NORMALIZE or aggregate not in native.AGGREGATE:
         raise ValueError(f"adsel::select_frames: unknown spatial/normalize/aggregate {spatial!r}/{normalize!r}/{aggregate!r}")
-    loc = _host(loc_xy, np.float64)
-    if loc.ndim != 2 or loc.shape[1] != 2:
+    if loc_xy.ndim != 2 or loc_xy.shape[1] != 2:
         raise ValueError("adsel::select_frames: loc_xy must be [n, 2]")
+    on_device = loc_xy.is_cuda
+    if on_device:
+        device = loc_xy.device.index
+        torch.cuda.current_stream(loc_xy.device).synchronize()      # the library reads the tensors on its own stream
+        loc_d = loc_xy.detach().to(torch.float64).contiguous()
+        grp_d = group_id.detach().to(device=loc_xy.device, dtype=torch.int32).contiguous()
+        box_d = n_boxes.detach().to(device=loc_xy.device, dtype=torch.int32).contiguous()
+        smp_d = sampled.detach().to(device=loc_xy.device, dtype=torch.int32).contiguous()
+        torch.cuda.current_stream(loc_xy.device).synchronize()
     engine = sharded.make_engine(device)
     try:
-        engine.set_pool(loc, _host(group_id, np.int32), _host(n_boxes, np.int32))
+        if on_device and hasattr(engine, "set_pool_device"):
+            engine.set_pool_device(loc_d.shape[0], loc_d.data_ptr(), grp_d.data_ptr(), box_d.data_ptr())
+        else:
+            on_device = False
+            engine.set_pool(_host(loc_xy, np.float64), _host(group_id, np.int32), _host(n_boxes, np.int32))
         max_spatial = 0.0
         if spatial == "geodesic":
             engine.build_knn_graph(k)
             if normalize == "linear":
                 max_spatial = engine.geodesic_max_finite()          # spatial_temporal_selector.py:139
-        selected, _ = engine.select(spatial=spatial, temporal=temporal, normalize=normalize, aggregate=aggregate,
-                                    lambda_t=lambda_t, max_spatial=max_spatial, max_temporal=max_temporal,
-                                    cost_b=cost_b, cost_f=cost_f, cost_start=cost_start, budget=budget,
-                                    forbid_sampled=forbid_sampled, sampled=_host(sampled, np.int32).tolist(),
-                                    first_index=first_index)
+        kw = dict(spatial=spatial, temporal=temporal, normalize=normalize, aggregate=aggregate, lambda_t=lambda_t,
+                  max_spatial=max_spatial, max_temporal=max_temporal, cost_b=cost_b, cost_f=cost_f, cost_start=cost_start,
+                  budget=budget, forbid_sampled=forbid_sampled, first_index=first_index)
+        if on_device:
+            m, _ = engine.select_device(smp_d.data_ptr(), smp_d.numel(), **kw)
+            out32 = torch.empty(m, dtype=torch.int32, device=loc_xy.device)
+            engine.copy_selected_device(out32.data_ptr(), m)
+            return out32.to(torch.int64)
+        selected, _ = engine.select(sampled=_host(sampled, np.int32).tolist(), **kw)
     finally:
         engine.close()
     return torch.tensor(selected, dtype=torch.int64, device=loc_xy.device)
@@ -86,17 +104,42 @@ def bev_descriptors(points: torch.Tensor, frame_off: torch.Tensor, point_range: 
     clipped to 31, norm2 int32 [F] = sum(level^2))."""
     if len(point_range) != 6 or len(voxel) != 3:
         raise ValueError("adsel::bev_descriptors: point_range needs 6 values, voxel 3")
-    pts, off = _host(points, np.float32), _host(frame_off, np.int64)
+    off = _host(frame_off, np.int64)                                # per-frame offsets: host metadata (a few KB)
+    dev = points.device
+    if points.is_cuda:
+        device = dev.index
     engine = native.Handle(device)                                  # descriptor build is per process, never sharded
     try:
-        engine.bev_set_points(pts, off)
+        if points.is_cuda:
+            pts_d = points.detach().to(torch.float32).contiguous()
+            torch.cuda.current_stream(dev).synchronize()
+            engine.bev_set_points_device(pts_d.data_ptr(), off)
+        else:
+            engine.bev_set_points(_host(points, np.float32), off)
         engine.bev_build(tuple(float(v) for v in point_range), tuple(float(v) for v in voxel))
+        if points.is_cuda:                                           # results copied device-to-device out of the handle
+            c_ptr, l_ptr, q_ptr, frames, cells = engine.bev_descriptors_device()
+            counts = _from_device_ptr(c_ptr, (frames, cells), torch.int32, dev).clone()
+            levels_bits = _from_device_ptr(l_ptr, (frames, cells), torch.int16, dev)
+            norm2 = _from_device_ptr(q_ptr, (frames,), torch.int32, dev).clone()
+            levels = (levels_bits.to(torch.int32) << 16).view(torch.float32).to(torch.int32)     # bf16 bit patterns of 0..31
+            torch.cuda.current_stream(dev).synchronize()
+            return counts, levels, norm2
         counts, levels_bf16, norm2 = engine.bev_get_descriptors()
     finally:
         engine.close()
     levels = (levels_bf16.astype(np.uint32) << 16).view(np.float32).astype(np.int32)     # bf16 bit patterns of 0..31
-    dev = points.device
     return (torch.from_numpy(counts).to(dev), torch.from_numpy(levels).to(dev), torch.from_numpy(norm2).to(dev))
+
+
+def _from_device_ptr(ptr: int, shape, dtype, device) -> torch.Tensor:
+    """A tensor VIEW of device memory owned by the library (``__cuda_array_interface__``); clone before the handle closes."""
+    typestr = {torch.int32: "<i4", torch.int16: "<i2", torch.float32: "<f4"}[dtype]
+
+    class _Mem:
+        __cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr, "data": (int(ptr), False),
+                                    "version": 3, "strides": None}
+    return torch.as_tensor(_Mem(), device=device)
 
 
 @bev_descriptors.register_fake

@@ -88,6 +88,21 @@ int adsel_set_pool(adsel_handle *h, int32_t n, const double *loc_xy, const int32
 
 /* ---- spatial graph (replaces cKDTree.query + dense scatter + dense->CSR,
  *      spatial_temporal_selector.py:93-101 and scipy's csgraph_from_dense |w|<=1e-8 drop) -------- */
+/* Device-pointer variants for callers whose arrays already live in HBM on the handle's device (torch.ops.adsel.*): the
+ * same semantics and errors as adsel_set_pool / adsel_select / adsel_bev_set_points, no host round trip of the inputs
+ * (validation, bounding box, group sizes and the frames-by-group table are computed by kernels; only a 64-byte summary
+ * and the result scalars cross to the host).  Pointers are read on the handle's stream: the caller orders its own
+ * producer streams before the call.  adsel_copy_selected_device copies the m indices of the last adsel_select* call. */
+int adsel_set_pool_device(adsel_handle *h, int32_t n, const double *d_loc_xy, const int32_t *d_group_id,
+                          const int32_t *d_n_boxes);
+int adsel_select_device(adsel_handle *h, const adsel_select_params *p, const int32_t *d_sampled, int32_t n_sampled,
+                        int32_t first_index, int32_t *out_m, double *out_cost);
+int adsel_copy_selected_device(adsel_handle *h, int32_t *d_dst, int32_t m);
+int adsel_bev_set_points_device(adsel_handle *h, const float *d_points, const int64_t *frame_off_host, int32_t n_frames);
+/* device pointers of the descriptors built by adsel_bev_build (owned by the handle, valid until the next build) */
+int adsel_bev_descriptors_device(adsel_handle *h, int32_t **d_counts, uint16_t **d_levels, int32_t **d_norm2, int32_t *frames,
+                                 int32_t *cells);
+
 int adsel_build_knn_graph(adsel_handle *h, int32_t k);
 /* test/inspection read-backs (host buffers): knn_idx [n,k+1] int32, knn_dist [n,k+1] float64 */
 int adsel_get_knn(adsel_handle *h, int32_t *knn_idx, double *knn_dist);
