@@ -723,9 +723,13 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dense_cluster_kernel(const Dens
     const int per = (a.n + DC_CTAS - 1) / DC_CTAS;
     const int c_lo = min((int)crank * per, a.n), c_len = min(per, a.n - c_lo);
     const bool writer = crank == 0 && tid == 0;
+    // Every CTA keeps its OWN copy of the selected-frame flags: with one shared copy a CTA that runs ahead would set the
+    // step's flag before a slower CTA has tested it, the slower one would see "already selected", leave the loop alone and
+    // the others would wait for it at the next cluster barrier for ever.
+    unsigned char *is_selected = a.is_selected + (size_t)crank * a.n;
     int fps_reg[ITEMS];
     if (a.forbid_sampled)
-        for (int t = tid; t < a.n_sampled; t += DC_THREADS) a.is_selected[a.sampled[t]] = 1;   // every CTA writes the same flags
+        for (int t = tid; t < a.n_sampled; t += DC_THREADS) is_selected[a.sampled[t]] = 1;
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const int j = tid + DC_THREADS * i;
@@ -739,7 +743,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dense_cluster_kernel(const Dens
     if (a.n_sampled == 0) {       // empty buffer: the caller's random.choice, costed up front (spatial_selector.py:112-117)
         cur = a.first_index;
         if (writer) a.out[0] = cur;
-        if (tid == 0) a.is_selected[cur] = 1;
+        if (tid == 0) is_selected[cur] = 1;
         m = 1;
         cost = __dadd_rn(cost, a.cost_f);
         cost = __dadd_rn(cost, __dmul_rn((double)a.n_boxes[cur], a.cost_b));
@@ -794,14 +798,14 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dense_cluster_kernel(const Dens
         if (seeding) {
             seeding = false;
             if (writer) a.out[0] = nxt;
-            if (tid == 0) a.is_selected[nxt] = 1;
+            if (tid == 0) is_selected[nxt] = 1;
             m = 1;
             cost = __dadd_rn(cost, a.cost_f);
             cost = __dadd_rn(cost, box_cost);
             cur = nxt;
             continue;
         }
-        if (__ldcg(&a.is_selected[nxt])) {   // flags of earlier steps: written before at least one cluster barrier
+        if (__ldcg(&is_selected[nxt])) {   // this CTA's flags of earlier steps: written before at least one barrier
             status = ADSEL_ERR_RESELECTED;
             offending = nxt;
             break;
@@ -814,7 +818,7 @@ __global__ void __launch_bounds__(DC_THREADS, 1) dense_cluster_kernel(const Dens
             break;
         }
         if (writer) a.out[m] = nxt;
-        if (tid == 0) __stcg(&a.is_selected[nxt], (unsigned char)1);
+        if (tid == 0) __stcg(&is_selected[nxt], (unsigned char)1);
         m += 1;
         cur = nxt;
     }
@@ -875,7 +879,7 @@ int dense_prepare(adsel_handle *h, int32_t n_sampled, int32_t out_cap) {
     ADSEL_REQUIRE(h->pd_n > 0, "adsel_select_dense: call adsel_pairdist_build first");
     ADSEL_TRY(h->pd_fps.reserve((size_t)h->pd_cols + 4));   // the generic greedy variant touches it in 16-byte words
     ADSEL_TRY(h->pd_boxes.reserve(h->pd_n));
-    ADSEL_TRY(h->is_selected.reserve(h->pd_n));
+    ADSEL_TRY(h->is_selected.reserve((size_t)h->pd_n * DC_CTAS));   // one private copy per CTA of the cluster variant
     ADSEL_TRY(h->d_sampled.reserve(n_sampled > 0 ? n_sampled : 1));
     ADSEL_TRY(h->d_out.reserve(out_cap));
     ADSEL_TRY(h->d_result.reserve(8));
@@ -923,7 +927,7 @@ static int dense_enqueue(adsel_handle *h, const adsel_select_params *p, const in
     ADSEL_CUDA(cudaMemcpyAsync(h->pd_boxes.p, n_boxes_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
     if (n_sampled > 0)
         ADSEL_CUDA(cudaMemcpyAsync(h->d_sampled.p, sampled, sizeof(int32_t) * n_sampled, cudaMemcpyHostToDevice, h->stream));
-    ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, n, h->stream));
+    ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n * (sharded ? 1 : DC_CTAS), h->stream));
     ADSEL_CUDA(cudaMemsetAsync(h->d_result.p, 0, sizeof(double) * 8, h->stream));
     CommView view;
     if (sharded) {
