@@ -30,6 +30,7 @@ class BaseSelector(object):
         self.infos_file = infos_origin
         self.buffer = load(buffer_file)                 # {"0": [], "<cumulative budget>": [idx, ...]}
         self.infos_origin = load(infos_origin)          # list[dict], whole pool in RAM (:39)
+        bb.settle_allocator(len(self.infos_origin))
         # budget: ``budget`` more cost units on top of the latest round (:40)
         self.budget = budget
         self.cost_b, self.cost_f = cost_b, cost_f
