@@ -559,7 +559,7 @@ def run_b200_arm(args):
 
         # ---- selection time per budget (BASELINE.json: budgets 600 / 1200 / 4800), device-timed, cold -------------
         per_budget = {str(BUDGET): ms_per_step}
-        for b in (600, 1200):
+        for b in (() if args.quick else (600, 1200)):
             acc = 0.0
             for it in range(1 + 3):
                 flush.add_(1)
@@ -581,9 +581,12 @@ def run_b200_arm(args):
                    logs_file=paths["logs"], distance_store_file=os.path.join(tmp, "unused.npy"),
                    detector=None, dataloader=None, logger=logging.getLogger("bench"), pred=False)
         e2e_times, ctor_times = [], []
+        selector = None
         for it in range(args.warmup + args.steps):
             json.dump({"0": []}, open(buf, "w"))
             random.seed(3407)
+            selector = None                            # the previous iteration's pool is freed BEFORE the next load: freeing a
+                                                       # 225 k-frame list after it would leave its chunks for the timed call to file
             tc = time.perf_counter()
             selector = build_selector(cfg)             # loads buffer + infos pkl into host RAM (untimed, as in the reference)
             tc = time.perf_counter() - tc
@@ -637,7 +640,7 @@ def run_b200_arm(args):
                              f"(all-pairs Dijkstra, superlinear); this library selects the identical list on the sample: {gpu_sel == cpu_sel}"}
         # ---- strong scaling on the fixed 28,130-frame pool, same N ranks (N > 1) ------------------
         strong = None
-        if world > 1:
+        if world > 1 and not args.quick:
             from adsel_b200 import synthetic
             infos28, _ = synthetic.generate_pool(getattr(synthetic, POOL))
             run28, _ = pool.consecutive_runs(pool.logfile_names(infos28))
@@ -793,6 +796,7 @@ def main():
     ap.add_argument("--no-full-reference", action="store_true",
                     help="--impl reference: skip the one full-size cold + warm selection of the unmodified reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="development: 1 timed device step, no per-budget runs, no extras")
     ap.add_argument("--no-cold-cli", action="store_true", help="skip the wall-clock of a fresh tools/active_select.py process")
     ap.add_argument("--no-bev", action="store_true", help="skip the BEV-descriptor extras (histogram / tcgen05 tiles)")
     ap.add_argument("--bev-scale", type=int, default=1, help="N > 1 only: also run the dense BEV path on a pool of "

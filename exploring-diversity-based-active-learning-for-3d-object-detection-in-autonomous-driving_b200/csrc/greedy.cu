@@ -1010,7 +1010,15 @@ struct __align__(16) FastShared {
     unsigned long long sub_val[8];
     int sub_idx[8];
     int err, err_frame, sat, winner;
-    uint4 xrec[2];               // CLUSTER: this CTA's (value, frame) maximum of the step, read by the peers
+};
+
+// Exchange state of the cluster variant only (the one-CTA variant has no shared memory to spare for it).
+template <bool CLUSTER>
+struct FastExchange {};
+template <>
+struct __align__(16) FastExchange<true> {
+    uint4 xrecs[2][CLUSTER_MAX];   // every CTA's (value, frame) maximum of the step, stored here by its owner
+    unsigned long long xbar[2];    // mbarriers (csize arrivals per phase), one per step parity
 };
 
 __device__ __forceinline__ int atom_inc_shared(int *p) {
@@ -1042,9 +1050,10 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // CLUSTER: the columns are split over the CTAs of a thread-block cluster; this CTA holds frames [c_lo, c_hi).  Every CTA
     // applies the part of a row that falls into its slice, reduces its own block maxima, and the CTAs' maxima are exchanged
-    // through distributed shared memory behind the hardware cluster barrier (a mailbox of tagged words polled by the
-    // CTAs, 414 cycles in isolation -- tools/microbench/dsmem.cu -- cost 4,600 cycles per step inside this loop; the
-    // barrier form costs ~1,500); the bookkeeping is replicated, CTA 0 writes the results.
+    // through distributed shared memory: remote stores of the records followed by a release-arrive on every CTA's mbarrier
+    // (a mailbox of plain tagged words polled by the CTAs, 414 cycles in isolation -- tools/microbench/dsmem.cu -- cost
+    // 4,600 cycles per step inside this loop, the hardware cluster barrier ~1,500); the bookkeeping is replicated, CTA 0
+    // writes the results.
     int crank = 0, csize = 1;
     if (CLUSTER) {
         crank = (int)cg::this_cluster().block_rank();
@@ -1086,6 +1095,7 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
     int *dirty_list = blk_idx + nblk;                                     // [2 * nblk]
     int *blk_step = dirty_list + 2 * nblk;                                // [nblk] step that last re-reduced the block (its cached record may still be landing)
     __shared__ FastShared sh;
+    __shared__ FastExchange<CLUSTER> xs;
 
     const unsigned long long far_bits = a.far_bits;
     for (int i = tid; i < cols; i += NT) fps_s[i] = i < c_len ? far_bits : 0ull;
@@ -1251,7 +1261,14 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
             }
         }
     }
-    if (CLUSTER) cg::this_cluster().sync();   // every CTA of the cluster is resident before the first exchange
+    if constexpr (CLUSTER) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&xs.xbar[0])), "r"(csize) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&xs.xbar[1])), "r"(csize) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cg::this_cluster().sync();   // every CTA is resident and its mbarriers are initialised before the first exchange
+    }
     long long steps = 0;
     bool seeding = a.n_sampled > 0;   // first pick = argmax without a preceding update (:165)
     if (!local_abort) {
@@ -1363,19 +1380,31 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
                 const bool take = w.hi > y.hi || (w.hi == y.hi && (w.lo > y.lo || (w.lo == y.lo && w.idx < y.idx)));
                 if (take) y = w;
             }
-            if (CLUSTER) {   // the CTAs' maxima -> the cluster's maximum, on every warp of every CTA
-                // every CTA publishes its maximum in its own shared memory, the hardware cluster barrier orders it, every warp
-                // reads the peers' records through distributed shared memory (records double-buffered by step parity)
+            if constexpr (CLUSTER) {   // the CTAs' maxima -> the cluster's maximum, on every warp of every CTA
+                // Warp 0 stores this CTA's (value, frame) record into EVERY CTA's shared memory and then arrives, with release
+                // semantics at cluster scope, on that CTA's mbarrier of the step's parity; everybody waits (acquire) on the
+                // own mbarrier, which completes when all csize records have landed, and reads them locally.  Records and
+                // mbarriers are double-buffered by step parity: a step's arrivals can never be counted in another step's phase.
                 const int xp = (int)(steps & 1);
-                if (tid == 0) sh.xrec[xp] = make_uint4(y.hi, y.lo, (unsigned)y.idx, 0u);
-                asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+                if (wid == 0 && lane < csize) {
+                    unsigned dst_rec, dst_bar;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst_rec) : "r"((unsigned)__cvta_generic_to_shared(&xs.xrecs[xp][crank])), "r"(lane));
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst_bar) : "r"((unsigned)__cvta_generic_to_shared(&xs.xbar[xp])), "r"(lane));
+                    asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst_rec), "r"(y.hi), "r"(y.lo), "r"((unsigned)y.idx), "r"(0u) : "memory");
+                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(dst_bar) : "memory");
+                }
+                {
+                    const unsigned bar = (unsigned)__cvta_generic_to_shared(&xs.xbar[xp]);
+                    const unsigned parity = (unsigned)((steps >> 1) & 1);
+                    unsigned done = 0;
+                    while (!done)
+                        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                }
                 unsigned hi1[1] = {0u}, lo1[1] = {0u};
                 int idx1[1] = {0x7fffffff};
                 if (lane < csize) {
-                    unsigned src;
-                    uint4 r;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(src) : "r"((unsigned)__cvta_generic_to_shared(&sh.xrec[xp])), "r"(lane));
-                    asm volatile("ld.shared::cluster.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(src) : "memory");
+                    const uint4 r = xs.xrecs[xp][lane];
                     hi1[0] = r.x;
                     lo1[0] = r.y;
                     idx1[0] = (int)r.z;

@@ -208,7 +208,6 @@ def extract_spatial_temporal(infos, known_logfiles=None):
     t1 = time.perf_counter()
     parts = _all_gather_slices(dist, world, mine, -(-n // world))
     t2 = time.perf_counter()
-    LAST_TIMING.update({"parse_own_slice_ms": (t1 - t0) * 1e3, "all_gather_ms": (t2 - t1) * 1e3})
     for p in parts:
         if p["missing"] is not None:
             raise KeyError(p["missing"])
@@ -221,6 +220,8 @@ def extract_spatial_temporal(infos, known_logfiles=None):
     max_td = int(lengths[:-1].max()) if len(lengths) > 1 else 0
     loc = np.ascontiguousarray(np.concatenate([p["loc"] for p in parts]))
     boxes = np.concatenate([p["boxes"] for p in parts]).astype(np.int32)
+    LAST_TIMING.update({"parse_own_slice_ms": (t1 - t0) * 1e3, "all_gather_ms": (t2 - t1) * 1e3,
+                        "assemble_ms": (time.perf_counter() - t2) * 1e3})
     return loc, run_id, max_td, boxes
 
 

@@ -46,6 +46,7 @@ class SpatialTemporalSelector(BaseSelector):
         t0 = time.perf_counter()
         infos = self.infos_origin
         known = {l["logfile"] for l in load(self.logs_file)}           # the reference raises KeyError at :80
+        t_logs = time.perf_counter()
         # :83-91 ego locations, :114-129 consecutive logfile runs, base_selector.py:85 box counts
         locations, run_id, max_td, n_boxes = pool.extract_spatial_temporal(infos, known)
         t1 = time.perf_counter()
@@ -59,7 +60,7 @@ class SpatialTemporalSelector(BaseSelector):
                              aggregate=self.aggregate, lambda_t=self.lambda_t, max_spatial=max_sd,
                              max_temporal=max_td)
             t3 = time.perf_counter()
-            self.last_stats["host_ms"] = {"extract": (t1 - t0) * 1e3, "pool+graph": (t2 - t1) * 1e3,
+            self.last_stats["host_ms"] = {"extract": (t1 - t0) * 1e3, "logs_file": (t_logs - t0) * 1e3, "pool+graph": (t2 - t1) * 1e3,
                                           "lists+greedy+readback": (t3 - t2) * 1e3, **pool.LAST_TIMING}
         finally:
             handle.close()

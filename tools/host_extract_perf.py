@@ -24,6 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dir", required=True)
     ap.add_argument("--iters", type=int, default=6)
+    ap.add_argument("--no-settle", action="store_true", help="skip the allocator settling the selector's constructor performs")
     ap.add_argument("--no-gc", action="store_true", help="pause the cyclic GC around the timed call")
     args = ap.parse_args()
     dist.init_process_group("gloo")
@@ -39,6 +40,9 @@ def main():
     rows = []
     for it in range(args.iters):
         infos = fileio.load(paths["infos"])            # a fresh list per call, like a fresh selector
+        if not args.no_settle:
+            from adsel_b200.selectors import budget_buffer
+            budget_buffer.settle_allocator(len(infos))   # what BaseSelector.__init__ does after the load
         dist.barrier()
         if args.no_gc:
             gc.disable()
