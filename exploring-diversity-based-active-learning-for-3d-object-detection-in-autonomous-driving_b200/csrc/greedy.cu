@@ -1040,9 +1040,9 @@ __device__ __forceinline__ uint4 lds128_volatile(const void *p) {   // one 16-by
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int RB, bool CLUSTER, bool PROFILE>
-__global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs a) {
-    constexpr int NT = RES_NT, NW = NT / 32, PER = RB / 32, NSUB = RB / 32;   // NSUB <= NW: one sub-block of the own block per warp
+template <int RB, int NT, bool CLUSTER, bool PROFILE>
+__global__ void __launch_bounds__(NT, 1) greedy_fast_kernel(const GreedyArgs a) {
+    constexpr int NW = NT / 32, PER = RB / 32, NSUB = RB / 32;   // the own block's NSUB sub-blocks are dealt out to the NW warps
     constexpr int SHIFT = RB == 256 ? 8 : 7;
     static_assert(RB == 128 || RB == 256, "block size");
     unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1321,19 +1321,19 @@ __global__ void __launch_bounds__(RES_NT, 1) greedy_fast_kernel(const GreedyArgs
                 prof_acc[14] += nd;
             }
             const int ref_blk = cur_blk;   // -1: nothing was applied in this iteration (seeding)
-            if (ref_blk >= 0 && wid < NSUB) {
-                const int lj = (ref_blk << SHIFT) + 32 * wid + lane;
+            for (int sb = wid; sb < NSUB && ref_blk >= 0; sb += NW) {
+                const int lj = (ref_blk << SHIFT) + 32 * sb + lane;
                 const unsigned long long v = fps_s[lj];
                 unsigned hi[1] = {(unsigned)(v >> 32)}, lo[1] = {(unsigned)v};
                 int idx[1] = {lj < c_len ? c_lo + lj : 0x7fffffff};
                 const Win x = warp_argmax<1>(hi, lo, idx);
                 if (lane == 0) {
-                    sh.sub_val[wid] = ((unsigned long long)x.hi << 32) | x.lo;
-                    sh.sub_idx[wid] = x.idx;
+                    sh.sub_val[sb] = ((unsigned long long)x.hi << 32) | x.lo;
+                    sh.sub_idx[sb] = x.idx;
                     if (x.idx != 0x7fffffff) {
                         cp_async_wait_all();   // the slot's previous copy (a step ago) has landed: no reordering of two copies
-                        cp_async16(&sh.sub_rec[wid][0], recs + x.idx);
-                        cp_async16(&sh.sub_rec[wid][1], reinterpret_cast<const char *>(recs + x.idx) + 16);
+                        cp_async16(&sh.sub_rec[sb][0], recs + x.idx);
+                        cp_async16(&sh.sub_rec[sb][1], reinterpret_cast<const char *>(recs + x.idx) + 16);
                     }
                 }
             }
@@ -1620,9 +1620,9 @@ struct FastPlan {
     size_t smem = 0;
 };
 
-template <int RB, bool CLUSTER, bool PROFILE>
+template <int RB, int NT, bool CLUSTER, bool PROFILE>
 static cudaError_t launch_fast(adsel_handle *h, const GreedyArgs &a, size_t smem, bool dry_run, int *max_clusters) {
-    auto kernel = greedy_fast_kernel<RB, CLUSTER, PROFILE>;
+    auto kernel = greedy_fast_kernel<RB, NT, CLUSTER, PROFILE>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (CLUSTER && a.csize > 8) {
@@ -1632,7 +1632,7 @@ static cudaError_t launch_fast(adsel_handle *h, const GreedyArgs &a, size_t smem
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(CLUSTER ? a.csize : 1), 1, 1);
-    cfg.blockDim = dim3(RES_NT, 1, 1);
+    cfg.blockDim = dim3(NT, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
@@ -1649,13 +1649,24 @@ static cudaError_t launch_fast(adsel_handle *h, const GreedyArgs &a, size_t smem
     return cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
+static int fast_threads() {   // ADSEL_FAST_THREADS=128/256: threads of a fast CTA (measurement aid; default 256)
+    const char *e = getenv("ADSEL_FAST_THREADS");
+    return (e && atoi(e) == 128) ? 128 : 256;
+}
+
 static cudaError_t dispatch_fast(adsel_handle *h, const GreedyArgs &a, const FastPlan &pl, bool dry_run, int *max_clusters) {
-    if (pl.csize > 1) return a.prof ? launch_fast<256, true, true>(h, a, pl.smem, dry_run, max_clusters)
-                                    : launch_fast<256, true, false>(h, a, pl.smem, dry_run, max_clusters);
-    if (a.prof) return pl.rb == 128 ? launch_fast<128, false, true>(h, a, pl.smem, dry_run, max_clusters)
-                                    : launch_fast<256, false, true>(h, a, pl.smem, dry_run, max_clusters);
-    return pl.rb == 128 ? launch_fast<128, false, false>(h, a, pl.smem, dry_run, max_clusters)
-                        : launch_fast<256, false, false>(h, a, pl.smem, dry_run, max_clusters);
+    const bool t128 = fast_threads() == 128;
+    if (pl.csize > 1) {
+        if (a.prof) return launch_fast<256, 256, true, true>(h, a, pl.smem, dry_run, max_clusters);
+        return t128 ? launch_fast<256, 128, true, false>(h, a, pl.smem, dry_run, max_clusters)
+                    : launch_fast<256, 256, true, false>(h, a, pl.smem, dry_run, max_clusters);
+    }
+    if (a.prof) return pl.rb == 128 ? launch_fast<128, 256, false, true>(h, a, pl.smem, dry_run, max_clusters)
+                                    : launch_fast<256, 256, false, true>(h, a, pl.smem, dry_run, max_clusters);
+    if (t128) return pl.rb == 128 ? launch_fast<128, 128, false, false>(h, a, pl.smem, dry_run, max_clusters)
+                                  : launch_fast<256, 128, false, false>(h, a, pl.smem, dry_run, max_clusters);
+    return pl.rb == 128 ? launch_fast<128, 256, false, false>(h, a, pl.smem, dry_run, max_clusters)
+                        : launch_fast<256, 256, false, false>(h, a, pl.smem, dry_run, max_clusters);
 }
 
 // The lean step (greedy_fast_kernel): no Euclid term, contiguous temporal groups, the whole pool on this device, its
@@ -1740,9 +1751,9 @@ int greedy_preload() {
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<256, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<512, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<1024, false>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<128, false, false>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, false, false>));
-    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, true, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<128, 256, false, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, 256, false, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, 256, true, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<128, false, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<256, false, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<128, true, false>));
