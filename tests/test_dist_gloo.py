@@ -87,6 +87,36 @@ def _worker(rank, world, init_file, pool_dir, out_dir):
         result["retry_calls"] = [c if isinstance(c, str) else c[0] for c in w2.handle.calls]
         result["retry_list_cap"] = w2._list_cap
         fake_native.FakeShardHandle.overflow_once = False
+
+        # 4. round-2 schedule and guards: sharded build + replicated loop by default, comm_check after every selection, the
+        #    first frame of an empty buffer is rank 0's draw on every rank, a buffer that differs between ranks is refused
+        result["mode"] = w2.mode
+        result["replicate_flag"] = bool(getattr(w2.handle, "replicate", False))
+        result["comm_checks"] = sum(1 for c in w2.handle.calls if (c if isinstance(c, str) else c[0]) == "comm_check")
+        from adsel_b200 import dist as adist
+        result["agreed"] = list(adist.agree_from_rank0((1000 + rank, 7)))
+        result["max"] = adist.all_ranks_max(rank * 5)
+        try:
+            adist.check_same_on_all_ranks((rank,), "a value that differs")
+            result["mismatch"] = "not detected"
+        except RuntimeError as e:
+            result["mismatch"] = str(e)[:30]
+        random.seed(3407 + 17 * rank)                                    # unsynchronised per-rank RNG (a library user without the CLI)
+        buffer2 = os.path.join(out_dir, "buffer2.json")
+        if rank == 0:
+            json.dump({"0": []}, open(buffer2, "w"))
+        dist.barrier()
+        sel = build_selector(dict(type="SpatialTemporalSelector", budget=50, buffer_file=buffer2, infos_origin=infos_path,
+                                  logs_file=logs_path, distance_store_file=os.path.join(out_dir, "unused.npy")))
+        sel.select_samples(local_rank=rank)
+        result["unsynced_rng_selection"] = sel.get_selected_samples()["50"]
+        os.environ["ADSEL_SHARD"] = "columns"
+        result["mode_forced"] = sharded.shard_mode(300)
+        os.environ.pop("ADSEL_SHARD")
+        result["mode_big"] = sharded.shard_mode(500_000)
+        result["lazy"] = [sharded.lazy_rows(28130, dict(spatial="geodesic", normalize="linear")),
+                          sharded.lazy_rows(28130, dict(spatial="geodesic", normalize="exp")),
+                          sharded.lazy_rows(2000, dict(spatial="geodesic", normalize="raw"))]
         json.dump(result, open(os.path.join(out_dir, f"rank{rank}.json"), "w"))
         dist.barrier()
         dist.destroy_process_group()
@@ -117,6 +147,12 @@ def test_two_ranks_select_like_the_reference_and_only_rank0_writes(pools, tmp_pa
         assert r["retry_list_cap"] == int(1010 * 1.1) + 1024                  # ... sized for the largest need over the ranks
     assert json.load(open(os.path.join(out_dir, "buffer.json"))) == {"0": [], "50": want["50"], "100": want["100"]}
     assert os.path.exists(pl["paths"]["infos"].replace(".pkl", "_100.pkl"))
+    for r in (r0, r1):
+        assert r["mode"] == "replicate" and r["replicate_flag"] and r["comm_checks"] >= 1
+        assert r["agreed"] == [1000, 7] and r["max"] == 5 and r["mismatch"].startswith("ranks disagree on")
+        assert r["mode_forced"] == "columns" and r["mode_big"] == "columns" and r["lazy"] == [True, False, False]
+    # both ranks started from rank 0's random.choice although their RNGs were seeded differently
+    assert r0["unsynced_rng_selection"] == r1["unsynced_rng_selection"] and len(r0["unsynced_rng_selection"]) > 0
 
 
 def _extract_worker(rank, world, init_file, pool_dir, out_dir):

@@ -580,3 +580,37 @@ def test_reference_registry_builds_the_drop_in_selector(pools, tmp_path):
             del sys.modules[k]
         sys.modules.update(saved)
         sys.path[:] = saved_path
+
+
+def test_settle_allocator_is_harmless_and_bounded():
+    """selectors/budget_buffer.settle_allocator: a few throw-away allocations after the unpickle (glibc only); small pools
+    are left alone and nothing is raised where libc is not glibc."""
+    import time
+    from adsel_b200.selectors import budget_buffer as bb
+    bb.settle_allocator(10)                       # below the threshold: no work
+    t0 = time.perf_counter()
+    bb.settle_allocator(281300)
+    assert time.perf_counter() - t0 < 2.0
+
+
+def test_fused_feature_selectors_keep_the_reference_constructors(pools, tmp_path):
+    """SpatialFeatureSelector / SpatialTemporalFeatureSelector: registry names, keyword defaults and assertions of
+    spatial_feature_selector.py:18-60 / spatial_temporal_feature_selector.py:18-64; pred=True (running the detector) is refused."""
+    import inspect
+    from adsel_b200.selectors import SELECTORS, build_selector
+    pl = pools("P300")
+    buf = str(tmp_path / "buffer.json")
+    json.dump({"0": []}, open(buf, "w"))
+    sf, stf = SELECTORS.get("SpatialFeatureSelector"), SELECTORS.get("SpatialTemporalFeatureSelector")
+    d_sf = {k: v.default for k, v in inspect.signature(sf.__init__).parameters.items() if v.default is not inspect.Parameter.empty}
+    d_stf = {k: v.default for k, v in inspect.signature(stf.__init__).parameters.items() if v.default is not inspect.Parameter.empty}
+    assert (d_sf["pred"], d_sf["k"], d_sf["p"], d_sf["aggregate"], d_sf["buffer_path"]) == (False, 8, 2, "sum", "")
+    assert (d_stf["pred"], d_stf["k"], d_stf["p"], d_stf["lambda_f"], d_stf["lambda_t"]) == (True, 8, 2, 1, 1)
+    base = dict(budget=10, buffer_file=buf, infos_origin=pl["paths"]["infos"], logs_file=pl["paths"]["logs"])
+    with pytest.raises(AssertionError):
+        build_selector(dict(type="SpatialFeatureSelector", aggregate="mean", **base))
+    with pytest.raises(AssertionError):
+        build_selector(dict(type="SpatialTemporalFeatureSelector", p=3, **base))
+    sel = build_selector(dict(type="SpatialTemporalFeatureSelector", **base))      # pred defaults to True, like the reference
+    with pytest.raises(NotImplementedError):
+        sel.select_samples(local_rank=0)
