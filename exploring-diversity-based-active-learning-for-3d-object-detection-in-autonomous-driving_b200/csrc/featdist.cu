@@ -107,93 +107,120 @@ feature_l1_kernel(const float *__restrict__ x, int n, int dim, int p2, float *__
 
 
 // ---- torch's summation order, bit for bit ---------------------------------------------------------------------
-// One warp per output at a time: lane l accumulates the terms c = 32 pos + l (pos = 0 .. C/32 - 1), i.e. it is torch's
-// accumulator (k = l / 8, lane = l % 8) of the 4 x 8 interleaved vector accumulators; every 16 terms the running sum is
-// folded into the next level exactly as multi_row_sum does.  Then ((a0 + a1) + a2) + a3 over k and the 8 lanes in
-// order.  A CTA stages 64 "j" rows in shared memory; each of its 8 warps takes 8 "i" rows, one after the other, with
-// the i row in registers.  Two outputs are in flight per warp so that the serial shuffle tail of one overlaps the
-// accumulation of the other.
+// A warp works on one "i" row against 32 "j" rows at a time.  Lane l accumulates, for each of the 32 outputs, the terms
+// c = 32 pos + l (pos = 0 .. C/32 - 1): it IS torch's accumulator (k = l / 8, lane = l % 8) of the 4 x 8 interleaved vector
+// accumulators, and every 16 terms the running sums are folded into the next level exactly as multi_row_sum does -- 32
+// independent accumulation chains per lane.  The 32 x 32 partial sums then go through a padded shared-memory transpose so
+// that lane j holds all 32 accumulators of output j and finishes it alone, in torch's order: ((a0 + a1) + a2) + a3 over the
+// four accumulators of each of the 8 vector lanes, then the 8 lanes in order.  A CTA stages 64 "j" rows in shared memory
+// (fewer when 64 do not fit) and reuses them for a chunk of up to 4,096 "i" rows: each of its 8 warps takes every 8th row
+// of the chunk and keeps it in registers.
 constexpr int FT_ROWS = 64, FT_THREADS = 256, FT_MAXREG = 32;   // C <= 32 * FT_MAXREG = 1024 keeps the i row in registers
 
-__device__ __forceinline__ float torch_tail(float acc) {   // acc: this lane's accumulator (k = lane / 8, l8 = lane % 8)
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    // partial_sums[0] += partial_sums[k], k = 1, 2, 3 (lanes 0..7 hold the result)
-    float v = acc;
-    v = __fadd_rn(v, __shfl_sync(full, acc, (lane & 7) + 8));
-    v = __fadd_rn(v, __shfl_sync(full, acc, (lane & 7) + 16));
-    v = __fadd_rn(v, __shfl_sync(full, acc, (lane & 7) + 24));
-    // final_acc = 0; final_acc += partials[0..7] in order
-    float s = 0.0f;
+// One (i row, 32 j rows) batch: returns nothing, leaves the 32 x 32 partial sums in `tile`.  LITERAL: evaluate the reference's
+// sqrt(fl(d*d)) term as written (needed only when a staged value may make d*d leave float32's normal range -- see
+// plain_value above; otherwise sqrt(fl(d*d)) == |d| exactly and the IEEE square root, ~20 instructions per term, is skipped).
+template <bool LITERAL>
+__device__ __forceinline__ void ft_batch(const float (&a)[FT_MAXREG], const float *b, int dim, int nvec, float *tile, int lane) {
+    float acc0[32], acc1[32], acc2[32], acc3[32];
 #pragma unroll
-    for (int l = 0; l < 8; ++l) s = __fadd_rn(s, __shfl_sync(full, v, l));
-    return s;
+    for (int o = 0; o < 32; ++o) acc0[o] = acc1[o] = acc2[o] = acc3[o] = 0.f;
+    int pos = 0;
+#pragma unroll 1
+    for (; pos + 16 <= nvec;) {
+#pragma unroll
+        for (int q = 0; q < FT_MAXREG; ++q) {
+            if (q >= pos && q < pos + 16) {
+#pragma unroll
+                for (int o = 0; o < 32; ++o) {
+                    const float d = __fsub_rn(b[(size_t)o * dim + 32 * q], a[q]);
+                    acc0[o] = __fadd_rn(acc0[o], LITERAL ? __fsqrt_rn(__fmul_rn(d, d)) : fabsf(d));
+                }
+            }
+        }
+        pos += 16;
+#pragma unroll
+        for (int o = 0; o < 32; ++o) {   // fold through the levels like multi_row_sum (level_power = 4)
+            acc1[o] = __fadd_rn(acc1[o], acc0[o]);
+            acc0[o] = 0.f;
+            if ((pos & 0xf0) == 0) {
+                acc2[o] = __fadd_rn(acc2[o], acc1[o]);
+                acc1[o] = 0.f;
+                if ((pos & 0xf00) == 0) {
+                    acc3[o] = __fadd_rn(acc3[o], acc2[o]);
+                    acc2[o] = 0.f;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < FT_MAXREG; ++q) {
+        if (q >= pos && q < nvec) {
+#pragma unroll
+            for (int o = 0; o < 32; ++o) {
+                const float d = __fsub_rn(b[(size_t)o * dim + 32 * q], a[q]);
+                acc0[o] = __fadd_rn(acc0[o], LITERAL ? __fsqrt_rn(__fmul_rn(d, d)) : fabsf(d));
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        float t = __fadd_rn(acc0[o], acc1[o]);
+        t = __fadd_rn(t, acc2[o]);
+        t = __fadd_rn(t, acc3[o]);
+        tile[o * 33 + lane] = t;            // accumulator `lane` of output o
+    }
+    __syncwarp();
 }
 
 template <int P2>
 __global__ void __launch_bounds__(FT_THREADS)
-feature_l1_torch_kernel(const float *__restrict__ x, int n, int dim, float *__restrict__ out, int ld, int rows) {
-    extern __shared__ float ft_smem[];   // [rows][dim]: 64 rows, fewer (an even number) when 64 do not fit 227 KB
+feature_l1_torch_kernel(const float *__restrict__ x, int n, int dim, float *__restrict__ out, int ld, int rows, int ichunk) {
+    extern __shared__ float ft_smem[];   // [rows][dim] j rows | [8 warps][32][33] transpose tiles
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int j0 = blockIdx.x * rows, i0 = blockIdx.y * rows;
+    const int j0 = blockIdx.x * rows, i0 = blockIdx.y * ichunk;   // the staged j tile is reused by `ichunk` i rows
+    // The map is symmetric BIT FOR BIT (|a - b| == |b - a| term by term, same summation order), so only the rows i >= j0 of
+    // a j tile are computed and every result below the diagonal tile is stored twice: out[i][j] and out[j][i].
+    if (i0 + ichunk <= j0) return;
     const int nvec = dim / 32;            // torch's size_ilp: vectors per interleaved accumulator
+    float *tile = ft_smem + (size_t)rows * dim + (size_t)wid * 32 * 33;
+    int odd = 0;
     for (int e = threadIdx.x; e < rows * dim; e += FT_THREADS) {
         const int r = e / dim, c = e - r * dim;
-        ft_smem[e] = j0 + r < n ? x[(size_t)(j0 + r) * dim + c] : 0.0f;
+        const float v = j0 + r < n ? x[(size_t)(j0 + r) * dim + c] : 0.0f;
+        ft_smem[e] = v;
+        odd |= plain_value(v) ? 0 : 1;
     }
-    __syncthreads();
-    for (int ii = wid; ii < rows; ii += FT_THREADS / 32) {
+    const bool plain_j = __syncthreads_or(odd) == 0;   // also the barrier that publishes the tile
+    for (int ii = wid; ii < ichunk; ii += FT_THREADS / 32) {
         const int i = i0 + ii;
         if (i >= n) break;
+        if (i < j0) continue;
         float a[FT_MAXREG];
 #pragma unroll
         for (int q = 0; q < FT_MAXREG; ++q) a[q] = q < nvec ? x[(size_t)i * dim + 32 * q + lane] : 0.0f;
-        for (int jj = 0; jj < rows; jj += 2) {
-            const float *b0 = ft_smem + (size_t)jj * dim + lane, *b1 = b0 + dim;
-            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-            int pos = 0;
-#pragma unroll 1
-            for (; pos + 16 <= nvec; ) {
+        int odd_i = 0;
 #pragma unroll
-                for (int q = 0; q < FT_MAXREG; ++q) {
-                    if (q >= pos && q < pos + 16) {
-                        const float d0 = __fsub_rn(b0[32 * q], a[q]), d1 = __fsub_rn(b1[32 * q], a[q]);
-                        acc[0][0] = __fadd_rn(acc[0][0], P2 ? __fsqrt_rn(__fmul_rn(d0, d0)) : fabsf(d0));
-                        acc[1][0] = __fadd_rn(acc[1][0], P2 ? __fsqrt_rn(__fmul_rn(d1, d1)) : fabsf(d1));
-                    }
-                }
-                pos += 16;
+        for (int q = 0; q < FT_MAXREG; ++q) odd_i |= plain_value(a[q]) ? 0 : 1;
+        const bool plain_i = __any_sync(0xffffffffu, odd_i) == 0;
+        for (int jj = 0; jj < rows; jj += 32) {
+            const float *b = ft_smem + (size_t)jj * dim + lane;
+            if (P2 && !(plain_j && plain_i)) ft_batch<true>(a, b, dim, nvec, tile, lane);
+            else ft_batch<false>(a, b, dim, nvec, tile, lane);
+            // lane o finishes output o: partial_sums[0] += partial_sums[k] per vector lane, then the 8 lanes in order
+            float s = 0.0f;
 #pragma unroll
-                for (int o = 0; o < 2; ++o) {   // fold through the levels like multi_row_sum (level_power = 4)
-                    acc[o][1] = __fadd_rn(acc[o][1], acc[o][0]);
-                    acc[o][0] = 0.f;
-                    if ((pos & 0xf0) == 0) {
-                        acc[o][2] = __fadd_rn(acc[o][2], acc[o][1]);
-                        acc[o][1] = 0.f;
-                        if ((pos & 0xf00) == 0) {
-                            acc[o][3] = __fadd_rn(acc[o][3], acc[o][2]);
-                            acc[o][2] = 0.f;
-                        }
-                    }
-                }
+            for (int l8 = 0; l8 < 8; ++l8) {
+                float v = tile[lane * 33 + l8];
+                v = __fadd_rn(v, tile[lane * 33 + l8 + 8]);
+                v = __fadd_rn(v, tile[lane * 33 + l8 + 16]);
+                v = __fadd_rn(v, tile[lane * 33 + l8 + 24]);
+                s = __fadd_rn(s, v);
             }
-#pragma unroll
-            for (int q = 0; q < FT_MAXREG; ++q) {
-                if (q >= pos && q < nvec) {
-                    const float d0 = __fsub_rn(b0[32 * q], a[q]), d1 = __fsub_rn(b1[32 * q], a[q]);
-                    acc[0][0] = __fadd_rn(acc[0][0], P2 ? __fsqrt_rn(__fmul_rn(d0, d0)) : fabsf(d0));
-                    acc[1][0] = __fadd_rn(acc[1][0], P2 ? __fsqrt_rn(__fmul_rn(d1, d1)) : fabsf(d1));
-                }
-            }
-#pragma unroll
-            for (int o = 0; o < 2; ++o) {
-                float t = __fadd_rn(acc[o][0], acc[o][1]);
-                t = __fadd_rn(t, acc[o][2]);
-                t = __fadd_rn(t, acc[o][3]);
-                const float s = torch_tail(t);
-                const int j = j0 + jj + o;
-                if (lane == 0 && j < ld) out[(size_t)i * ld + j] = j < n ? s : 0.0f;
-            }
+            const int j = j0 + jj + lane;
+            if (jj + lane < rows && j < ld) out[(size_t)i * ld + j] = j < n ? s : 0.0f;
+            if (jj + lane < rows && j < n && i >= j0 + rows) out[(size_t)j * ld + i] = s;   // mirror image
         }
     }
 }
@@ -227,16 +254,20 @@ int feature_distance_build(adsel_handle *h, const float *feats_host, int32_t n, 
     ADSEL_TRY(begin_stage(h));
     const bool exact = dim % 32 == 0 && dim <= 32 * FT_MAXREG && !getenv("ADSEL_FEATDIST_INDEX_ORDER");
     if (exact) {   // torch's summation order: the map is the reference's, bit for bit
-        int rows = FT_ROWS;
-        while ((size_t)rows * dim * sizeof(float) > 220 * 1024) rows -= 2;
-        dim3 grid((n + rows - 1) / rows, (n + rows - 1) / rows);
-        const size_t smem = sizeof(float) * rows * dim;
+        int rows = FT_ROWS;     // a multiple of 32: a warp finishes 32 outputs at a time
+        const size_t tiles = sizeof(float) * (FT_THREADS / 32) * 32 * 33;
+        while (rows > 32 && (size_t)rows * dim * sizeof(float) + tiles > 220 * 1024) rows -= 32;
+        // every CTA stages one tile of j rows and reuses it for `ichunk` i rows: enough CTAs to fill the GPU a few times over
+        int ichunk = 4096;
+        while (ichunk > 256 && (long long)((n + rows - 1) / rows) * ((n + ichunk - 1) / ichunk) < 8LL * h->num_sms) ichunk /= 2;
+        dim3 grid((n + rows - 1) / rows, (n + ichunk - 1) / ichunk);
+        const size_t smem = sizeof(float) * rows * dim + tiles;
         if (p == 2) {
             ADSEL_CUDA(cudaFuncSetAttribute(feature_l1_torch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            feature_l1_torch_kernel<1><<<grid, FT_THREADS, smem, h->stream>>>(h->feat.p, n, dim, reinterpret_cast<float *>(h->d2_p), ld, rows);
+            feature_l1_torch_kernel<1><<<grid, FT_THREADS, smem, h->stream>>>(h->feat.p, n, dim, reinterpret_cast<float *>(h->d2_p), ld, rows, ichunk);
         } else {
             ADSEL_CUDA(cudaFuncSetAttribute(feature_l1_torch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            feature_l1_torch_kernel<0><<<grid, FT_THREADS, smem, h->stream>>>(h->feat.p, n, dim, reinterpret_cast<float *>(h->d2_p), ld, rows);
+            feature_l1_torch_kernel<0><<<grid, FT_THREADS, smem, h->stream>>>(h->feat.p, n, dim, reinterpret_cast<float *>(h->d2_p), ld, rows, ichunk);
         }
     } else {
         dim3 grid((n + FD_TILE - 1) / FD_TILE, (n + FD_TILE - 1) / FD_TILE);

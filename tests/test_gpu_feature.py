@@ -78,6 +78,25 @@ def test_fused_feature_selectors_drop_in_select_like_the_reference(pools, tmp_pa
     assert len(golden["cases"]) == 11
 
 
+def test_p2_extreme_magnitudes_in_torchs_order_too():
+    """The torch-order kernel skips the IEEE square root of p=2 only where sqrt(fl(d*d)) == |d| is provable; rows / tiles with
+    values outside that range take the literal expression (dimension 64: the bit-exact kernel)."""
+    rng = np.random.default_rng(8)
+    feats = rng.standard_normal((200, 64)).astype(np.float32)
+    feats[3, 5] = 1e-30
+    feats[150, 9] = 3e19
+    feats[77] = 0.0
+    h = native.Handle(0)
+    try:
+        for p in (1, 2):
+            h.feature_distance_build(feats, p)
+            got = h.feature_distance_rows(0, len(feats))
+            ref = np.stack([R.feature_row(feats, i, p) for i in range(len(feats))])
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), p
+    finally:
+        h.close()
+
+
 def test_p2_extreme_magnitudes_follow_the_literal_expression():
     """sqrt(fl(d*d)) differs from |d| only when d*d underflows / overflows float32: those terms are evaluated literally."""
     feats = np.zeros((4, 8), dtype=np.float32)
