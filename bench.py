@@ -71,6 +71,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_first(self, timeout=6.0):
+        """nvidia-smi needs most of a second to start; the timed region of this bench lasts a few hundred milliseconds."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -533,6 +539,7 @@ def run_b200_arm(args):
 
         clocks = ClockSampler(local_rank)      # sampled from the warm-up on: the timed region alone lasts < 0.1 s
         clocks.start()
+        clocks.wait_first()
         for _ in range(args.warmup):
             sel, _ = step()
         launches0 = h.counters()["launches"]
