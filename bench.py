@@ -612,6 +612,9 @@ def run_b200_arm(args):
         assert e2e_sel == sel, "device-resident and end-to-end arms disagree"
         e2e_sec = max_over_ranks(sum(e2e_times) / len(e2e_times))
         h2d = loc.nbytes + run_id.nbytes + n_boxes.nbytes + 4 * (int(run_id.max()) + 2) + 4 * n
+        ego_check = dict(pool.LAST_EGO_CHECK)          # every frame's ego location redone on the device (csrc/ego_check.cu)
+        if ego_check:
+            h2d += ego_check["frames"] * (9 + 2) * 8 + 16   # this rank's pose entries + locations + the result words
         d2h = 4 * len(sel) + 64 + 12       # selected indices + result block + nnz/list-total scalars
 
         # ---- parity spot-check against the committed golden (reference output) ------------------
@@ -778,6 +781,7 @@ def run_b200_arm(args):
                     "constructor_ms": 1e3 * sum(ctor_times) / len(ctor_times),      # unpickling the pool + settling the allocator: outside the timed call, stated
                     "with_constructor_ms": e2e_sec * 1e3 + 1e3 * sum(ctor_times) / len(ctor_times),
                     "rank0_host_ms_last_step": selector.last_stats.get("host_ms"),
+                    "ego_location_check": ego_check or None,    # frames redone on the device / frames that differed (inside the timed call)
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clock_info,
             "e2e_cold_cli_s": cold_cli,

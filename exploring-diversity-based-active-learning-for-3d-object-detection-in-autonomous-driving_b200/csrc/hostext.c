@@ -108,13 +108,15 @@ static PyObject *extract(PyObject *self, PyObject *args) {
     const Py_ssize_t m = hi - lo;
     PyObject *loc_b = PyBytes_FromStringAndSize(NULL, m * 16), *box_b = PyBytes_FromStringAndSize(NULL, m * 4);
     PyObject *chg_b = PyBytes_FromStringAndSize(NULL, m);
+    PyObject *pose_b = PyBytes_FromStringAndSize(NULL, m * 72); /* the nine pose entries the location uses, per frame */
     PyObject *names = PyList_New(m);
     PyObject *k_cal = PyUnicode_InternFromString("car_from_global"), *k_path = PyUnicode_InternFromString("cam_front_path"),
              *k_gt = PyUnicode_InternFromString("gt_names");
-    if (!loc_b || !box_b || !chg_b || !names || !k_cal || !k_path || !k_gt) goto fail;
+    if (!loc_b || !box_b || !chg_b || !pose_b || !names || !k_cal || !k_path || !k_gt) goto fail;
     double *loc = (double *)PyBytes_AS_STRING(loc_b);
     int32_t *box = (int32_t *)PyBytes_AS_STRING(box_b);
     unsigned char *chg = (unsigned char *)PyBytes_AS_STRING(chg_b);
+    double *pose = (double *)PyBytes_AS_STRING(pose_b);
     PyObject *last_name = NULL; /* names[i-1], borrowed from the list */
     PyObject *prev_name = NULL, *prev_path = NULL;
     Py_ssize_t prev_prefix = 0; /* length of "<dir>/<name>__" in prev_path */
@@ -204,6 +206,11 @@ static PyObject *extract(PyObject *self, PyObject *args) {
 #else
         if (read_cal(cal, c) != 0) goto fail;
 #endif
+        for (int r = 0; r < 3; ++r) { /* handed to the device, which redoes every frame (csrc/ego_check.cu) */
+            pose[9 * i + 3 * r] = c[r][0];
+            pose[9 * i + 3 * r + 1] = c[r][1];
+            pose[9 * i + 3 * r + 2] = c[r][3];
+        }
         for (int j = 0; j < 2; ++j) {
             double v;
             if (fused) v = fma(c[2][3], c[2][j], fma(c[1][3], c[1][j], c[0][3] * c[0][j]));
@@ -275,11 +282,12 @@ static PyObject *extract(PyObject *self, PyObject *args) {
     Py_DECREF(k_cal);
     Py_DECREF(k_path);
     Py_DECREF(k_gt);
-    return Py_BuildValue("(NNNN)", loc_b, box_b, names, chg_b);
+    return Py_BuildValue("(NNNNN)", loc_b, box_b, names, chg_b, pose_b);
 fail:
     Py_XDECREF(loc_b);
     Py_XDECREF(box_b);
     Py_XDECREF(chg_b);
+    Py_XDECREF(pose_b);
     Py_XDECREF(names);
     Py_XDECREF(k_cal);
     Py_XDECREF(k_path);
@@ -287,7 +295,7 @@ fail:
     return NULL;
 }
 
-static PyMethodDef methods[] = {{"extract", extract, METH_VARARGS, "extract(infos, lo, hi, fused) -> (loc bytes, boxes bytes, names)"},
+static PyMethodDef methods[] = {{"extract", extract, METH_VARARGS, "extract(infos, lo, hi, fused) -> (loc bytes, boxes bytes, names, change bytes, pose9 bytes)"},
                                 {NULL, NULL, 0, NULL}};
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_adsel_hostext", "host-side extraction helper", -1, methods};
 PyMODINIT_FUNC PyInit__adsel_hostext(void) { return PyModule_Create(&moddef); }

@@ -99,6 +99,8 @@ _SIGNATURES = {
     "adsel_select_fused_feature": (ctypes.c_int, [_P, ctypes.POINTER(SelectParams), ctypes.c_double, ctypes.c_int32, _P, ctypes.c_int32,
                                                   ctypes.c_int32, _P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
                                                   ctypes.POINTER(ctypes.c_double)]),
+    "adsel_check_ego_locations": (ctypes.c_int, [ctypes.c_int, _P, _P, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                                 ctypes.POINTER(ctypes.c_int64)]),
     "adsel_feature_distance_build": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
     "adsel_pairdist_build_sharded": (ctypes.c_int, [_P]),
     "adsel_select_dense_prepare": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32]),
@@ -181,6 +183,18 @@ def device_count() -> int:
     c = ctypes.c_int(0)
     _check(load().adsel_device_count(ctypes.byref(c)))
     return c.value
+
+
+def check_ego_locations(device: int, pose9, loc_xy, fused: bool):
+    """``(n_bad, first_bad)``: every frame's ego location redone on the device in the literal order of
+    spatial_temporal_selector.py:83-91 and compared bit-for-bit with ``loc_xy`` (csrc/ego_check.cu)."""
+    pose9 = np.ascontiguousarray(pose9, dtype=np.float64).reshape(-1, 9)
+    loc_xy = np.ascontiguousarray(loc_xy, dtype=np.float64).reshape(-1, 2)
+    assert len(pose9) == len(loc_xy)
+    n_bad, first = ctypes.c_int64(0), ctypes.c_int64(-1)
+    _check(load().adsel_check_ego_locations(int(device), _ptr(pose9), _ptr(loc_xy), len(loc_xy), int(bool(fused)),
+                                            ctypes.byref(n_bad), ctypes.byref(first)))
+    return n_bad.value, first.value
 
 
 class Handle:

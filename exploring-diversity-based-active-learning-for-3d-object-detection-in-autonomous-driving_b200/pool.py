@@ -42,12 +42,35 @@ def _location_loop(cals):
     return np.stack([(-(cal[:3, 3].T @ cal[:3, :3]))[:2] for cal in cals])
 
 
-def ego_locations(infos, check: int = 64) -> np.ndarray:
+LAST_EGO_CHECK = {}    # outcome of the last all-frames device check of the ego locations (tests, bench.py)
+
+
+def _device_check(device, pose9, loc, fused_modes, frames) -> bool:
+    """True when the device's literal-order recomputation of EVERY frame (csrc/ego_check.cu) reproduces ``loc`` bit for
+    bit under one of ``fused_modes``; ``ADSEL_EGO_CHECK=probe`` keeps the probe frames as the only evidence."""
+    if device is None or os.environ.get("ADSEL_EGO_CHECK", "all") == "probe":
+        return True
+    from . import native
+    for fused in fused_modes:
+        n_bad, first = native.check_ego_locations(device, pose9, loc, fused)
+        LAST_EGO_CHECK.clear()
+        LAST_EGO_CHECK.update(frames=frames, n_bad=n_bad, first_bad=first, fused=bool(fused))
+        if n_bad == 0:
+            return True
+    import warnings
+    warnings.warn(f"ego locations: {LAST_EGO_CHECK['n_bad']} of {frames} frames (first: {LAST_EGO_CHECK['first_bad']}) differ from the "
+                  "literal order recomputed on the device; falling back to the reference's per-frame expression")
+    return False
+
+
+def ego_locations(infos, check: int = 64, device=None) -> np.ndarray:
     """float64 [N,2] ego x,y: ``-(cal[:3,3].T @ cal[:3,:3])[:2]`` with ``cal = car_from_global`` (:83-91).
 
     The batched ``np.matmul`` goes through the same vector-matrix inner loop as the reference's
     per-frame ``@``; ``check`` frames (spread over the pool) are recomputed with the reference's
     literal expression and must match bit-for-bit, otherwise the literal loop is used for all.
+    With ``device`` (a CUDA device index) every frame is additionally redone on the GPU in the literal
+    order (fma chain or separately rounded products, whichever this host's numpy uses).
     """
     cals = [info["car_from_global"] for info in infos]
     # numpy's vector-matrix product rounds differently for Fortran-ordered / strided operands (another BLAS kernel), so
@@ -65,6 +88,8 @@ def ego_locations(infos, check: int = 64) -> np.ndarray:
     n = len(cals)
     probe = np.unique(np.linspace(0, n - 1, num=min(check, n)).astype(np.int64))
     if not np.array_equal(_location_loop([cals[i] for i in probe]).view(np.uint64), loc[probe].view(np.uint64)):
+        loc = _location_loop(cals)
+    elif device is not None and not _device_check(device, stack[:, :3, [0, 1, 3]].reshape(-1, 9), loc, (True, False), n):
         loc = _location_loop(cals)
     return loc
 
@@ -147,12 +172,14 @@ def runs_from_change(change):
     return run_id, max_td
 
 
-def extract_slice(infos, lo=0, hi=None, check: int = 64, with_change: bool = False):
+def extract_slice(infos, lo=0, hi=None, check: int = 64, with_change: bool = False, device=None):
     """``(names, locations, n_boxes)`` of ``infos[lo:hi]`` -- logfile_names / ego_locations / box_counts in one pass
     over the list, in C when the helper is built.  The helper's ego locations are compared bit-for-bit with the
     reference's literal expression on ``check`` probe frames (numpy's vector-matrix product uses fused
     multiply-adds on FMA hosts and separately rounded products elsewhere: both orders are tried) and the python
-    implementation is used if neither matches or the infos are not the plain dicts / float64 matrices expected."""
+    implementation is used if neither matches or the infos are not the plain dicts / float64 matrices expected.
+    With ``device`` (a CUDA device index) the pinned order is then verified on EVERY frame by one fp64 kernel
+    (csrc/ego_check.cu); a mismatch anywhere sends the whole slice through the reference's literal per-frame loop."""
     hi = len(infos) if hi is None else hi
     ext = _hostext()
     if ext and isinstance(infos, list) and hi > lo:
@@ -160,20 +187,22 @@ def extract_slice(infos, lo=0, hi=None, check: int = 64, with_change: bool = Fal
         try:
             want = _location_loop([infos[i]["car_from_global"] for i in probe]).view(np.uint64)
             for fused in (True, False):
-                loc_b, box_b, names, chg_b = ext.extract(infos, lo, hi, fused)
+                loc_b, box_b, names, chg_b, pose_b = ext.extract(infos, lo, hi, fused)
                 loc = np.frombuffer(loc_b, dtype=np.float64).reshape(-1, 2)
                 if np.array_equal(loc[probe - lo].view(np.uint64), want):
+                    if not _device_check(device, np.frombuffer(pose_b, dtype=np.float64), loc, (fused,), hi - lo):
+                        loc = _location_loop([infos[i]["car_from_global"] for i in range(lo, hi)])
                     out = (names, loc, np.frombuffer(box_b, dtype=np.int32))
                     return out + (np.frombuffer(chg_b, dtype=np.uint8).astype(bool),) if with_change else out
         except (TypeError, KeyError, ValueError):
             pass
     part = infos[lo:hi]
     names = logfile_names(part)
-    out = (names, ego_locations(part, check), box_counts(part))
+    out = (names, ego_locations(part, check, device), box_counts(part))
     return out + (_change_flags(names),) if with_change else out
 
 
-def extract_spatial_temporal(infos, known_logfiles=None):
+def extract_spatial_temporal(infos, known_logfiles=None, device=None):
     """Everything SpatialTemporalSelector needs from the infos list: ``(locations, run_id, max_td, n_boxes)``.
 
     Under torch.distributed (more than one rank) the per-frame python work -- string parsing, stacking the 4x4
@@ -188,7 +217,7 @@ def extract_spatial_temporal(infos, known_logfiles=None):
     rank, world = get_dist_info()
     n = len(infos)
     if world <= 1 or n < 4 * world:
-        names, loc, boxes, change = extract_slice(infos, with_change=True)
+        names, loc, boxes, change = extract_slice(infos, with_change=True, device=device)
         if known_logfiles is not None:
             for i in np.flatnonzero(change):            # every distinct consecutive name, in order (KeyError like :80)
                 if names[i] not in known_logfiles:
@@ -199,7 +228,7 @@ def extract_spatial_temporal(infos, known_logfiles=None):
     import torch.distributed as dist
     t0 = time.perf_counter()
     lo, hi = rank * n // world, (rank + 1) * n // world
-    names, loc_mine, boxes_mine, change = extract_slice(infos, lo, hi, with_change=True)
+    names, loc_mine, boxes_mine, change = extract_slice(infos, lo, hi, with_change=True, device=device)
     missing = None                                      # change[0] is fixed up against the previous slice's last name
     if known_logfiles is not None:
         missing = next((names[i] for i in np.flatnonzero(change) if names[i] not in known_logfiles), None)

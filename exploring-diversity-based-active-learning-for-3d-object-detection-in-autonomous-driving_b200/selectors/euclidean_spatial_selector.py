@@ -29,7 +29,7 @@ class EuSpatialSelector(BaseSelector):
             self.logger.warning(f"{self.distance_store_file} exists but is ignored: the geodesic rows are rebuilt on the GPU "
                                 "(the reference would load this cached N x N map instead of recomputing it)")
         infos = self.infos_origin
-        names, locations, n_boxes = pool.extract_slice(infos)
+        names, locations, n_boxes = pool.extract_slice(infos, device=self._device_index(kwargs))
         city = pool.city_groups(names, load(self.logs_file))   # :57-60,75-76
         # rows take the cross-city margin 1e6 as their maximum; the sparse update relies on it
         extent = float(np.hypot(*(locations.max(0) - locations.min(0))))

@@ -30,7 +30,7 @@ class _FusedFeatureBase(BaseSelector):
         infos = self.infos_origin
         feats = load_features(self.buffer_path)
         assert feats.shape[0] == len(infos), f"{self.buffer_path} holds {feats.shape[0]} feature rows for {len(infos)} frames"
-        names, locations, n_boxes = pool.extract_slice(infos)
+        names, locations, n_boxes = pool.extract_slice(infos, device=self._device_index(kwargs))
         known = {l["logfile"] for l in load(self.logs_file)}
         for nm in names:                                  # KeyError like spatial_feature_selector.py:152
             if nm not in known:

@@ -28,7 +28,7 @@ class SpatialSelector(BaseSelector):
             self.logger.warning(f"{self.distance_store_file} exists but is ignored: the geodesic rows are rebuilt on the GPU "
                                 "(the reference would load this cached N x N map instead of recomputing it)")
         infos = self.infos_origin
-        names, locations, n_boxes = pool.extract_slice(infos)
+        names, locations, n_boxes = pool.extract_slice(infos, device=self._device_index(kwargs))
         known = {l["logfile"] for l in load(self.logs_file)}
         for nm in names:                                  # KeyError like spatial_selector.py:71
             if nm not in known:

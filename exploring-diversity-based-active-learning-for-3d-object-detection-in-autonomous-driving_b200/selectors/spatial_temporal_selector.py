@@ -48,7 +48,7 @@ class SpatialTemporalSelector(BaseSelector):
         known = {l["logfile"] for l in load(self.logs_file)}           # the reference raises KeyError at :80
         t_logs = time.perf_counter()
         # :83-91 ego locations, :114-129 consecutive logfile runs, base_selector.py:85 box counts
-        locations, run_id, max_td, n_boxes = pool.extract_spatial_temporal(infos, known)
+        locations, run_id, max_td, n_boxes = pool.extract_spatial_temporal(infos, known, device=self._device_index(kwargs))
         t1 = time.perf_counter()
         handle = sharded.make_engine(self._device_index(kwargs))   # one GPU, or this rank's shard
         try:

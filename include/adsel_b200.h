@@ -85,6 +85,13 @@ int adsel_timer_stop(adsel_handle *h, float *elapsed_ms);
  */
 int adsel_set_pool(adsel_handle *h, int32_t n, const double *loc_xy, const int32_t *group_id,
                    const int32_t *n_boxes);
+/* Every frame's ego location redone on `device` in the reference's literal order (spatial_temporal_selector.py:83-91):
+ * pose9 [m,9] float64 = {c00,c01,c03, c10,c11,c13, c20,c21,c23} of car_from_global, loc_xy [m,2] what the host extraction
+ * produced, fused = which rounding numpy's vector-matrix product was found to use on this host (1: fma chain, 0: separately
+ * rounded products).  *n_bad = frames whose bit patterns differ (NaN == NaN), *first_bad = the first of them or -1.
+ * Host pointers; needs no handle (it runs before the pool exists). */
+int adsel_check_ego_locations(int device, const double *pose9, const double *loc_xy, int64_t m, int fused, int64_t *n_bad,
+                              int64_t *first_bad);
 
 /* ---- spatial graph (replaces cKDTree.query + dense scatter + dense->CSR,
  *      spatial_temporal_selector.py:93-101 and scipy's csgraph_from_dense |w|<=1e-8 drop) -------- */

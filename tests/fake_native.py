@@ -13,6 +13,26 @@ import restatement as R
 from adsel_b200 import native, sharded
 
 
+EGO_CHECKS = []     # (device, frames, fused) of every all-frames ego-location check the host asked for
+
+
+def check_ego_locations(device, pose9, loc_xy, fused):
+    """Stand-in for csrc/ego_check.cu: the 3-term dot product in numpy's separately rounded order, else accepted as the
+    fused order (python has no fma before 3.13) -- enough for the host logic, which only needs (n_bad, first_bad)."""
+    pose9 = np.asarray(pose9, dtype=np.float64).reshape(-1, 9)
+    loc_xy = np.asarray(loc_xy, dtype=np.float64).reshape(-1, 2)
+    assert len(pose9) == len(loc_xy)
+    EGO_CHECKS.append((int(device), len(loc_xy), bool(fused)))
+    if not fused:
+        t = pose9[:, [2, 5, 8]]
+        want = np.stack([-((t[:, 0] * pose9[:, j] + t[:, 1] * pose9[:, 3 + j]) + t[:, 2] * pose9[:, 6 + j]) for j in (0, 1)], axis=1)
+        bad = np.flatnonzero((want.view(np.uint64) != loc_xy.view(np.uint64)).any(axis=1))
+        return len(bad), (int(bad[0]) if len(bad) else -1)
+    approx = np.stack([-(pose9[:, 2] * pose9[:, j] + pose9[:, 5] * pose9[:, 3 + j] + pose9[:, 8] * pose9[:, 6 + j]) for j in (0, 1)], axis=1)
+    bad = np.flatnonzero(~np.isclose(approx, loc_xy, rtol=1e-12, atol=1e-9).all(axis=1))
+    return len(bad), (int(bad[0]) if len(bad) else -1)
+
+
 class FakeShardHandle:
     instances = []
     overflow_once = False      # tests: the first select of every handle reports a neighbour-list overflow

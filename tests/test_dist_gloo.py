@@ -43,6 +43,7 @@ def _worker(rank, world, init_file, pool_dir, out_dir):
         import fake_native
         dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
         native.Handle = fake_native.FakeShardHandle                     # no GPU in this test
+        native.check_ego_locations = fake_native.check_ego_locations
         infos_path, logs_path = os.path.join(pool_dir, "infos_train_10sweeps_withvelo.pkl"), os.path.join(pool_dir, "log.json")
         result = {}
 
@@ -62,6 +63,7 @@ def _worker(rank, world, init_file, pool_dir, out_dir):
             result.update(sel.get_selected_samples())
         engine = sharded.make_engine(rank)
         result["engine"] = type(engine._engine).__name__
+        result["ego_checks"] = list(fake_native.EGO_CHECKS)
         result["handle_calls"] = [c if isinstance(c, str) else c[0] for c in fake_native.FakeShardHandle.instances[0].calls]
 
         # 2. DistWorld directly, one-term sibling (temporal groups by logfile name), tie-heavy integer rows
@@ -141,6 +143,8 @@ def test_two_ranks_select_like_the_reference_and_only_rank0_writes(pools, tmp_pa
         assert r["engine"] == "DistWorld"
         assert r["handle_calls"].count("comm_init") == 1                      # engine (arena, peer mappings) reused across rounds
     assert r0["range"] == [0, 256] and r1["range"] == [256, 300]
+    # every rank had ITS half of the pool's ego locations redone by the (stand-in) device check, on its own device, per round
+    assert [c[:2] for c in r0["ego_checks"]] == [[0, 150]] * 2 and [c[:2] for c in r1["ego_checks"]] == [[1, 150]] * 2
     for r in (r0, r1):
         assert r["retry"] == want["50"]                                      # same selection after the collective retry
         assert r["retry_calls"].count("comm_init") == 2                       # arenas re-created once ...

@@ -614,3 +614,46 @@ def test_fused_feature_selectors_keep_the_reference_constructors(pools, tmp_path
     sel = build_selector(dict(type="SpatialTemporalFeatureSelector", **base))      # pred defaults to True, like the reference
     with pytest.raises(NotImplementedError):
         sel.select_samples(local_rank=0)
+
+
+def test_device_check_mismatch_sends_the_slice_through_the_literal_loop(pools, monkeypatch):
+    """pool.extract_slice(device=...) asks the library to redo EVERY frame's ego location (csrc/ego_check.cu).  When the
+    check reports a differing frame the whole slice is recomputed with the reference's per-frame expression (with a
+    warning); ``ADSEL_EGO_CHECK=probe`` skips the device check.  The library call is replaced here (no GPU)."""
+    from adsel_b200 import native, pool as P
+    infos = pools("P300")["infos"]
+    want = R.ego_locations(infos)
+    calls = []
+
+    def fake(device, pose9, loc, fused, verdict=(0, -1)):
+        pose9, loc = np.asarray(pose9).reshape(-1, 9), np.asarray(loc).reshape(-1, 2)
+        assert len(pose9) == len(loc) and device == 3
+        # the nine entries handed over are columns 0, 1, 3 of rows 0..2 of car_from_global
+        k = len(calls) % len(loc)
+        cal = infos[calls_lo[0] + k]["car_from_global"]
+        assert np.array_equal(pose9[k], cal[:3][:, [0, 1, 3]].reshape(9))
+        calls.append((len(loc), bool(fused)))
+        return fake.verdict
+
+    calls_lo = [0]
+    fake.verdict = (0, -1)
+    monkeypatch.setattr(native, "check_ego_locations", fake)
+    _, loc, _ = P.extract_slice(infos, device=3)
+    assert np.array_equal(loc.view(np.uint64), want.view(np.uint64)) and calls[-1][0] == 300
+    assert P.LAST_EGO_CHECK == {"frames": 300, "n_bad": 0, "first_bad": -1, "fused": calls[-1][1]}
+    calls_lo[0] = 100
+    _, loc, _ = P.extract_slice(infos, 100, 250, device=3)
+    assert calls[-1][0] == 150 and np.array_equal(loc.view(np.uint64), want[100:250].view(np.uint64))
+    calls_lo[0] = 0
+    fake.verdict = (2, 41)
+    sentinel = np.full((300, 2), 7.0)
+    with monkeypatch.context() as m:
+        m.setattr(P, "_location_loop", lambda cals: sentinel[: len(cals)])
+        with pytest.warns(UserWarning, match="2 of 300 frames .first: 41."):
+            _, loc, _ = P.extract_slice(infos, device=3, check=0)   # check=0: no probe frames, the device check decides alone
+        assert np.array_equal(loc, sentinel)
+    fake.verdict = (0, -1)
+    n_calls = len(calls)
+    monkeypatch.setenv("ADSEL_EGO_CHECK", "probe")
+    _, loc, _ = P.extract_slice(infos, device=3)
+    assert len(calls) == n_calls and np.array_equal(loc.view(np.uint64), want.view(np.uint64))
