@@ -8,7 +8,7 @@ import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libadsel_b200.so")
-SOURCES = ["api.cu", "pool_device.cu", "ego_check.cu", "knn_graph.cu", "geodesic.cu", "greedy.cu", "lazy.cu", "fused.cu", "comm.cu", "bev.cu", "pairdist.cu", "featdist.cu"]
+SOURCES = ["api.cu", "pool_device.cu", "ego_check.cu", "knn_graph.cu", "geodesic.cu", "greedy.cu", "greedy_warp.cu", "lazy.cu", "fused.cu", "comm.cu", "bev.cu", "pairdist.cu", "featdist.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

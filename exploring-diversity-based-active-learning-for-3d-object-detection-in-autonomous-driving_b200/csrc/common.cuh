@@ -161,12 +161,13 @@ struct adsel_handle {
     // greedy state
     adsel::DevBuf<unsigned long long> fps;       // ordered-u64 view of non-negative doubles
     adsel::DevBuf<adsel::FrameRec> frame_rec;    // per-frame record read once per greedy step
+    adsel::DevBuf<unsigned char> slots;          // per-frame record + first entries of its neighbour list in one fixed-size slot (greedy_warp.cu)
     adsel::DevBuf<unsigned char> is_selected;
     adsel::DevBuf<double> tlut;
     adsel::DevBuf<int32_t> d_sampled, d_out;
     adsel::DevBuf<double> d_result;              // [0] cost, [1] status, [2] m, [3] steps, [4] offending frame
     int greedy_cluster = 0;                      // cluster size of the last greedy launch (0: global-memory variant)
-    int greedy_variant = 0;                      // kernel of the last selection: 0 global-memory, 1 fast resident CTA, 2 resident cluster, 3 lazy rows
+    int greedy_variant = 0;                      // kernel of the last selection: 0 global-memory, 1 fast resident CTA, 2 resident cluster, 3 lazy rows, 4 fused feature, 5 one-warp resident
     bool groups_contiguous = false;              // every group is one contiguous index range (consecutive runs)
 
     // pool sharding across ranks (comm.cu): this rank owns frames [shard_lo, shard_hi)
@@ -296,6 +297,30 @@ __device__ __forceinline__ double combine(int spatial, int temporal, int aggrega
     return spatial != ADSEL_SPATIAL_NONE ? s : t;
 }
 
+
+// Arguments of the greedy kernels (greedy.cu, greedy_warp.cu).
+struct GreedyArgs {
+    int n, nblk, lo, hi, blk_lo, blk_hi, tl_n, sel_words;
+    int csize, cta_cols, r_nblk;   // resident variant: CTAs per cluster, columns and blocks per CTA
+    int spatial, temporal, aggregate, groups_contiguous, pull;
+    double lambda_t, s_far, t_far;
+    double cost_b, cost_f, cost_start, budget;
+    int forbid_sampled, n_sampled, first_index, out_cap;
+    long long list_capacity;
+    unsigned long long far_bits;             // ordered key of the value every untouched row entry takes
+    const unsigned long long *list_cursor;   // [0] entries the list build needed (overflow check)
+    const FrameRec *rec;
+    const double2 *loc;
+    const int32_t *group_members;
+    const int32_t *list_idx;
+    const double *list_val, *tlut;
+    unsigned long long *fps;
+    unsigned char *is_selected;
+    const int32_t *sampled;
+    int32_t *out;
+    double *result;   // [0] cost, [1] status, [2] m, [3] steps, [4] offending frame, [5] list entries needed
+    unsigned long long *prof;   // PROFILE builds: clock64 cycles of thread 0 per phase
+};
 
 struct Win {
     unsigned hi, lo;

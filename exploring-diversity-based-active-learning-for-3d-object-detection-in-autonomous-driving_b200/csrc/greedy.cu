@@ -42,28 +42,6 @@ namespace adsel {
 constexpr int BLK = ADSEL_BLK;        // frames per block-max entry
 constexpr int MAX_BLKS = 9800;        // 20 B of shared memory per block + 32 KB LUT: n <= 1,254,400 frames
 
-struct GreedyArgs {
-    int n, nblk, lo, hi, blk_lo, blk_hi, tl_n, sel_words;
-    int csize, cta_cols, r_nblk;   // resident variant: CTAs per cluster, columns and blocks per CTA
-    int spatial, temporal, aggregate, groups_contiguous, pull;
-    double lambda_t, s_far, t_far;
-    double cost_b, cost_f, cost_start, budget;
-    int forbid_sampled, n_sampled, first_index, out_cap;
-    long long list_capacity;
-    unsigned long long far_bits;             // ordered key of the value every untouched row entry takes
-    const unsigned long long *list_cursor;   // [0] entries the list build needed (overflow check)
-    const FrameRec *rec;
-    const double2 *loc;
-    const int32_t *group_members;
-    const int32_t *list_idx;
-    const double *list_val, *tlut;
-    unsigned long long *fps;
-    unsigned char *is_selected;
-    const int32_t *sampled;
-    int32_t *out;
-    double *result;   // [0] cost, [1] status, [2] m, [3] steps, [4] offending frame, [5] list entries needed
-    unsigned long long *prof;   // PROFILE builds: clock64 cycles of thread 0 per phase
-};
 
 struct Best {
     unsigned long long v;
@@ -968,6 +946,9 @@ int lazy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *sa
 int lists_prepare(adsel_handle *h, bool sharded);
 int grow_lists(adsel_handle *h, long long needed);
 int comm_view(adsel_handle *h, CommView *view);
+int warp_prepare(adsel_handle *h, const adsel_select_params *p, bool sharded);
+int warp_preload();
+int warp_enqueue(adsel_handle *h, const adsel_select_params *p, GreedyArgs &a, bool sharded, bool *launched);
 
 static unsigned long long *greedy_prof_ptr() {
     static unsigned long long *buf = nullptr;
@@ -1042,9 +1023,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <int RB, int NT, bool CLUSTER, bool PROFILE>
 __global__ void __launch_bounds__(NT, 1) greedy_fast_kernel(const GreedyArgs a) {
-    constexpr int NW = NT / 32, PER = RB / 32, NSUB = RB / 32;   // the own block's NSUB sub-blocks are dealt out to the NW warps
-    constexpr int SHIFT = RB == 256 ? 8 : 7;
-    static_assert(RB == 128 || RB == 256, "block size");
+    // Blocks of RB frames; the row's own block is re-reduced as NSUB sub-blocks of SUBF frames dealt out to the NW warps.
+    // RB = 512 halves the number of block maxima every warp scans at the end of a step (55 at 28,130 frames: two per lane).
+    constexpr int NW = NT / 32, PER = RB / 32, SUBF = RB == 512 ? 64 : 32, NSUB = RB / SUBF, SPL = SUBF / 32;
+    constexpr int SHIFT = RB == 512 ? 9 : RB == 256 ? 8 : 7;
+    constexpr int QB = RB == 512 ? 2 : 4;   // block maxima per lane and pass of the final arg-max
+    static_assert(RB == 128 || RB == 256 || RB == 512, "block size");
+    static_assert(NSUB <= 8, "FastShared holds eight sub-block slots");
     unsigned long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long prof_t = PROFILE ? clock64() : 0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1322,11 +1307,18 @@ __global__ void __launch_bounds__(NT, 1) greedy_fast_kernel(const GreedyArgs a) 
             }
             const int ref_blk = cur_blk;   // -1: nothing was applied in this iteration (seeding)
             for (int sb = wid; sb < NSUB && ref_blk >= 0; sb += NW) {
-                const int lj = (ref_blk << SHIFT) + 32 * sb + lane;
-                const unsigned long long v = fps_s[lj];
-                unsigned hi[1] = {(unsigned)(v >> 32)}, lo[1] = {(unsigned)v};
-                int idx[1] = {lj < c_len ? c_lo + lj : 0x7fffffff};
-                const Win x = warp_argmax<1>(hi, lo, idx);
+                const int lj0 = (ref_blk << SHIFT) + SUBF * sb + lane;
+                unsigned hi[SPL], lo[SPL];
+                int idx[SPL];
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) {
+                    const int lj = lj0 + 32 * i;
+                    const unsigned long long v = fps_s[lj];
+                    hi[i] = (unsigned)(v >> 32);
+                    lo[i] = (unsigned)v;
+                    idx[i] = lj < c_len ? c_lo + lj : 0x7fffffff;
+                }
+                const Win x = warp_argmax<SPL>(hi, lo, idx);
                 if (lane == 0) {
                     sh.sub_val[sb] = ((unsigned long long)x.hi << 32) | x.lo;
                     sh.sub_idx[sb] = x.idx;
@@ -1359,11 +1351,11 @@ __global__ void __launch_bounds__(NT, 1) greedy_fast_kernel(const GreedyArgs a) 
             Win y;
             y.hi = y.lo = 0u;
             y.idx = 0x7fffffff;
-            for (int b0 = 0; b0 < nblk; b0 += 4 * 32) {   // uniform trip count: the REDUX inside need every lane
-                unsigned hi[5], lo[5];
-                int idx[5];
+            for (int b0 = 0; b0 < nblk; b0 += QB * 32) {   // uniform trip count: the REDUX inside need every lane
+                unsigned hi[QB + 1], lo[QB + 1];
+                int idx[QB + 1];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < QB; ++q) {
                     const int b = b0 + lane + 32 * q;
                     const bool ok = b < nblk && b != ref_blk;
                     const unsigned long long v = ok ? blk_val[b] : 0ull;
@@ -1371,12 +1363,12 @@ __global__ void __launch_bounds__(NT, 1) greedy_fast_kernel(const GreedyArgs a) 
                     lo[q] = (unsigned)v;
                     idx[q] = ok ? blk_idx[b] : 0x7fffffff;
                 }
-                hi[4] = b0 == 0 ? shi : 0u;
-                lo[4] = b0 == 0 ? slo : 0u;
-                idx[4] = b0 == 0 ? sidx : 0x7fffffff;
-                if (PROFILE) asm volatile("" ::"r"(hi[0] + hi[3] + idx[0] + idx[3]));
+                hi[QB] = b0 == 0 ? shi : 0u;
+                lo[QB] = b0 == 0 ? slo : 0u;
+                idx[QB] = b0 == 0 ? sidx : 0x7fffffff;
+                if (PROFILE) asm volatile("" ::"r"(hi[0] + hi[QB - 1] + idx[0] + idx[QB - 1]));
                 FPROF(9)
-                const Win w = warp_argmax<5>(hi, lo, idx);
+                const Win w = warp_argmax<QB + 1>(hi, lo, idx);
                 const bool take = w.hi > y.hi || (w.hi == y.hi && (w.lo > y.lo || (w.lo == y.lo && w.idx < y.idx)));
                 if (take) y = w;
             }
@@ -1447,7 +1439,7 @@ __global__ void __launch_bounds__(NT, 1) greedy_fast_kernel(const GreedyArgs a) 
             if (cur_blk < 0) {   // CLUSTER only: one global round trip (the owner's cache is not visible from here)
                 ldg_rec_async(recs + nxt, rlo, rhi);
             } else if (cur_blk == ref_blk) {
-                const int w = ((nxt - c_lo) >> 5) & (NSUB - 1);
+                const int w = ((nxt - c_lo) & (RB - 1)) / SUBF;
                 while (true) {
                     rlo = lds128_volatile(&sh.sub_rec[w][0]);
                     rhi = lds128_volatile(&sh.sub_rec[w][1]);
@@ -1661,12 +1653,15 @@ static cudaError_t dispatch_fast(adsel_handle *h, const GreedyArgs &a, const Fas
         return t128 ? launch_fast<256, 128, true, false>(h, a, pl.smem, dry_run, max_clusters)
                     : launch_fast<256, 256, true, false>(h, a, pl.smem, dry_run, max_clusters);
     }
-    if (a.prof) return pl.rb == 128 ? launch_fast<128, 256, false, true>(h, a, pl.smem, dry_run, max_clusters)
-                                    : launch_fast<256, 256, false, true>(h, a, pl.smem, dry_run, max_clusters);
-    if (t128) return pl.rb == 128 ? launch_fast<128, 128, false, false>(h, a, pl.smem, dry_run, max_clusters)
-                                  : launch_fast<256, 128, false, false>(h, a, pl.smem, dry_run, max_clusters);
-    return pl.rb == 128 ? launch_fast<128, 256, false, false>(h, a, pl.smem, dry_run, max_clusters)
-                        : launch_fast<256, 256, false, false>(h, a, pl.smem, dry_run, max_clusters);
+    if (a.prof) return pl.rb == 128   ? launch_fast<128, 256, false, true>(h, a, pl.smem, dry_run, max_clusters)
+                       : pl.rb == 256 ? launch_fast<256, 256, false, true>(h, a, pl.smem, dry_run, max_clusters)
+                                      : launch_fast<512, 256, false, true>(h, a, pl.smem, dry_run, max_clusters);
+    if (t128) return pl.rb == 128   ? launch_fast<128, 128, false, false>(h, a, pl.smem, dry_run, max_clusters)
+                     : pl.rb == 256 ? launch_fast<256, 128, false, false>(h, a, pl.smem, dry_run, max_clusters)
+                                    : launch_fast<512, 128, false, false>(h, a, pl.smem, dry_run, max_clusters);
+    return pl.rb == 128   ? launch_fast<128, 256, false, false>(h, a, pl.smem, dry_run, max_clusters)
+           : pl.rb == 256 ? launch_fast<256, 256, false, false>(h, a, pl.smem, dry_run, max_clusters)
+                          : launch_fast<512, 256, false, false>(h, a, pl.smem, dry_run, max_clusters);
 }
 
 // The lean step (greedy_fast_kernel): no Euclid term, contiguous temporal groups, the whole pool on this device, its
@@ -1684,11 +1679,15 @@ static bool plan_fast(adsel_handle *h, GreedyArgs &a, bool sharded, int g_want, 
     const size_t budget = 232448 - 512;   // 227 KB opt-in maximum per CTA minus the static shared variables (FastShared: 400 B)
     for (int cs = 1; cs <= CLUSTER_MAX; cs *= 2) {
         if (forced > 0 && cs != forced) continue;
-        for (int rb = 128; rb <= 256; rb *= 2) {
+        const char *rbe = getenv("ADSEL_FAST_BLOCK");   // 128/256/512: frames per block (measurement aid)
+        const int rb_forced = rbe ? atoi(rbe) : 0;
+        for (int rb = 128; rb <= 512; rb *= 2) {
             if (cs > 1 && rb != 256) continue;
             long long cols = ((long long)a.n + cs - 1) / cs;
             cols = (cols + rb - 1) / rb * rb;
             const long long nblk = cols / rb;
+            // one CTA: the smallest block size whose maxima are at most two per lane in the step's final arg-max (<= 64 blocks)
+            if (cs == 1 && (rb_forced ? rb != rb_forced : (rb < 512 && nblk > 64))) continue;
             const size_t fixed = (size_t)cols * 8 + (size_t)nblk * (8 + 32 + 4 + 8 + 4) + 8;
             if (fixed > budget) continue;
             long long g = (long long)((budget - fixed) / 8);
@@ -1753,6 +1752,7 @@ int greedy_preload() {
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_select_kernel<1024, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<128, 256, false, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, 256, false, false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<512, 256, false, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_fast_kernel<256, 256, true, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<128, false, false>));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_resident_kernel<256, false, false>));
@@ -1760,6 +1760,7 @@ int greedy_preload() {
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, temporal_lut_kernel));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, fill_u64_kernel2));
     ADSEL_CUDA(cudaFuncGetAttributes(&attr, frame_rec_kernel));
+    ADSEL_TRY(warp_preload());
     return ADSEL_OK;
 }
 
@@ -1798,6 +1799,7 @@ int greedy_prepare(adsel_handle *h, const adsel_select_params *p, int32_t n_samp
     ADSEL_TRY(h->d_sampled.reserve(n_sampled > 0 ? n_sampled : 1));
     ADSEL_TRY(h->d_out.reserve(out_cap));
     ADSEL_TRY(h->d_result.reserve(8));
+    ADSEL_TRY(warp_prepare(h, p, false));   // (a replicated multi-rank selection runs the single-device kernels too)
     return ADSEL_OK;
 }
 
@@ -1902,7 +1904,10 @@ static int enqueue_greedy(adsel_handle *h, const adsel_select_params *p, const i
     FastPlan fast;
     const int tl_want = a.temporal ? (p->normalize == ADSEL_NORM_EXP && a.tl_n > 64 ? 64 : a.tl_n) : 0;
     const int tl_all = a.tl_n, sel_all = a.sel_words;
-    if (plan_fast(h, a, sharded, tl_want, &fast)) {   // resident in one CTA or a cluster, lean step
+    bool warp_launched = false;
+    ADSEL_TRY(warp_enqueue(h, p, a, sharded, &warp_launched));   // one warp on resident columns (greedy_warp.cu)
+    if (warp_launched) {
+    } else if (plan_fast(h, a, sharded, tl_want, &fast)) {   // resident in one CTA or a cluster, lean step
         ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n * fast.csize, h->stream));
         int unused = 0;
         ADSEL_CUDA(dispatch_fast(h, a, fast, false, &unused));
@@ -1985,6 +1990,11 @@ int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *
             unsigned long long prof[16];
             cudaMemcpy(prof, greedy_prof_ptr(), sizeof(prof), cudaMemcpyDeviceToHost);
             const double steps = result[3] > 0 ? result[3] : 1;
+            if (h->greedy_variant == 5)
+                fprintf(stderr, "[warp profile] cycles/step: issue %.0f | finalise %.0f | spec group %.0f | slot wait %.0f | accept+group %.0f | list %.0f | "
+                                "dirty blocks %.0f | loads+tree %.0f | redux %.0f\n",
+                        prof[6] / steps, prof[7] / steps, prof[0] / steps, prof[1] / steps, prof[8] / steps, prof[2] / steps, prof[3] / steps,
+                        prof[4] / steps, prof[5] / steps);
             if (h->greedy_variant == 1)
                 fprintf(stderr, "[fast profile] cycles/step: issue+group %.0f | bar0 %.0f | list lower %.0f | pend+flags %.0f | bar1 %.0f | "
                                 "refresh loads %.0f | refresh argmax %.0f | refresh store %.0f | bar2 %.0f | reduce loads %.0f | reduce argmax %.0f | bookkeeping %.0f\n",

@@ -1,0 +1,490 @@
+// greedy_warp.cu -- the greedy k-center loop (spatial_temporal_selector.py:157-193) as ONE WARP on resident columns.
+//
+// What a step of the headline configuration touches is tiny: the selected frame's truncated geodesic neighbourhood
+// (24 entries on average at 28,130 frames, 3.5 % of the rows longer than 64), at most 2 x 38 - 1 frames of its temporal
+// group (the exp-normalised LUT saturates at 38 frames), one 512-frame block to re-reduce and 55 block maxima.  The
+// multi-warp kernels (greedy.cu) spend their step on keeping 8 warps in step: three CTA barriers, a record cache so that
+// the row's list address is known without a second L2 round trip, redundant reductions in every warp -- 2,670 cycles
+// per step of which ~350 are the one L2 round trip.  Here
+//   * one warp owns the loop: no CTA barrier, no broadcast, every piece of state is a register of all 32 lanes;
+//   * the frame record and the first 64 entries of its neighbour list sit in ONE fixed-size slot per frame
+//     (slot_build_kernel, 800 B): address = frame x 800, so the step's only L2 round trip starts the moment the
+//     winner is known -- no record cache, no cp.async, no polling.  Longer lists continue in the list pool (a second,
+//     dependent round trip, on 3.5 % of the steps);
+//   * everything that does not need the slot runs in the shadow of its load: the candidates of the temporal group
+//     (index window around the winner, values from a shared-memory LUT, the comparison with fps and the "is this
+//     the block's maximum" test) are evaluated speculatively and only masked by the group bounds when the header
+//     arrives; the previous step's own-block maximum is finalised (three REDUX on registers) there too;
+//   * the final arg-max is one pass: 16 entries of the row's own block + 2 block maxima per lane, a per-lane
+//     compare/select tree, three REDUX.
+// Bit-exact like the other kernels: the same minima, np.argmax's first-maximum rule, the same rounded cost sums.
+#include "common.cuh"
+
+namespace adsel {
+
+constexpr int WARP_K = 64;                          // list entries held in a slot (two per lane)
+constexpr int WARP_SLOT = 32 + WARP_K * 12;         // header (32 B) | idx[K] int32 | val[K] float64
+constexpr int WARP_RB = 512, WARP_SHIFT = 9, WARP_PER = WARP_RB / 32;
+constexpr int WARP_SPEC = 3;                        // speculative group candidates per lane: window of 96 >= 2 * sat - 1
+
+__global__ void slot_build_kernel(unsigned char *__restrict__ slots, const FrameRec *__restrict__ rec,
+                                  const int32_t *__restrict__ lidx, const double *__restrict__ lval, int n, long long capacity,
+                                  const unsigned long long *__restrict__ cursor) {
+    const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const FrameRec r = rec[w];
+    unsigned char *s = slots + (size_t)w * WARP_SLOT;
+    if (lane == 0) {
+        *reinterpret_cast<uint4 *>(s) = make_uint4((unsigned)r.list_off, (unsigned)((unsigned long long)r.list_off >> 32),
+                                                    (unsigned)r.list_len, (unsigned)w);
+        *reinterpret_cast<uint4 *>(s + 16) = make_uint4((unsigned)r.e0, (unsigned)r.e1, (unsigned)r.n_boxes, (unsigned)w);
+    }
+    if (lidx == nullptr || (cursor && (long long)*cursor > capacity)) return;   // overflowed pool: the greedy kernel reports it
+    int32_t *si = reinterpret_cast<int32_t *>(s + 32);
+    double *sv = reinterpret_cast<double *>(s + 32 + 4 * WARP_K);
+    const int len = min(r.list_len, WARP_K);
+    for (int t = lane; t < len; t += 32) {
+        si[t] = lidx[r.list_off + t];
+        sv[t] = lval[r.list_off + t];
+    }
+}
+
+__device__ __forceinline__ uint4 ldg_v4(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_s32(const void *p) {
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ldg_u64(const void *p) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// shared memory by 32-bit shared-window address; a conditional store is ONE predicated STS
+__device__ __forceinline__ unsigned long long lds64(unsigned addr) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64_if(unsigned addr, unsigned long long v, bool p) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.u64 [%0], %1;\n}" ::"r"(addr), "l"(v), "r"((unsigned)p) : "memory");
+}
+__device__ __forceinline__ void sts32_if(unsigned addr, int v, bool p) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.s32 [%0], %1;\n}" ::"r"(addr), "r"(v), "r"((unsigned)p) : "memory");
+}
+
+struct Cand {   // a 64-bit key with its frame
+    unsigned long long k;
+    int i;
+};
+// b comes after a in index order: it wins only with a strictly larger key (np.argmax keeps the first maximum)
+__device__ __forceinline__ Cand later_wins_if_larger(const Cand a, const Cand b) { return b.k > a.k ? b : a; }
+__device__ __forceinline__ Cand better_of(const Cand a, const Cand b) { return (b.k > a.k || (b.k == a.k && b.i < a.i)) ? b : a; }
+
+#define WPROF(slot) WPROF_DEP(slot, 0)
+// the clock is read after `dep` is available (a register the preceding phase produces)
+#define WPROF_DEP(slot, dep)                                                                                         \
+    if (PROFILE) {                                                                                                   \
+        long long now;                                                                                               \
+        asm volatile("{\n.reg .b32 t;\nmov.b32 t, %1;\nmov.u64 %0, %%clock64;\n}" : "=l"(now) : "r"((int)(dep)) : "memory"); \
+        prof_acc[slot] += (unsigned long long)(now - prof_t);                                                        \
+        prof_t = now;                                                                                                \
+    }
+
+template <bool PROFILE>
+__global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, const unsigned char *__restrict__ slots) {
+    constexpr int SHIFT = WARP_SHIFT, PER = WARP_PER, K = WARP_K;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    unsigned long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_t = PROFILE ? clock64() : 0;
+
+    const int n = a.n, cols = a.cta_cols, nblk = a.r_nblk, G = a.tl_n, out_cap = a.out_cap;
+    const int32_t *const lidx = a.list_idx;
+    const double *const lval = a.list_val;
+    int32_t *const out = a.out;
+    unsigned char *const sel_bytes = a.is_selected;
+    const double budget = a.budget, cost_f = a.cost_f, cost_b = a.cost_b;
+    const bool has_group = a.temporal != 0;
+
+    extern __shared__ unsigned long long warp_smem[];
+    unsigned long long *fps_s = warp_smem;              // [cols]   min distance to the selected set, ordered-u64 keys
+    unsigned long long *blk_val = fps_s + cols;         // [nblk]   maximum of every 512-frame block
+    unsigned long long *gval = blk_val + nblk;          // [G]      row value of a group member at index gap d
+    int *blk_idx = reinterpret_cast<int *>(gval + G);   // [nblk]   frame holding it (lowest index among equals)
+
+    const unsigned long long far_bits = a.far_bits;
+    for (int i = lane; i < cols; i += 32) fps_s[i] = i < n ? far_bits : 0ull;
+    for (int d = lane; d < G; d += 32)
+        gval[d] = (unsigned long long)__double_as_longlong(combine(a.spatial, a.temporal, a.aggregate, a.lambda_t, a.s_far, a.tlut[d]));
+    for (int lb = lane; lb < nblk; lb += 32) {   // every entry starts at `far`: a block's best is its first frame
+        const bool nonempty = (lb << SHIFT) < n;
+        blk_val[lb] = nonempty ? far_bits : 0ull;
+        blk_idx[lb] = nonempty ? (lb << SHIFT) : 0x7fffffff;
+    }
+    // Saturation of the temporal LUT: for d >= sat, tlut[d] equals the far value bit for bit (exp: 38).
+    int sat = 0x3fffffff;
+    if (has_group) {
+        const int lim = min(n, 4096);
+        const unsigned long long tfar = (unsigned long long)__double_as_longlong(a.t_far);
+        int mx = 0;
+        for (int d = lane; d < lim; d += 32)
+            if ((unsigned long long)__double_as_longlong(a.tlut[d]) != tfar) mx = d + 1;
+        mx = __reduce_max_sync(FULL, mx);
+        sat = mx >= lim ? 0x3fffffff : mx;
+    }
+    const bool spec_group = has_group && 2 * sat - 1 <= 32 * WARP_SPEC && sat <= G;
+    __syncwarp();
+
+    double cost = a.cost_start;
+    int m = 0, stop = 0, err_frame = -1;
+    long long steps = 0;
+    bool marking = true;
+
+    // Re-reduce one block from shared memory (other blocks whose maximum was lowered: 2 % of the steps; seeding).
+    auto refresh_block = [&](int lb) {
+        const int base = (lb << SHIFT) + lane;
+        unsigned hi[PER], lo[PER];
+        int idx[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const unsigned long long v = fps_s[base + 32 * i];
+            hi[i] = (unsigned)(v >> 32);
+            lo[i] = (unsigned)v;
+            idx[i] = base + 32 * i < n ? base + 32 * i : 0x7fffffff;
+        }
+        const Win x = warp_argmax<PER>(hi, lo, idx);
+        if (lane == 0) {
+            blk_val[lb] = ((unsigned long long)x.hi << 32) | x.lo;
+            blk_idx[lb] = x.idx;
+        }
+    };
+
+    bool local_abort = false;
+    {
+        const unsigned long long needed = a.list_cursor ? *a.list_cursor : 0ull;
+        if (lane == 0) a.result[5] = (double)needed;
+        if ((long long)needed > a.list_capacity) {   // neighbour-list pool too small: the host grows it and reruns
+            local_abort = true;
+            if (lane == 0) {
+                a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                a.result[4] = -1.0;
+            }
+        }
+    }
+
+    // mode of the frame at the top of the loop: 0 = row of a frame already in the buffer (applied only), 1 = taken
+    // unconditionally (the caller's first frame / the first pick after seeding, :165-174), 2 = candidate (:182-189)
+    int mode = 1, cur = a.first_index, t_sampled = 0;
+    if (!local_abort) {
+        if (a.forbid_sampled && lane == 0)
+            for (int t = 0; t < a.n_sampled; ++t) sel_bytes[a.sampled[t]] = 1;
+        if (a.n_sampled > 0) {
+            mode = 0;
+            cur = a.sampled[0];
+            marking = false;
+        }
+    }
+    int cur_blk = cur >> SHIFT, prev_blk = -1;
+    Cand part{0ull, 0x7fffffff};   // this lane's best of the previous row's own block (finalised lazily)
+    // Shared memory through explicit 32-bit shared-window addresses: generic pointers make the compiler rebuild the window
+    // base (S2UR SR_CgaCtaId + ULEA) in front of every access, and `if (...) smem[j] = v` becomes a divergent branch;
+    // here a conditional store is one predicated STS and the loop body is straight-line code.
+    const unsigned s_fps = (unsigned)__cvta_generic_to_shared(fps_s), s_bval = (unsigned)__cvta_generic_to_shared(blk_val),
+                   s_gval = (unsigned)__cvta_generic_to_shared(gval), s_bidx = (unsigned)__cvta_generic_to_shared(blk_idx);
+    const int sat1 = sat - 1;
+
+    while (!local_abort) {
+        unsigned long long dirty = 0ull;
+        // ---- 1. the slot: header + the first 64 list entries, one L2 round trip ----
+        const unsigned char *sp = slots + (size_t)cur * WARP_SLOT;
+        const uint4 h0 = ldg_v4(sp), h1 = ldg_v4(sp + 16);
+        const int j0 = ldg_s32(sp + 32 + 4 * lane), j1 = ldg_s32(sp + 32 + 4 * (lane + 32));
+        const unsigned long long v0 = ldg_u64(sp + 32 + 4 * K + 8 * lane), v1 = ldg_u64(sp + 32 + 4 * K + 8 * (lane + 32));
+        unsigned flag_seen = 0;
+        if (mode == 2 && lane == 0) flag_seen = __ldcg(sel_bytes + cur);
+        WPROF(6)
+        // ---- 2. in its shadow ----
+        // (a) the previous row's own block gets its maximum, unless this row re-reduces the same block anyway
+        if (prev_blk >= 0 && prev_blk != cur_blk) {
+            unsigned hi1[1] = {(unsigned)(part.k >> 32)}, lo1[1] = {(unsigned)part.k};
+            int idx1[1] = {part.i};
+            const Win x = warp_argmax<1>(hi1, lo1, idx1);
+            sts64_if(s_bval + 8u * prev_blk, ((unsigned long long)x.hi << 32) | x.lo, lane == 0);
+            sts32_if(s_bidx + 4u * prev_blk, x.idx, lane == 0);
+            __syncwarp();
+        }
+        WPROF(7)
+        // (b) temporal group, speculatively: the frames within the LUT's reach of cur, whatever the group's bounds are
+        int gj[WARP_SPEC];
+        unsigned long long gv[WARP_SPEC];
+        bool gneed[WARP_SPEC] = {false, false, false}, gmax[WARP_SPEC] = {false, false, false};
+        if (spec_group) {
+            unsigned long long old[WARP_SPEC];
+            int bi[WARP_SPEC];
+#pragma unroll
+            for (int q = 0; q < WARP_SPEC; ++q) {
+                const int j = cur - sat1 + lane + 32 * q;
+                const int d = abs(j - cur);
+                const bool valid = (unsigned)j < (unsigned)n && d < sat;
+                gj[q] = valid ? j : cur;
+                gv[q] = lds64(s_gval + 8u * (valid ? d : 0));
+                old[q] = lds64(s_fps + 8u * gj[q]);
+                bi[q] = lds32(s_bidx + 4u * (gj[q] >> SHIFT));
+                gneed[q] = valid;
+            }
+#pragma unroll
+            for (int q = 0; q < WARP_SPEC; ++q) {
+                gneed[q] = gneed[q] && gv[q] < old[q];
+                gmax[q] = marking && (gj[q] >> SHIFT) != cur_blk && bi[q] == gj[q];
+            }
+        }
+        WPROF_DEP(0, (int)gneed[0] + (int)gmax[WARP_SPEC - 1])
+        // ---- 3. the header is here ----
+        const long long l_off = (long long)(((unsigned long long)h0.y << 32) | h0.x);
+        const int l_len = (int)h0.z, e0 = (int)h1.x, e1 = (int)h1.y;
+        const double box_cost = __dmul_rn((double)(int)h1.z, cost_b);   // n_boxes * cost_b, one rounded product (base_selector.py:85)
+        asm volatile("" ::"r"(h0.w), "r"(h1.w));   // (keeps the unused words' registers from being recycled while the load is in flight)
+        WPROF_DEP(1, l_len + e0 + j0 + j1 + (int)v0 + (int)v1)
+        if (mode == 2) {
+            flag_seen = __shfl_sync(FULL, flag_seen, 0);
+            cost = __dadd_rn(cost, cost_f);        // :184
+            cost = __dadd_rn(cost, box_cost);      // :185
+            const bool over = cost > budget;       // :186
+            const bool full = !over && m >= out_cap;
+            if (flag_seen) {                       // :182 comes before the cost test
+                err_frame = cur;
+                stop = 2;
+                break;
+            }
+            if (over || full) {
+                if (full && lane == 0) {
+                    a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                    a.result[4] = -2.0;
+                }
+                stop = over ? 1 : 2;
+                break;
+            }
+        } else if (mode == 1) {                    // :168,172-174 -- taken and costed up front, no budget check
+            cost = __dadd_rn(cost, cost_f);
+            cost = __dadd_rn(cost, box_cost);
+        }
+        if (mode != 0) {
+            if (lane == 0) {
+                out[m] = cur;
+                sel_bytes[cur] = 1;
+            }
+            m += 1;
+        }
+        // group entries first, list entries second: list values of same-group frames are <= the group values
+        if (spec_group) {
+#pragma unroll
+            for (int q = 0; q < WARP_SPEC; ++q) {
+                const bool w = gneed[q] && gj[q] >= e0 && gj[q] < e1;
+                sts64_if(s_fps + 8u * gj[q], gv[q], w);
+                if (w && gmax[q]) dirty |= 1ull << (gj[q] >> SHIFT);
+            }
+        } else if (has_group) {
+            const int g0 = max(e0, cur - sat + 1), g1 = min(e1, cur + sat);
+            for (int j = g0 + lane; j < g1; j += 32) {
+                const int d = abs(j - cur);
+                const unsigned long long v = d < G ? gval[d]
+                    : (unsigned long long)__double_as_longlong(combine(a.spatial, a.temporal, a.aggregate, a.lambda_t, a.s_far, a.tlut[d]));
+                if (v < fps_s[j]) {
+                    fps_s[j] = v;
+                    const int lb = j >> SHIFT;
+                    if (lb != cur_blk && marking && blk_idx[lb] == j) dirty |= 1ull << lb;
+                }
+            }
+        }
+        __syncwarp();
+        WPROF_DEP(8, (int)dirty)
+        {   // the slot's 64 entries: two per lane, straight-line
+            const bool p0 = lane < l_len, p1 = lane + 32 < l_len;
+            const int c0 = p0 ? j0 : cur, c1 = p1 ? j1 : cur;
+            const unsigned long long o0 = lds64(s_fps + 8u * c0), o1 = lds64(s_fps + 8u * c1);
+            const int b0 = lds32(s_bidx + 4u * (c0 >> SHIFT)), b1 = lds32(s_bidx + 4u * (c1 >> SHIFT));
+            const bool w0 = p0 && v0 < o0, w1 = p1 && v1 < o1;
+            sts64_if(s_fps + 8u * c0, v0, w0);
+            sts64_if(s_fps + 8u * c1, v1, w1);
+            if (w0 && marking && (c0 >> SHIFT) != cur_blk && b0 == c0) dirty |= 1ull << (c0 >> SHIFT);
+            if (w1 && marking && (c1 >> SHIFT) != cur_blk && b1 == c1) dirty |= 1ull << (c1 >> SHIFT);
+        }
+        if (l_len > K) {   // rows longer than a slot continue in the list pool (3.5 % of the rows)
+            for (int t = K + lane; t < l_len; t += 32) {
+                const int j = lidx[l_off + t];
+                const unsigned long long v = (unsigned long long)__double_as_longlong(lval[l_off + t]);
+                if (v < fps_s[j]) {
+                    fps_s[j] = v;
+                    const int lb = j >> SHIFT;
+                    if (lb != cur_blk && marking && blk_idx[lb] == j) dirty |= 1ull << lb;
+                }
+            }
+        }
+        __syncwarp();
+        WPROF_DEP(2, (int)dirty)
+        if (mode == 0) {   // next row of the buffer; after the last one every block maximum from scratch, then the first pick
+            t_sampled += 1;
+            if (t_sampled < a.n_sampled) {
+                cur = a.sampled[t_sampled];
+                cur_blk = cur >> SHIFT;
+                continue;
+            }
+            marking = true;
+            for (int lb = 0; lb < nblk; ++lb) refresh_block(lb);
+            __syncwarp();
+            cur_blk = -1;
+            prev_blk = -1;
+        }
+        // ---- 4. other blocks whose maximum was lowered (2 % of the steps) ----
+        if (__any_sync(FULL, dirty != 0ull)) {
+            unsigned dlo = __reduce_or_sync(FULL, (unsigned)dirty), dhi = __reduce_or_sync(FULL, (unsigned)(dirty >> 32));
+            while (dlo) {
+                refresh_block(__ffs(dlo) - 1);
+                dlo &= dlo - 1;
+            }
+            while (dhi) {
+                refresh_block(32 + __ffs(dhi) - 1);
+                dhi &= dhi - 1;
+            }
+            __syncwarp();
+        }
+        WPROF(3)
+        // ---- 5. arg-max: the row's own block from its 512 entries, every other block from its maximum ----
+        Cand bm[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int b = lane + 32 * q;
+            const bool ok = b < nblk && b != cur_blk;
+            const unsigned long long k = lds64(s_bval + 8u * (ok ? b : 0));
+            const int i = lds32(s_bidx + 4u * (ok ? b : 0));
+            bm[q].k = ok ? k : 0ull;
+            bm[q].i = ok ? i : 0x7fffffff;
+        }
+        Cand own{0ull, 0x7fffffff};
+        if (cur_blk >= 0) {
+            const int base = (cur_blk << SHIFT) + lane;
+            Cand c[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                c[i].k = lds64(s_fps + 8u * (base + 32 * i));
+                c[i].i = base + 32 * i;
+            }
+#pragma unroll
+            for (int w = 1; w < PER; w *= 2)
+#pragma unroll
+                for (int i = 0; i + w < PER; i += 2 * w) c[i] = later_wins_if_larger(c[i], c[i + w]);
+            own = c[0];
+            if (own.i >= n) own.i = 0x7fffffff;   // padding of the last block (key 0): never before a real frame
+        }
+        part = own;
+        const Cand best = better_of(own, better_of(bm[0], bm[1]));
+        WPROF_DEP(4, (int)best.k + best.i)
+        unsigned hi1[1] = {(unsigned)(best.k >> 32)}, lo1[1] = {(unsigned)best.k};
+        int idx1[1] = {best.i};
+        const Win y = warp_argmax<1>(hi1, lo1, idx1);
+        WPROF_DEP(5, y.idx)
+        ++steps;
+        const int nxt = y.idx;
+        if (nxt < 0 || nxt >= n) {   // empty pool: cannot happen with n > 0
+            if (lane == 0) a.result[1] = (double)ADSEL_ERR_INVALID;
+            stop = 2;
+            break;
+        }
+        prev_blk = cur_blk;
+        mode = mode == 0 ? 1 : 2;
+        cur = nxt;
+        cur_blk = nxt >> SHIFT;
+    }
+    __syncwarp();
+    // the last row's own block never got its maximum; adsel_get_fps reads the values only
+    if (stop == 2 && err_frame >= 0 && lane == 0) {
+        a.result[1] = (double)ADSEL_ERR_RESELECTED;
+        a.result[4] = (double)err_frame;
+    }
+    for (int i = lane; i < n; i += 32) a.fps[i] = fps_s[i];
+    if (lane == 0) {
+        a.result[0] = cost;
+        a.result[2] = (double)m;
+        a.result[3] = (double)steps;
+        if (PROFILE)
+            for (int i = 0; i < 12; ++i) a.prof[i] = prof_acc[i];
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static bool warp_enabled() {
+    const char *e = getenv("ADSEL_GREEDY_WARP");
+    if (e && atoi(e) == 0) return false;
+    const char *f = getenv("ADSEL_GREEDY_FAST");       // the switches of the multi-warp kernels ask for those kernels
+    const char *c = getenv("ADSEL_GREEDY_CLUSTER");
+    const char *b = getenv("ADSEL_FAST_BLOCK");
+    return !(f && *f) && !(c && *c) && !(b && *b);
+}
+
+// The one-warp kernel serves the configuration its slot layout is made for: truncated geodesic lists (exp
+// normalisation: radius 38, a few dozen entries), temporal groups that are contiguous index ranges (or none), the whole
+// pool on this device and resident in one CTA's shared memory.
+bool warp_eligible(const adsel_handle *h, const adsel_select_params *p, bool sharded) {
+    if (!warp_enabled() || sharded) return false;
+    if (p->spatial != ADSEL_SPATIAL_GEODESIC || p->normalize != ADSEL_NORM_EXP) return false;
+    if (p->temporal && !h->groups_contiguous) return false;
+    const long long cols = ((long long)h->n + WARP_RB - 1) / WARP_RB * WARP_RB, nblk = cols / WARP_RB;
+    return nblk <= 64 && (size_t)cols * 8 + (size_t)nblk * 12 + 64 * 8 + 16 <= 232448 - 64;
+}
+
+int warp_prepare(adsel_handle *h, const adsel_select_params *p, bool sharded) {
+    if (warp_eligible(h, p, sharded)) ADSEL_TRY(h->slots.reserve((size_t)h->n * WARP_SLOT));
+    return ADSEL_OK;
+}
+
+int warp_preload() {
+    cudaFuncAttributes attr;
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, greedy_warp_kernel<false>));
+    ADSEL_CUDA(cudaFuncGetAttributes(&attr, slot_build_kernel));
+    return ADSEL_OK;
+}
+
+// Enqueues slot build + the one-warp loop; *launched = false when this selection is not for it.
+int warp_enqueue(adsel_handle *h, const adsel_select_params *p, GreedyArgs &a, bool sharded, bool *launched) {
+    *launched = false;
+    if (!warp_eligible(h, p, sharded) || h->slots.cap < (size_t)h->n * WARP_SLOT || a.list_capacity >= (1ll << 40)) return ADSEL_OK;
+    const int n = h->n;
+    const long long cols = ((long long)n + WARP_RB - 1) / WARP_RB * WARP_RB, nblk = cols / WARP_RB;
+    const int g = a.temporal ? (a.tl_n < 64 ? a.tl_n : 64) : 0;
+    a.csize = 1;
+    a.cta_cols = (int)cols;
+    a.r_nblk = (int)nblk;
+    a.tl_n = g;
+    a.sel_words = 0;
+    const size_t smem = (size_t)cols * 8 + (size_t)nblk * 8 + (size_t)g * 8 + (size_t)nblk * 4 + 16;
+    ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n, h->stream));
+    slot_build_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, h->stream>>>(h->slots.p, a.rec, a.list_idx, a.list_val, n,
+                                                                                       a.list_capacity, a.list_cursor);
+    ADSEL_CUDA(cudaGetLastError());
+    h->launches += 1;
+    if (a.prof) {
+        ADSEL_CUDA(cudaFuncSetAttribute(greedy_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        greedy_warp_kernel<true><<<1, 32, smem, h->stream>>>(a, h->slots.p);
+    } else {
+        ADSEL_CUDA(cudaFuncSetAttribute(greedy_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        greedy_warp_kernel<false><<<1, 32, smem, h->stream>>>(a, h->slots.p);
+    }
+    ADSEL_CUDA(cudaGetLastError());
+    h->greedy_cluster = 1;
+    h->greedy_variant = 5;
+    *launched = true;
+    return ADSEL_OK;
+}
+
+}   // namespace adsel

@@ -256,16 +256,34 @@ def test_resident_variants_of_the_greedy_loop_select_identically(handle, pools, 
         monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", var)
         with pytest.raises(AssertionError, match="has been selected"):
             handle.select(**{**kw, "budget": 10 ** 6, "first_index": 7})
+    if cluster == "1":      # every block size of the one-CTA step: same selection, same final fps, same exhaustion
+        for rb in ("128", "256", "512"):
+            monkeypatch.setenv("ADSEL_FAST_BLOCK", rb)
+            with pytest.raises(AssertionError, match="has been selected"):
+                handle.select(**{**kw, "budget": 10 ** 6, "first_index": 7})
+            _set_spatial_pool(handle, infos)
+            handle.build_knn_graph(8)
+            got, cost = handle.select(**kw)
+            assert got == want and cost == want_cost, rb
+            assert np.array_equal(handle.get_fps().view(np.uint64), want_fps.view(np.uint64)), rb
+            assert handle.greedy_info()["kernel"] == "greedy_fast_kernel"
+            _set_spatial_pool(handle, small)
+            handle.build_knn_graph(8)
+        monkeypatch.delenv("ADSEL_FAST_BLOCK")
     monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
 
 
-@pytest.mark.parametrize("variant", ["0", "2", "generic"])
+@pytest.mark.parametrize("variant", ["0", "2", "generic", "block256", "block512"])
 def test_every_golden_case_with_the_global_memory_the_cluster_and_the_generic_resident_kernel(pools, tmp_path, monkeypatch, variant):
-    """The default (one resident CTA, fast step where the mode allows) is what the golden tests above run; the same
-    18 cases through the global-memory kernel (pools beyond 16 CTAs' shared memory, the multi-GPU column shards), a
-    2-CTA cluster and the generic one-CTA resident kernel."""
+    """The default (one resident CTA, fast step where the mode allows; 128-frame blocks at this pool size) is what the
+    golden tests above run; the same 18 cases through the global-memory kernel (pools beyond 16 CTAs' shared memory, the
+    multi-GPU column shards), a 2-CTA cluster, the generic one-CTA resident kernel, and the fast step with the 256- and
+    512-frame blocks larger pools get (ADSEL_FAST_BLOCK)."""
     if variant == "generic":
         monkeypatch.setenv("ADSEL_GREEDY_FAST", "0")
+        variant = "1"
+    if variant.startswith("block"):
+        monkeypatch.setenv("ADSEL_FAST_BLOCK", variant[5:])
         variant = "1"
     monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", variant)
     golden = load_golden("P2K_all.json")
