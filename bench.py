@@ -286,7 +286,8 @@ def run_reference_arm(args):
 def greedy_latency_floor(greedy_ms, steps, clock_info, kernel="greedy_fast_kernel"):
     """What bounds the greedy loop is the LENGTH of its dependency chain, not bandwidth.  The model is the
     chain of a step with the latencies MEASURED on this pool's B200s by tools/microbench/latency.cu (one SM, 8 warps):
-    dependent L2 hit 295 cycles, LDS 31, REDUX 26, CTA barrier + consumer 71.  Resident kernels: one L2 round trip (the
+    dependent L2 hit 295 cycles, LDS 31, REDUX 26, CTA barrier + consumer 71, 64-bit compare + select 20.  One-warp kernel:
+    one L2 round trip (the frame's slot), the row minimum, the own block's compare tree, three REDUX.  Resident kernels: one L2 round trip (the
     selected frame's list entries), three barriers, two arg-max chains (LDS + 3 REDUX each), one record read.  The
     global-memory kernel (pools beyond a cluster's shared memory): four L2 round trips and three barriers.  Reported next
     to the achieved time per step so that the headroom is a number; a model, not a measurement."""
@@ -296,6 +297,10 @@ def greedy_latency_floor(greedy_ms, steps, clock_info, kernel="greedy_fast_kerne
         sm_mhz = 1965.0
     if kernel == "greedy_select_kernel":
         cycles, model = 4 * 295 + 3 * 71, "4 dependent L2 hits x 295 cycles + 3 CTA barriers x 71 cycles per step"
+    elif kernel == "greedy_warp_kernel":     # one warp, no barrier: slot load -> row minimum -> own block + block maxima -> arg-max
+        cycles = 295 + 2 * 31 + 4 * 20 + 3 * 26
+        model = ("1 L2 hit x 295 (slot: record + list entries) + 2 x LDS 31 (row minimum, own block) + 4-level compare tree x 20 "
+                 "(64-bit compare + select) + 3 REDUX x 26 cycles per step, no barrier")
     else:
         cycles = 295 + 3 * 71 + 2 * (31 + 3 * 26) + 31
         model = "1 L2 hit x 295 + 3 CTA barriers x 71 + 2 arg-max chains x (LDS 31 + 3 REDUX x 26) + record LDS 31 cycles per step"

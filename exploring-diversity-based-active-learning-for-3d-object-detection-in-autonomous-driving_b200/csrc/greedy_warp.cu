@@ -196,12 +196,14 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
         }
     }
     int cur_blk = cur >> SHIFT, prev_blk = -1;
+    bool cur_key_zero = false;
     Cand part{0ull, 0x7fffffff};   // this lane's best of the previous row's own block (finalised lazily)
     // Shared memory through explicit 32-bit shared-window addresses: generic pointers make the compiler rebuild the window
     // base (S2UR SR_CgaCtaId + ULEA) in front of every access, and `if (...) smem[j] = v` becomes a divergent branch;
     // here a conditional store is one predicated STS and the loop body is straight-line code.
-    const unsigned s_fps = (unsigned)__cvta_generic_to_shared(fps_s), s_bval = (unsigned)__cvta_generic_to_shared(blk_val),
-                   s_gval = (unsigned)__cvta_generic_to_shared(gval), s_bidx = (unsigned)__cvta_generic_to_shared(blk_idx);
+    unsigned s_fps = (unsigned)__cvta_generic_to_shared(fps_s), s_bval = (unsigned)__cvta_generic_to_shared(blk_val),
+             s_gval = (unsigned)__cvta_generic_to_shared(gval), s_bidx = (unsigned)__cvta_generic_to_shared(blk_idx);
+    asm volatile("" : "+r"(s_fps), "+r"(s_bval), "+r"(s_gval), "+r"(s_bidx));   // opaque: kept in registers, not rebuilt per access
     const int sat1 = sat - 1;
 
     while (!local_abort) {
@@ -212,7 +214,9 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
         const int j0 = ldg_s32(sp + 32 + 4 * lane), j1 = ldg_s32(sp + 32 + 4 * (lane + 32));
         const unsigned long long v0 = ldg_u64(sp + 32 + 4 * K + 8 * lane), v1 = ldg_u64(sp + 32 + 4 * K + 8 * (lane + 32));
         unsigned flag_seen = 0;
-        if (mode == 2 && lane == 0) flag_seen = __ldcg(sel_bytes + cur);
+        // A frame that was selected before has fps == 0 (its own row holds 0 for itself), so only a winner whose key is 0 can be a
+        // re-selection (:182): the flag is read on those steps only (pool exhausted, duplicates of a selected frame).
+        if (mode == 2 && cur_key_zero) flag_seen = __ldcg(sel_bytes + cur);
         WPROF(6)
         // ---- 2. in its shadow ----
         // (a) the previous row's own block gets its maximum, unless this row re-reduces the same block anyway
@@ -257,22 +261,23 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
         asm volatile("" ::"r"(h0.w), "r"(h1.w));   // (keeps the unused words' registers from being recycled while the load is in flight)
         WPROF_DEP(1, l_len + e0 + j0 + j1 + (int)v0 + (int)v1)
         if (mode == 2) {
-            flag_seen = __shfl_sync(FULL, flag_seen, 0);
             cost = __dadd_rn(cost, cost_f);        // :184
             cost = __dadd_rn(cost, box_cost);      // :185
             const bool over = cost > budget;       // :186
             const bool full = !over && m >= out_cap;
-            if (flag_seen) {                       // :182 comes before the cost test
-                err_frame = cur;
-                stop = 2;
-                break;
-            }
-            if (over || full) {
-                if (full && lane == 0) {
-                    a.result[1] = (double)ADSEL_ERR_CAPACITY;
-                    a.result[4] = -2.0;
+            unsigned verdict = (flag_seen != 0 ? 1u : 0u) | (over ? 2u : 0u) | (full ? 4u : 0u);
+            asm volatile("" : "+r"(verdict));      // opaque: cicc 12.9 was seen to drop the capacity term from a fused condition
+            if (verdict != 0u) {
+                if (verdict & 1u) {                // :182 comes before the cost test
+                    err_frame = cur;
+                    stop = 2;
+                } else {
+                    if ((verdict & 4u) && lane == 0) {
+                        a.result[1] = (double)ADSEL_ERR_CAPACITY;
+                        a.result[4] = -2.0;
+                    }
+                    stop = (verdict & 2u) ? 1 : 2;
                 }
-                stop = over ? 1 : 2;
                 break;
             }
         } else if (mode == 1) {                    // :168,172-174 -- taken and costed up front, no budget check
@@ -396,6 +401,7 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
         WPROF_DEP(5, y.idx)
         ++steps;
         const int nxt = y.idx;
+        cur_key_zero = (y.hi | y.lo) == 0u;
         if (nxt < 0 || nxt >= n) {   // empty pool: cannot happen with n > 0
             if (lane == 0) a.result[1] = (double)ADSEL_ERR_INVALID;
             stop = 2;

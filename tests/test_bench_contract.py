@@ -119,4 +119,6 @@ def test_greedy_latency_floor_model():
     r = bench.greedy_latency_floor(5.4, 4047, {"sm_mhz": 1965.0})                      # resident kernels: one L2 round trip
     assert r["cycles_per_step"] == 295 + 3 * 71 + 2 * (31 + 3 * 26) + 31 and r["cycles_per_step"] < m["cycles_per_step"]
     assert bench.greedy_latency_floor(9.02, 4047, None)["floor_us_per_step"] == r["floor_us_per_step"]   # clocks unavailable
+    w = bench.greedy_latency_floor(4.1, 4047, {"sm_mhz": 1965.0}, "greedy_warp_kernel")                  # one warp: no barrier
+    assert w["cycles_per_step"] == 295 + 2 * 31 + 4 * 20 + 3 * 26 and 0.2 < w["frac"] < 0.3
     assert bench.greedy_latency_floor(0.0, 0, {"sm_mhz": None})["frac"] is None

@@ -301,3 +301,63 @@ def test_p850_temporal_selector_budget_1200_identical_to_reference(pools, tmp_pa
     for cid, case in golden["cases"].items():
         res, _ = _run_case_through_selectors(pl, case, tmp_path)
         assert res == case["selected_index"], cid
+
+
+def test_one_warp_kernel_against_the_global_memory_kernel(handle, pools, monkeypatch):
+    """greedy_warp_kernel (the default for geodesic + exp rows on a pool that fits one CTA's shared memory): same
+    selection, cost, final fps, resumed round and exhaustion error as ADSEL_GREEDY_CLUSTER=0 -- with the speculative
+    temporal-group window (groups >= 38 frames), the bounded loop (shorter groups: the LUT is shorter than its reach),
+    no temporal term at all, and rows longer than the 64 entries a slot holds."""
+    infos = pools("P8K")["infos"]
+    for groups in ("runs", "short", "none"):
+        loc, run_id, max_td = _set_spatial_pool(handle, infos)
+        if groups == "short":                      # consecutive groups of 20 frames
+            handle.set_pool(loc, (np.arange(len(infos)) // 20).astype(np.int32), np.ones(len(infos), np.int32))
+        handle.build_knn_graph(8)
+        kw = dict(spatial="geodesic", temporal=groups != "none", normalize="exp", aggregate="sum", lambda_t=1.0, budget=700,
+                  first_index=4242)
+        monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", "0")
+        want, want_cost = handle.select(**kw)
+        assert handle.greedy_info()["kernel"] == "greedy_select_kernel"
+        want_fps = handle.get_fps()
+        want2, _ = handle.select(**{**kw, "budget": 1000, "sampled": want, "first_index": -1, "cost_start": want_cost})
+        monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
+        got, cost = handle.select(**kw)
+        assert handle.greedy_info() == {"kernel": "greedy_warp_kernel", "cluster": 1}
+        assert got == want and cost == want_cost, groups
+        assert np.array_equal(handle.get_fps().view(np.uint64), want_fps.view(np.uint64)), groups
+        got2, _ = handle.select(**{**kw, "budget": 1000, "sampled": got, "first_index": -1, "cost_start": cost})
+        assert got2 == want2, groups
+        for agg in ("min", "max"):
+            if groups == "none":
+                continue
+            monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", "0")
+            w, _ = handle.select(**{**kw, "aggregate": agg})
+            monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
+            g, _ = handle.select(**{**kw, "aggregate": agg})
+            assert g == w and handle.greedy_info()["kernel"] == "greedy_warp_kernel", (groups, agg)
+    # dense cluster of frames: rows far longer than a slot (the tail comes from the list pool)
+    rng = np.random.default_rng(3)
+    n = 3000
+    loc = np.concatenate([rng.normal(scale=6.0, size=(400, 2)), rng.uniform(-400, 400, size=(n - 400, 2))])
+    handle.set_pool(loc, (np.arange(n) // 45).astype(np.int32), rng.integers(0, 30, n).astype(np.int32))
+    handle.build_knn_graph(8)
+    kw = dict(spatial="geodesic", temporal=True, normalize="exp", budget=300, first_index=5)
+    monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", "0")
+    want, want_cost = handle.select(**kw)
+    want_fps = handle.get_fps()
+    monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
+    got, cost = handle.select(**kw)
+    assert handle.greedy_info()["kernel"] == "greedy_warp_kernel" and got == want and cost == want_cost
+    assert np.array_equal(handle.get_fps().view(np.uint64), want_fps.view(np.uint64))
+    assert handle.counters()["list_entries"] / n > 20 and np.isfinite(handle.geodesic_rows(np.array([0], np.int32), radius=38.0)).sum() > 64
+    # exhaustion: every frame taken, then the reference's assertion (spatial_temporal_selector.py:182)
+    small = pools("P300")["infos"]
+    _set_spatial_pool(handle, small)
+    handle.build_knn_graph(8)
+    with pytest.raises(AssertionError, match="has been selected"):
+        handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=10 ** 6, first_index=7)
+    assert handle.greedy_info()["kernel"] == "greedy_warp_kernel"
+    # out_idx capacity
+    with pytest.raises(Exception, match="capacity"):
+        handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=10 ** 6, first_index=7, out_cap=10)
