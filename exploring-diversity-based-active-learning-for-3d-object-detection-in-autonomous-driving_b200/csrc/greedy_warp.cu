@@ -14,22 +14,29 @@
 //   * everything that does not need the slot runs in the shadow of its load: the candidates of the temporal group
 //     (index window around the winner, values from a shared-memory LUT, the comparison with fps and the "is this
 //     the block's maximum" test) are evaluated speculatively and only masked by the group bounds when the header
-//     arrives; the previous step's own-block maximum is finalised (three REDUX on registers) there too;
+//     arrives; cost + cost_f is formed there too (the box cost n_boxes * cost_b comes rounded from the slot);
 //   * the final arg-max is one pass: 16 entries of the row's own block + 2 block maxima per lane, a per-lane
-//     compare/select tree, three REDUX.
+//     compare/select tree, then TWO interleaved chains of three REDUX: the step's winner, and the own block's new
+//     maximum (stored for the steps in which the block is no longer the row's own) -- the second chain hides in the
+//     latency of the first.
 // Bit-exact like the other kernels: the same minima, np.argmax's first-maximum rule, the same rounded cost sums.
 #include "common.cuh"
 
 namespace adsel {
 
 constexpr int WARP_K = 64;                          // list entries held in a slot (two per lane)
-constexpr int WARP_SLOT = 32 + WARP_K * 12;         // header (32 B) | idx[K] int32 | val[K] float64
-constexpr int WARP_RB = 512, WARP_SHIFT = 9, WARP_PER = WARP_RB / 32;
+constexpr int WARP_SLOT = 32 + WARP_K * 12;         // header {list_off, list_len, frame | e0, e1, box cost f64} | idx[K] int32 | val[K] float64
+#ifndef ADSEL_WARP_RB
+#define ADSEL_WARP_RB 512
+#endif
+constexpr int WARP_RB = ADSEL_WARP_RB, WARP_SHIFT = WARP_RB == 512 ? 9 : 8, WARP_PER = WARP_RB / 32;   // frames per block
+constexpr int WARP_NB = WARP_RB == 512 ? 2 : 4;     // block maxima per lane in the final arg-max: up to 64 / 128 blocks
+static_assert(WARP_RB == 512 || WARP_RB == 256, "block size");
 constexpr int WARP_SPEC = 3;                        // speculative group candidates per lane: window of 96 >= 2 * sat - 1
 
 __global__ void slot_build_kernel(unsigned char *__restrict__ slots, const FrameRec *__restrict__ rec,
                                   const int32_t *__restrict__ lidx, const double *__restrict__ lval, int n, long long capacity,
-                                  const unsigned long long *__restrict__ cursor) {
+                                  const unsigned long long *__restrict__ cursor, double cost_b) {
     const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (w >= n) return;
     const FrameRec r = rec[w];
@@ -37,7 +44,9 @@ __global__ void slot_build_kernel(unsigned char *__restrict__ slots, const Frame
     if (lane == 0) {
         *reinterpret_cast<uint4 *>(s) = make_uint4((unsigned)r.list_off, (unsigned)((unsigned long long)r.list_off >> 32),
                                                     (unsigned)r.list_len, (unsigned)w);
-        *reinterpret_cast<uint4 *>(s + 16) = make_uint4((unsigned)r.e0, (unsigned)r.e1, (unsigned)r.n_boxes, (unsigned)w);
+        // n_boxes * cost_b as ONE rounded product (base_selector.py:85), formed here so that the greedy step adds it as is
+        const unsigned long long bc = (unsigned long long)__double_as_longlong(__dmul_rn((double)r.n_boxes, cost_b));
+        *reinterpret_cast<uint4 *>(s + 16) = make_uint4((unsigned)r.e0, (unsigned)r.e1, (unsigned)bc, (unsigned)(bc >> 32));
     }
     if (lidx == nullptr || (cursor && (long long)*cursor > capacity)) return;   // overflowed pool: the greedy kernel reports it
     int32_t *si = reinterpret_cast<int32_t *>(s + 32);
@@ -114,7 +123,7 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
     const double *const lval = a.list_val;
     int32_t *const out = a.out;
     unsigned char *const sel_bytes = a.is_selected;
-    const double budget = a.budget, cost_f = a.cost_f, cost_b = a.cost_b;
+    const double budget = a.budget, cost_f = a.cost_f;
     const bool has_group = a.temporal != 0;
 
     extern __shared__ unsigned long long warp_smem[];
@@ -197,7 +206,6 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
     }
     int cur_blk = cur >> SHIFT, prev_blk = -1;
     bool cur_key_zero = false;
-    Cand part{0ull, 0x7fffffff};   // this lane's best of the previous row's own block (finalised lazily)
     // Shared memory through explicit 32-bit shared-window addresses: generic pointers make the compiler rebuild the window
     // base (S2UR SR_CgaCtaId + ULEA) in front of every access, and `if (...) smem[j] = v` becomes a divergent branch;
     // here a conditional store is one predicated STS and the loop body is straight-line code.
@@ -207,27 +215,24 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
     const int sat1 = sat - 1;
 
     while (!local_abort) {
-        unsigned long long dirty = 0ull;
+        unsigned long long dirty = 0ull, dirty1 = 0ull;   // blocks 0..63 / 64..127 whose maximum was lowered
+        auto mark = [&](int lb) {
+            const unsigned long long bit = 1ull << (lb & 63);
+            if (WARP_NB == 2 || lb < 64) dirty |= bit;
+            else dirty1 |= bit;
+        };
         // ---- 1. the slot: header + the first 64 list entries, one L2 round trip ----
         const unsigned char *sp = slots + (size_t)cur * WARP_SLOT;
         const uint4 h0 = ldg_v4(sp), h1 = ldg_v4(sp + 16);
         const int j0 = ldg_s32(sp + 32 + 4 * lane), j1 = ldg_s32(sp + 32 + 4 * (lane + 32));
         const unsigned long long v0 = ldg_u64(sp + 32 + 4 * K + 8 * lane), v1 = ldg_u64(sp + 32 + 4 * K + 8 * (lane + 32));
+        const double cost_pre = __dadd_rn(cost, cost_f);   // :184
         unsigned flag_seen = 0;
         // A frame that was selected before has fps == 0 (its own row holds 0 for itself), so only a winner whose key is 0 can be a
         // re-selection (:182): the flag is read on those steps only (pool exhausted, duplicates of a selected frame).
         if (mode == 2 && cur_key_zero) flag_seen = __ldcg(sel_bytes + cur);
         WPROF(6)
         // ---- 2. in its shadow ----
-        // (a) the previous row's own block gets its maximum, unless this row re-reduces the same block anyway
-        if (prev_blk >= 0 && prev_blk != cur_blk) {
-            unsigned hi1[1] = {(unsigned)(part.k >> 32)}, lo1[1] = {(unsigned)part.k};
-            int idx1[1] = {part.i};
-            const Win x = warp_argmax<1>(hi1, lo1, idx1);
-            sts64_if(s_bval + 8u * prev_blk, ((unsigned long long)x.hi << 32) | x.lo, lane == 0);
-            sts32_if(s_bidx + 4u * prev_blk, x.idx, lane == 0);
-            __syncwarp();
-        }
         WPROF(7)
         // (b) temporal group, speculatively: the frames within the LUT's reach of cur, whatever the group's bounds are
         int gj[WARP_SPEC];
@@ -255,14 +260,15 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
         }
         WPROF_DEP(0, (int)gneed[0] + (int)gmax[WARP_SPEC - 1])
         // ---- 3. the header is here ----
+        // (ptxas places the first use of the header right after the loads' issue; forcing it behind the shadow work with a
+        //  run-time-zero dependency was measured slower, 1.03 vs 0.96 us per step, and is not done)
         const long long l_off = (long long)(((unsigned long long)h0.y << 32) | h0.x);
         const int l_len = (int)h0.z, e0 = (int)h1.x, e1 = (int)h1.y;
-        const double box_cost = __dmul_rn((double)(int)h1.z, cost_b);   // n_boxes * cost_b, one rounded product (base_selector.py:85)
-        asm volatile("" ::"r"(h0.w), "r"(h1.w));   // (keeps the unused words' registers from being recycled while the load is in flight)
+        const double box_cost = __longlong_as_double((long long)(((unsigned long long)h1.w << 32) | h1.z));   // n_boxes * cost_b (slot_build_kernel)
+        asm volatile("" ::"r"(h0.w));   // (keeps the unused word's register from being recycled while the load is in flight)
         WPROF_DEP(1, l_len + e0 + j0 + j1 + (int)v0 + (int)v1)
         if (mode == 2) {
-            cost = __dadd_rn(cost, cost_f);        // :184
-            cost = __dadd_rn(cost, box_cost);      // :185
+            cost = __dadd_rn(cost_pre, box_cost);  // :184-185 (cost + cost_f was formed while the slot was in flight)
             const bool over = cost > budget;       // :186
             const bool full = !over && m >= out_cap;
             unsigned verdict = (flag_seen != 0 ? 1u : 0u) | (over ? 2u : 0u) | (full ? 4u : 0u);
@@ -281,8 +287,7 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
                 break;
             }
         } else if (mode == 1) {                    // :168,172-174 -- taken and costed up front, no budget check
-            cost = __dadd_rn(cost, cost_f);
-            cost = __dadd_rn(cost, box_cost);
+            cost = __dadd_rn(cost_pre, box_cost);
         }
         if (mode != 0) {
             if (lane == 0) {
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
             for (int q = 0; q < WARP_SPEC; ++q) {
                 const bool w = gneed[q] && gj[q] >= e0 && gj[q] < e1;
                 sts64_if(s_fps + 8u * gj[q], gv[q], w);
-                if (w && gmax[q]) dirty |= 1ull << (gj[q] >> SHIFT);
+                if (w && gmax[q]) mark(gj[q] >> SHIFT);
             }
         } else if (has_group) {
             const int g0 = max(e0, cur - sat + 1), g1 = min(e1, cur + sat);
@@ -308,7 +313,7 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
                 if (v < fps_s[j]) {
                     fps_s[j] = v;
                     const int lb = j >> SHIFT;
-                    if (lb != cur_blk && marking && blk_idx[lb] == j) dirty |= 1ull << lb;
+                    if (lb != cur_blk && marking && blk_idx[lb] == j) mark(lb);
                 }
             }
         }
@@ -322,8 +327,8 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
             const bool w0 = p0 && v0 < o0, w1 = p1 && v1 < o1;
             sts64_if(s_fps + 8u * c0, v0, w0);
             sts64_if(s_fps + 8u * c1, v1, w1);
-            if (w0 && marking && (c0 >> SHIFT) != cur_blk && b0 == c0) dirty |= 1ull << (c0 >> SHIFT);
-            if (w1 && marking && (c1 >> SHIFT) != cur_blk && b1 == c1) dirty |= 1ull << (c1 >> SHIFT);
+            if (w0 && marking && (c0 >> SHIFT) != cur_blk && b0 == c0) mark(c0 >> SHIFT);
+            if (w1 && marking && (c1 >> SHIFT) != cur_blk && b1 == c1) mark(c1 >> SHIFT);
         }
         if (l_len > K) {   // rows longer than a slot continue in the list pool (3.5 % of the rows)
             for (int t = K + lane; t < l_len; t += 32) {
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
                 if (v < fps_s[j]) {
                     fps_s[j] = v;
                     const int lb = j >> SHIFT;
-                    if (lb != cur_blk && marking && blk_idx[lb] == j) dirty |= 1ull << lb;
+                    if (lb != cur_blk && marking && blk_idx[lb] == j) mark(lb);
                 }
             }
         }
@@ -352,23 +357,27 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
             prev_blk = -1;
         }
         // ---- 4. other blocks whose maximum was lowered (2 % of the steps) ----
-        if (__any_sync(FULL, dirty != 0ull)) {
-            unsigned dlo = __reduce_or_sync(FULL, (unsigned)dirty), dhi = __reduce_or_sync(FULL, (unsigned)(dirty >> 32));
-            while (dlo) {
-                refresh_block(__ffs(dlo) - 1);
-                dlo &= dlo - 1;
-            }
-            while (dhi) {
-                refresh_block(32 + __ffs(dhi) - 1);
-                dhi &= dhi - 1;
+        if (__any_sync(FULL, (dirty | dirty1) != 0ull)) {
+            unsigned long long words[2] = {dirty, dirty1};
+#pragma unroll
+            for (int w = 0; w < (WARP_NB == 2 ? 1 : 2); ++w) {
+                unsigned dlo = __reduce_or_sync(FULL, (unsigned)words[w]), dhi = __reduce_or_sync(FULL, (unsigned)(words[w] >> 32));
+                while (dlo) {
+                    refresh_block(64 * w + __ffs(dlo) - 1);
+                    dlo &= dlo - 1;
+                }
+                while (dhi) {
+                    refresh_block(64 * w + 32 + __ffs(dhi) - 1);
+                    dhi &= dhi - 1;
+                }
             }
             __syncwarp();
         }
         WPROF(3)
         // ---- 5. arg-max: the row's own block from its 512 entries, every other block from its maximum ----
-        Cand bm[2];
+        Cand bm[WARP_NB];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < WARP_NB; ++q) {
             const int b = lane + 32 * q;
             const bool ok = b < nblk && b != cur_blk;
             const unsigned long long k = lds64(s_bval + 8u * (ok ? b : 0));
@@ -392,12 +401,26 @@ __global__ void __launch_bounds__(32, 1) greedy_warp_kernel(const GreedyArgs a, 
             own = c[0];
             if (own.i >= n) own.i = 0x7fffffff;   // padding of the last block (key 0): never before a real frame
         }
-        part = own;
-        const Cand best = better_of(own, better_of(bm[0], bm[1]));
+        Cand best = better_of(bm[0], bm[1]);
+        if (WARP_NB == 4) best = better_of(best, better_of(bm[2], bm[3]));
+        best = better_of(own, best);
         WPROF_DEP(4, (int)best.k + best.i)
-        unsigned hi1[1] = {(unsigned)(best.k >> 32)}, lo1[1] = {(unsigned)best.k};
-        int idx1[1] = {best.i};
-        const Win y = warp_argmax<1>(hi1, lo1, idx1);
+        // Two arg-max chains interleaved, three REDUX each: (A) the step's winner over everything, (B) the own block's new
+        // maximum over its 512 entries, stored for the steps in which the block is no longer the row's own.
+        Win y;
+        {
+            const unsigned ah = (unsigned)(best.k >> 32), al = (unsigned)best.k, bh = (unsigned)(own.k >> 32), bl = (unsigned)own.k;
+            const unsigned mah = __reduce_max_sync(FULL, ah);
+            const unsigned mbh = __reduce_max_sync(FULL, bh);
+            const unsigned mal = __reduce_max_sync(FULL, ah == mah ? al : 0u);
+            const unsigned mbl = __reduce_max_sync(FULL, bh == mbh ? bl : 0u);
+            y.idx = __reduce_min_sync(FULL, (ah == mah && al == mal) ? best.i : 0x7fffffff);
+            const int bidx = __reduce_min_sync(FULL, (bh == mbh && bl == mbl) ? own.i : 0x7fffffff);
+            y.hi = mah;
+            y.lo = mal;
+            sts64_if(s_bval + 8u * max(cur_blk, 0), ((unsigned long long)mbh << 32) | mbl, lane == 0 && cur_blk >= 0);
+            sts32_if(s_bidx + 4u * max(cur_blk, 0), bidx, lane == 0 && cur_blk >= 0);
+        }
         WPROF_DEP(5, y.idx)
         ++steps;
         const int nxt = y.idx;
@@ -446,7 +469,7 @@ bool warp_eligible(const adsel_handle *h, const adsel_select_params *p, bool sha
     if (p->spatial != ADSEL_SPATIAL_GEODESIC || p->normalize != ADSEL_NORM_EXP) return false;
     if (p->temporal && !h->groups_contiguous) return false;
     const long long cols = ((long long)h->n + WARP_RB - 1) / WARP_RB * WARP_RB, nblk = cols / WARP_RB;
-    return nblk <= 64 && (size_t)cols * 8 + (size_t)nblk * 12 + 64 * 8 + 16 <= 232448 - 64;
+    return nblk <= 32 * WARP_NB && (size_t)cols * 8 + (size_t)nblk * 12 + 64 * 8 + 16 <= 232448 - 64;
 }
 
 int warp_prepare(adsel_handle *h, const adsel_select_params *p, bool sharded) {
@@ -476,7 +499,7 @@ int warp_enqueue(adsel_handle *h, const adsel_select_params *p, GreedyArgs &a, b
     const size_t smem = (size_t)cols * 8 + (size_t)nblk * 8 + (size_t)g * 8 + (size_t)nblk * 4 + 16;
     ADSEL_CUDA(cudaMemsetAsync(h->is_selected.p, 0, (size_t)n, h->stream));
     slot_build_kernel<<<(unsigned)(((size_t)n * 32 + 255) / 256), 256, 0, h->stream>>>(h->slots.p, a.rec, a.list_idx, a.list_val, n,
-                                                                                       a.list_capacity, a.list_cursor);
+                                                                                       a.list_capacity, a.list_cursor, a.cost_b);
     ADSEL_CUDA(cudaGetLastError());
     h->launches += 1;
     if (a.prof) {
