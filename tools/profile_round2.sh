@@ -6,8 +6,8 @@ $B > gpurun_out/r02_plain_bench.json 2> gpurun_out/r02_plain_bench.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv $B > gpurun_out/r02_ncu_bench.log 2>&1
 G="python tools/greedy_perf.py P28K 4800"
 $G "" > gpurun_out/r02_plain_greedy.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:greedy_fast -s 2 -c 1 -o gpurun_out/r02_greedy_fast $G "" > gpurun_out/r02_ncu_greedy.log 2>&1
-python tools/greedy_perf.py P281K 4800 "" > gpurun_out/r02_plain_greedy281k.log 2>&1 || exit 1
-ncu --set full --clock-control none --import-source on -k regex:greedy_fast -s 2 -c 1 -o gpurun_out/r02_greedy_fast_cluster16 python tools/greedy_perf.py P281K 4800 "" > gpurun_out/r02_ncu_greedy281k.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:greedy_warp -s 2 -c 1 -o gpurun_out/r02_greedy_warp $G "" > gpurun_out/r02_ncu_greedy.log 2>&1
+ADSEL_GREEDY_WARP=0 $G "" > gpurun_out/r02_plain_greedy_fast.log 2>&1 || exit 1
+ADSEL_GREEDY_WARP=0 ncu --set full --clock-control none --import-source on -k regex:greedy_fast -s 2 -c 1 -o gpurun_out/r02_greedy_fast $G "" > gpurun_out/r02_ncu_greedy_fast.log 2>&1
 tail -1 gpurun_out/r02_plain_greedy.log | cut -c1-120
-tail -1 gpurun_out/r02_plain_greedy281k.log | cut -c1-120
+tail -1 gpurun_out/r02_plain_greedy_fast.log | cut -c1-120
