@@ -567,6 +567,7 @@ def run_b200_arm(args):
         barrier()
         wall_ms = (time.perf_counter() - t_wall) * 1e3
         counters = h.counters()
+        greedy_info = h.greedy_info()          # kernel of the timed selections (the extras below run other pools through the handle)
         launches = counters["launches"] - launches0
         ms_per_step = max_over_ranks(dev_ms / args.steps)
         stages = {k: v / args.steps for k, v in stage_acc.items()}
@@ -692,7 +693,6 @@ def run_b200_arm(args):
                     boxes_big = np.random.default_rng(1).integers(0, 60, size=nbig).astype(np.int32)
                     bev_sh.update(bev_extras_sharded(h, nbig, boxes_big, first_index(nbig), peaks, max_over_ranks, barrier, reps=2,
                                                      budget=BUDGET, key="bev_sharded_scaled_pool"))
-        greedy_info = h.greedy_info()
         h.close()
 
         # ---- one-shot CLI, cold: a fresh `python tools/active_select.py` process (the reference's unit of work,
