@@ -140,8 +140,10 @@ int adsel_get_stage_ms(adsel_handle *h, float *ms8);
  * [2] total neighbour-list entries, [3] csr nnz */
 int adsel_get_counters(adsel_handle *h, int64_t *c4);
 /* which greedy kernel the last selection ran: info2[0] = 0 global-memory loop (pool beyond a cluster's shared memory, column
- * shards), 1 fast resident CTA, 2 resident thread-block cluster, 3 lazy rows (one search per selected frame);
- * info2[1] = CTAs of the cluster */
+ * shards), 1 multi-warp resident kernel (one CTA or a thread-block cluster: greedy_fast_kernel), 2 generic resident kernel
+ * (Euclid term, non-contiguous groups: greedy_resident_kernel), 3 lazy rows (one search per selected frame), 4 fused
+ * feature loop, 5 one warp on resident columns with one slot load per step (greedy_warp_kernel: geodesic rows with the exp
+ * normalisation on pools that fit one CTA's shared memory); info2[1] = CTAs of the cluster */
 int adsel_get_greedy_info(adsel_handle *h, int32_t *info2);
 
 /* ---- pool sharded over the GPUs of one NVSwitch box -------------------------------
