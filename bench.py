@@ -297,6 +297,11 @@ def greedy_latency_floor(greedy_ms, steps, clock_info, kernel="greedy_fast_kerne
         sm_mhz = 1965.0
     if kernel == "greedy_select_kernel":
         cycles, model = 4 * 295 + 3 * 71, "4 dependent L2 hits x 295 cycles + 3 CTA barriers x 71 cycles per step"
+    elif kernel == "greedy_warp_cluster_kernel":   # the same chain with the vector spread over a cluster's shared memory
+        cycles = 295 + 2 * 31 + 4 * 20 + 3 * 26 + 2 * 414
+        model = ("one-warp chain (1 L2 hit x 295 + 2 x LDS 31 + compare tree 4 x 20 + 3 REDUX x 26) + 2 exposed distributed-shared-memory "
+                 "round trips x 414 (the st.shared::cluster + poll exchange of tools/microbench/dsmem.cu, an upper bound for a remote load) "
+                 "cycles per step, no barrier, no exchange")
     elif kernel == "greedy_warp_kernel":     # one warp, no barrier: slot load -> row minimum -> own block + block maxima -> arg-max
         cycles = 295 + 2 * 31 + 4 * 20 + 3 * 26
         model = ("1 L2 hit x 295 (slot: record + list entries) + 2 x LDS 31 (row minimum, own block) + 4-level compare tree x 20 "

@@ -1990,7 +1990,7 @@ int greedy_select(adsel_handle *h, const adsel_select_params *p, const int32_t *
             unsigned long long prof[16];
             cudaMemcpy(prof, greedy_prof_ptr(), sizeof(prof), cudaMemcpyDeviceToHost);
             const double steps = result[3] > 0 ? result[3] : 1;
-            if (h->greedy_variant == 5)
+            if (h->greedy_variant == 5 || h->greedy_variant == 6)
                 fprintf(stderr, "[warp profile] cycles/step: issue %.0f | finalise %.0f | spec group %.0f | slot wait %.0f | accept+group %.0f | list %.0f | "
                                 "dirty blocks %.0f | loads+tree %.0f | redux %.0f\n",
                         prof[6] / steps, prof[7] / steps, prof[0] / steps, prof[1] / steps, prof[8] / steps, prof[2] / steps, prof[3] / steps,

@@ -398,7 +398,7 @@ class Handle:
         return dict(zip(("launches", "steps", "list_entries", "nnz"), c.tolist()))
 
     GREEDY_KERNELS = ("greedy_select_kernel", "greedy_fast_kernel", "greedy_resident_kernel", "greedy_lazy_kernel",
-                      "fused_feature_kernel", "greedy_warp_kernel")
+                      "fused_feature_kernel", "greedy_warp_kernel", "greedy_warp_cluster_kernel")
 
     def greedy_info(self):
         """Kernel of the last selection and its cluster size (csrc/greedy.cu, csrc/lazy.cu)."""

@@ -143,7 +143,8 @@ int adsel_get_counters(adsel_handle *h, int64_t *c4);
  * shards), 1 multi-warp resident kernel (one CTA or a thread-block cluster: greedy_fast_kernel), 2 generic resident kernel
  * (Euclid term, non-contiguous groups: greedy_resident_kernel), 3 lazy rows (one search per selected frame), 4 fused
  * feature loop, 5 one warp on resident columns with one slot load per step (greedy_warp_kernel: geodesic rows with the exp
- * normalisation on pools that fit one CTA's shared memory); info2[1] = CTAs of the cluster */
+ * normalisation on pools that fit one CTA's shared memory), 6 the same loop with the columns spread over the shared memory
+ * of a 2 / 4 / 8-CTA cluster of passive CTAs (greedy_warp_cluster_kernel, up to ~229 k frames); info2[1] = CTAs of the cluster */
 int adsel_get_greedy_info(adsel_handle *h, int32_t *info2);
 
 /* ---- pool sharded over the GPUs of one NVSwitch box -------------------------------

@@ -361,3 +361,44 @@ def test_one_warp_kernel_against_the_global_memory_kernel(handle, pools, monkeyp
     # out_idx capacity
     with pytest.raises(Exception, match="capacity"):
         handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=10 ** 6, first_index=7, out_cap=10)
+
+
+@pytest.mark.parametrize("bpc", ["4", "2", "1"])
+def test_one_warp_kernel_over_a_cluster_of_passive_memory_ctas(handle, pools, monkeypatch, bpc):
+    """greedy_warp_cluster_kernel: pools beyond one CTA's shared memory keep the one-warp loop; the min-distance vector is
+    split over the shared memory of a 2..16-CTA cluster and reached through distributed shared memory.
+    ADSEL_WARP_CLUSTER_BPC forces small slices (4 / 2 / 1 blocks of 512 frames per CTA: clusters of 4 / 8 / 16 CTAs on the
+    8,000-frame pool) so that every cluster size, the super-block level and the remote paths run on a pool the test can
+    afford; compared with the global-memory kernel: selection, cost, final fps, resumed round, exhaustion."""
+    infos = pools("P8K")["infos"]
+    for groups in ("runs", "short", "none"):
+        loc, run_id, max_td = _set_spatial_pool(handle, infos)
+        if groups == "short":
+            handle.set_pool(loc, (np.arange(len(infos)) // 20).astype(np.int32), np.ones(len(infos), np.int32))
+        handle.build_knn_graph(8)
+        kw = dict(spatial="geodesic", temporal=groups != "none", normalize="exp", aggregate="sum", lambda_t=1.0, budget=700,
+                  first_index=4242)
+        monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", "0")
+        want, want_cost = handle.select(**kw)
+        want_fps = handle.get_fps()
+        want2, _ = handle.select(**{**kw, "budget": 1000, "sampled": want, "first_index": -1, "cost_start": want_cost})
+        monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
+        monkeypatch.setenv("ADSEL_WARP_CLUSTER_BPC", bpc)
+        got, cost = handle.select(**kw)
+        assert handle.greedy_info() == {"kernel": "greedy_warp_cluster_kernel", "cluster": {"4": 4, "2": 8, "1": 16}[bpc]}
+        assert got == want and cost == want_cost, groups
+        assert np.array_equal(handle.get_fps().view(np.uint64), want_fps.view(np.uint64)), groups
+        got2, _ = handle.select(**{**kw, "budget": 1000, "sampled": got, "first_index": -1, "cost_start": cost})
+        assert got2 == want2, groups
+        monkeypatch.delenv("ADSEL_WARP_CLUSTER_BPC")
+    # exhaustion on a pool of 5 blocks (2,099 frames): every frame taken, then the reference's assertion (:182)
+    small = pools("P2K")["infos"]
+    _set_spatial_pool(handle, small)
+    handle.build_knn_graph(8)
+    monkeypatch.setenv("ADSEL_WARP_CLUSTER_BPC", "1" if bpc == "1" else "2")
+    with pytest.raises(AssertionError, match="has been selected"):
+        handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=10 ** 6, first_index=7)
+    assert handle.greedy_info()["kernel"] == "greedy_warp_cluster_kernel"
+    with pytest.raises(Exception, match="capacity"):
+        handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=10 ** 6, first_index=7, out_cap=10)
+    monkeypatch.delenv("ADSEL_WARP_CLUSTER_BPC")

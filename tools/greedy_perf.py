@@ -17,7 +17,13 @@ from adsel_b200 import native, pool, synthetic  # noqa: E402
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "P28K"
     budget = int(sys.argv[2]) if len(sys.argv) > 2 else 4800
-    infos, _ = synthetic.generate_pool(getattr(synthetic, name))
+    if "x" in name:          # P28Kx2 ...: bench.py's weak-scaled pools (same frame density)
+        base, world = getattr(synthetic, name.split("x")[0]), int(name.split("x")[1])
+        spec = synthetic.PoolSpec(name, base.n_scenes * world, base.n_long * world, base.long_len, base.short_len,
+                                  base.scenes_per_log, base.seed)
+        infos, _ = synthetic.generate_pool(spec, box_m=1600.0 * world ** 0.5)
+    else:
+        infos, _ = synthetic.generate_pool(getattr(synthetic, name))
     loc = pool.ego_locations(infos)
     run_id, max_td = pool.consecutive_runs(pool.logfile_names(infos))
     nb = pool.box_counts(infos)
