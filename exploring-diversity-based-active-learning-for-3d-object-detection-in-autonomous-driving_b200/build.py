@@ -77,7 +77,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             objs = list(ex.map(compile_one, _sources()))
         tmp = f"{LIB}.tmp{os.getpid()}"
         try:
-            subprocess.check_call([nvcc, "-shared", "-o", tmp] + objs + ["-lcuda"], cwd=CSRC)
+            # (the link step gets the arch too: without one nvcc assumes its default sm_52 and warns about it)
+            subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs + ["-lcuda"], cwd=CSRC)
             os.replace(tmp, LIB)
         finally:
             if os.path.exists(tmp):
