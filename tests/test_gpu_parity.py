@@ -402,3 +402,32 @@ def test_one_warp_kernel_over_a_cluster_of_passive_memory_ctas(handle, pools, mo
     with pytest.raises(Exception, match="capacity"):
         handle.select(spatial="geodesic", temporal=True, normalize="exp", budget=10 ** 6, first_index=7, out_cap=10)
     monkeypatch.delenv("ADSEL_WARP_CLUSTER_BPC")
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_cluster_kernel_at_the_sizes_of_the_weak_scaled_pools(monkeypatch, world):
+    """greedy_warp_cluster_kernel at full size -- bench.py's weak-scaled pools of 56,260 (2 CTAs) and 225,040 frames (8 CTAs:
+    54 blocks in CTA 0, 56 in each passive CTA) -- against the global-memory kernel: selection, cost, final fps, resumed round."""
+    from adsel_b200 import native, synthetic
+    base = synthetic.P28K
+    spec = synthetic.PoolSpec(f"P28Kx{world}", base.n_scenes * world, base.n_long * world, base.long_len, base.short_len,
+                              base.scenes_per_log, base.seed)
+    infos, _ = synthetic.generate_pool(spec, box_m=1600.0 * world ** 0.5)
+    h = native.Handle(0)
+    try:
+        _set_spatial_pool(h, infos)
+        h.build_knn_graph(8)
+        kw = dict(spatial="geodesic", temporal=True, normalize="exp", budget=2400, first_index=len(infos) // 3)
+        monkeypatch.setenv("ADSEL_GREEDY_CLUSTER", "0")
+        want, want_cost = h.select(**kw)
+        want_fps = h.get_fps()
+        want2, _ = h.select(**{**kw, "budget": 2700, "sampled": want, "first_index": -1, "cost_start": want_cost})
+        monkeypatch.delenv("ADSEL_GREEDY_CLUSTER")
+        got, cost = h.select(**kw)
+        assert h.greedy_info() == {"kernel": "greedy_warp_cluster_kernel", "cluster": world}
+        assert got == want and cost == want_cost
+        assert np.array_equal(h.get_fps().view(np.uint64), want_fps.view(np.uint64))
+        got2, _ = h.select(**{**kw, "budget": 2700, "sampled": got, "first_index": -1, "cost_start": cost})
+        assert got2 == want2 and len(got2) > 100
+    finally:
+        h.close()
