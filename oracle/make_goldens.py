@@ -81,7 +81,7 @@ def run_case(classes, sel_name, paths, kwargs, rounds, workdir, keep_store=None)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pool", default="P2K")
-    ap.add_argument("--only", default="all", help="all | st (SpatialTemporal exp/sum only) | st_linear | temporal (TemporalSelector only) | random | spatial (SpatialSelector at budget 1200)")
+    ap.add_argument("--only", default="all", help="all | st (SpatialTemporal exp/sum only) | st_agg | st_linear | temporal (TemporalSelector only) | random | spatial (SpatialSelector at budget 1200)")
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
     ap.add_argument("--budget", type=int, default=600, help="base budget B; chained cases use B/2,B/2,B")
     args = ap.parse_args()
@@ -112,6 +112,11 @@ def main():
             cases += [("random", "RandomSelector", {}, [B]),
                       ("random_rounds", "RandomSelector", {}, [H, H, B]),
                       ("random_cost", "RandomSelector", {"cost_b": 0.1, "cost_f": 0.3}, [B])]
+        elif args.only == "st_agg":     # the other aggregates / weights of the exp-normalised rows at full size (~5 min at P28K)
+            cases += [("st_exp_min_1200", "SpatialTemporalSelector", {"aggregate": "min"}, [1200]),
+                      ("st_exp_max_1200", "SpatialTemporalSelector", {"aggregate": "max"}, [1200]),
+                      ("st_exp_sum_l05_cost_1200", "SpatialTemporalSelector", {"lambda_t": 0.5, "cost_b": 0.1, "cost_f": 0.3}, [1200]),
+                      ("st_exp_max_rounds", "SpatialTemporalSelector", {"aggregate": "max"}, [300, 300])]
         elif args.only == "st":
             cases += [("st_exp_sum", "SpatialTemporalSelector", {}, [600]),
                       ("st_exp_sum_1200", "SpatialTemporalSelector", {}, [1200]),

@@ -147,6 +147,17 @@ def test_p28k_budgets_600_1200_4800_identical_to_reference(pools, tmp_path):
         assert res == case["selected_index"], cid
 
 
+def test_p28k_other_aggregates_and_weights_identical_to_reference(pools, tmp_path):
+    """Full size, the other exp-normalised variants (the one-warp kernel's `gval` table holds aggregate(s_far, tlut[d])):
+    min / max aggregates, lambda_t = 0.5 with other cost weights, chained rounds -- what the unmodified reference selects
+    (oracle/make_goldens.py --pool P28K --only st_agg)."""
+    golden = load_golden("P28K_st_agg.json")
+    pl = pools("P28K")
+    for cid, case in golden["cases"].items():
+        res, _ = _run_case_through_selectors(pl, case, tmp_path)
+        assert res == case["selected_index"], cid
+
+
 def test_fps_vector_matches_oracle(handle, pools):
     pl = pools("P2K")
     infos = pl["infos"]
