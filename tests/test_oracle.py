@@ -82,3 +82,14 @@ def test_restatement_reproduces_the_p28k_spatial_golden(pools):
     case = golden["cases"]["spatial_1200"]
     key, sel = R.select("spatial", pl["infos"], pl["logs"], {"0": []}, 1200, first_index_for(len(pl["infos"])))
     assert key == "1200" and sel == case["selected_index"][key]
+
+
+def test_restatement_reproduces_a_full_size_min_aggregate_golden(pools):
+    """28,130 frames, exp normalisation, aggregate="min", budget 1200 (oracle/make_goldens.py --pool P28K --only st_agg):
+    the streaming restatement against what the unmodified reference selected."""
+    golden = load_golden("P28K_st_agg.json")
+    pl = pools("P28K")
+    case = golden["cases"]["st_exp_min_1200"]
+    key, sel = R.select("spatial_temporal", pl["infos"], pl["logs"], {"0": []}, 1200, first_index_for(len(pl["infos"])),
+                        **case["kwargs"])
+    assert key == "1200" and sel == case["selected_index"][key]
